@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- MT-FJSP env-steps/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A "step" is one pass of the environment hot path over the whole env batch: random valid action
+(policy kernel) -> candidate-machine features (mfea1 kernel) -> fused transition + reward + reward
+scaling + observation + job mask (env kernel), i.e. everything the environment side of Run.py's rollout
+loop does per step.  Episodes wrap inside the timed region: every
+N = J*M steps the batch is reset (one more launch), as the reference's loop does.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|B|C]
+
+N > 1 is launched by the driver with torch.distributed.run; each rank owns its own env slice (weak
+scaling, no data-path collective; NCCL is used only for the barrier and the max-over-ranks time).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1..3]
+    "A": dict(name="J6M6E2 synthetic, 65536 envs/GPU, random-action rollouts", J=6, M=6, E=2, B=65536, seed=1002),
+    "B": dict(name="J10M10E3 synthetic, 16384 envs/GPU, env step + mask/feature build", J=10, M=10, E=3, B=16384, seed=1003),
+    "C": dict(name="J30M20E5 synthetic, 4096 envs/GPU", J=30, M=20, E=5, B=4096, seed=1004),
+}
+METRIC = "MT-FJSP env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_rate(wl, nthreads, target_seconds):
+    """Times the CPU restatement (oracle/) on a bounded sample of the same workload: whole random rollouts,
+    every step = mask + candidates + mfea1 + transition + reward + scaling + observation (oracle_rollout_random)."""
+    from oracle.mtfjsp_oracle import OracleEnv
+
+    ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
+    J, M, E = wl["J"], wl["M"], wl["E"]
+    N = J * M
+    probe_B = max(nthreads * 4, 64 if N <= 100 else 16)
+
+    def run(B, episodes):
+        d = ins.synthetic_instances(0, B, J, M, E, wl["seed"])
+        w = ins.random_weights(0, B, wl["seed"])
+        o = OracleEnv(B, J, M, E, left_shift=True, nthreads=nthreads)
+        o.load(d["t"], d["p"], d["transT"], d["edge"])
+        o.scaler_init()
+        o.reset(w)
+        o.rollout_random(N, seed=1)  # warm-up episode
+        t0 = time.perf_counter()
+        for ep in range(episodes):
+            o.reset(w)
+            o.scaler_reset()
+            o.rollout_random(N, seed=2 + ep)
+        return B * N * episodes / (time.perf_counter() - t0)
+
+    rate = run(probe_B, 1)
+    B = int(min(max(probe_B, rate * target_seconds / (N * 4)), 262144))
+    B = max(nthreads, (B // nthreads) * nthreads)
+    rate = run(B, 4)
+    return rate, "%d envs x 4 episodes x %d steps (%s), %d thread(s)" % (B, N, wl["name"].split(",")[0], nthreads)
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself is Python over
+    networkx and cannot travel to the GPU box; this times its C restatement (oracle/, kind 'port') with all
+    host threads on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.mtfjsp_oracle import max_threads
+
+    cores = max(1, min(max_threads(), os.cpu_count() or 1))
+    rates = []
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_port_rate(wl, cores, 1.0)
+    t0 = time.perf_counter()
+    sample = ""
+    for _ in range(max(1, min(args.steps, 5))):
+        r, sample = cpu_port_rate(wl, cores, 4.0)
+        rates.append(r)
+    rates.sort()
+    val = rates[len(rates) // 2]
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": wl["name"], "note": "CPU restatement of the reference env (oracle/, OpenMP over envs); "
+                       "the Python reference itself measured ~157 env-steps/s/core at survey time (BASELINE.md)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, wl):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("e2e-mappo-for-mt-fjsp_b200")
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    ins = pkg.instances
+    J, M, E, B = wl["J"], wl["M"], wl["E"], args.batch or wl["B"]
+    N = J * M
+    first = rank * B  # weak scaling: env i of the job lives on rank i // B
+    d = ins.synthetic_instances(first, B, J, M, E, wl["seed"])
+    w = torch.as_tensor(ins.random_weights(first, B, wl["seed"])).to(dev)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32, mask_mode=envm.MASK_ESA)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    env.reset(w)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = {"s": 0}
+
+    def one_step(seed=1234):
+        if state["s"] == N:  # episode finished for every env: next episode (Run.py:615-665)
+            env.reset(w)
+            env.scaler_reset()
+            state["s"] = 0
+        env.random_step(seed=seed, env_offset=first)
+        state["s"] += 1
+
+    for _ in range(max(W, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = env.launch_count - l0
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = B * world * K / (ms * 1e-3)
+
+    # ---- dominant kernel alone: fused step+obs launches replaying recorded actions (device resident) ----
+    env.reset(w); env.scaler_reset()
+    rec_op = torch.empty((N, B), dtype=torch.int32, device=dev)
+    rec_mc = torch.empty((N, B), dtype=torch.int32, device=dev)
+    for s in range(N):
+        env.random_step(seed=99, env_offset=first)
+        rec_op[s].copy_(env.op); rec_mc[s].copy_(env.mach)
+    assert int(env.done.sum().item()) == B and int(env.invalid.sum().item()) == 0
+    kms, klaunch = 0.0, 0
+    reps = max(1, min(4, K // N))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(N)]
+    for rep in range(reps + 1):
+        env.reset(w); env.scaler_reset()
+        for s in range(N):
+            evs[s][0].record()
+            env.step_obs(rec_op[s], rec_mc[s])
+            evs[s][1].record()
+        torch.cuda.synchronize()
+        if rep > 0:  # first replay is warm-up
+            kms += sum(a.elapsed_time(b) for a, b in evs)
+            klaunch += N
+    k_us = kms * 1e3 / klaunch
+    bytes_step = env.bytes_per_step()
+    peak, peak_src = measured_peak()
+    achieved = bytes_step * B / (k_us * 1e-6) / 1e9
+
+    # ---- e2e: host-buffer C-ABI call per step (pinned H2D actions, D2H step info + mask + candidates) ----
+    h_op = rec_op.cpu().pin_memory(); h_mc = rec_mc.cpu().pin_memory()
+    info6 = torch.empty((B, 6), dtype=torch.float64).pin_memory()
+    h_jm = torch.empty((B, J), dtype=torch.uint8).pin_memory()
+    h_cd = torch.empty((B, J), dtype=torch.int32).pin_memory()
+    Ke = min(K, 4 * N)
+
+    def e2e_steps(n):
+        s = 0
+        env.reset(w); env.scaler_reset()
+        for _ in range(n):
+            if s == N:
+                env.reset(w); env.scaler_reset(); s = 0
+            env.step_host(h_op[s], h_mc[s], info6, h_jm, h_cd)
+            s += 1
+
+    e2e_steps(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(Ke)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm.item())
+    e2e_val = B * world * Ke / e2e_s
+    assert float(info6[:, 1].sum()) in (0.0, float(B))
+    clocks = sampler.stop() if sampler else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r1, sample = cpu_port_rate(wl, 1, 8.0)
+        cpu = {"value": r1, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "envs_per_gpu": B, "jobs": J, "machines": M, "edges": E, "obs_dtype": "f32",
+                       "mask_mode": "ESA", "left_shift": True, "parallelism": "env-slices x%d (no data-path collective)" % world,
+                       "l2": "working set %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (B * (bytes_step + 2000) / 1e6),
+                       "launches_per_step": 3},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * (48 + 5 * J),
+                    "api": "mtfjsp_step_host (C ABI, pinned host buffers; observation tensors stay on the device)",
+                    "steps": Ke},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "env_kernel<STEP|OBS,float>", "kernel_us": k_us,
+                         "bytes_per_env_step": bytes_step, "peak_source": peak_src,
+                         "steps_per_s_kernel_only": B / (k_us * 1e-6)},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=360)
+    ap.add_argument("--warmup", type=int, default=36)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

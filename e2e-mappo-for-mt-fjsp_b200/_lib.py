@@ -1,0 +1,91 @@
+"""Loader (and in-tree builder) of the C-ABI shared library ``libmtfjsp_b200.so``.
+
+The product path fails loudly when the CUDA extension is missing or cannot be loaded: there is no CPU
+fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC_DIR = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libmtfjsp_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "mtfjsp.h")
+SOURCES = ["mtfjsp_env.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    mt = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(SRC_DIR, s) for s in os.listdir(SRC_DIR)] + [HEADER]
+    return any(os.path.getmtime(d) > mt for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree so it travels to the GPU box."""
+    if force or _stale():
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+              [os.path.join(SRC_DIR, s) for s in SOURCES]
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+_VP, _I, _U64, _D = C.c_void_p, C.c_int, C.c_uint64, C.c_double
+
+# every symbol include/mtfjsp.h declares: (argtypes, restype)
+SIGNATURES = {
+    "mtfjsp_create": ([C.POINTER(_VP), _I, _I, _I, _I, _I, _I], _I),
+    "mtfjsp_destroy": ([_VP], _I),
+    "mtfjsp_set_params": ([_VP, _D, _D, _D, _D, _D], _I),
+    "mtfjsp_load": ([_VP, _VP, _VP, _VP, _VP, _I, _VP], _I),
+    "mtfjsp_scaler_init": ([_VP, _VP], _I),
+    "mtfjsp_scaler_reset": ([_VP, _VP], _I),
+    "mtfjsp_reset": ([_VP, _VP, _VP], _I),
+    "mtfjsp_step": ([_VP] + [_VP] * 6 + [_VP], _I),
+    "mtfjsp_obs": ([_VP] + [_VP] * 6 + [_I, _I, _VP], _I),
+    "mtfjsp_step_obs": ([_VP] + [_VP] * 12 + [_I, _I, _VP], _I),
+    "mtfjsp_mfea1": ([_VP, _VP, _VP, _VP, _I, _VP], _I),
+    "mtfjsp_dense_adj": ([_VP, _VP, _I, _VP], _I),
+    "mtfjsp_costs": ([_VP, _VP, _VP], _I),
+    "mtfjsp_export_state": ([_VP] + [_VP] * 4 + [_VP], _I),
+    "mtfjsp_export_scaler": ([_VP] + [_VP] * 4 + [_VP], _I),
+    "mtfjsp_policy_random": ([_VP, _U64, _U64, _I, _VP, _VP, _VP], _I),
+    "mtfjsp_random_step": ([_VP, _U64, _U64] + [_VP] * 14 + [_I, _I, _VP], _I),
+    "mtfjsp_step_host": ([_VP] + [_VP] * 9 + [_I, _I, _VP], _I),
+    "mtfjsp_launch_count": ([_VP], C.c_int64),
+    "mtfjsp_bytes_per_step": ([_VP, _I], C.c_int64),
+    "mtfjsp_last_error": ([], C.c_char_p),
+    "mtfjsp_version": ([], C.c_char_p),
+}
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it is absent: build it with ``__graft_entry__.build()``."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "CUDA extension %s is missing; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in SIGNATURES.items():
+            fn = getattr(_lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = restype
+    return _lib
+
+
+class MTFJSPError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise MTFJSPError("%s failed (%d): %s" % (what, rc, lib().mtfjsp_last_error().decode()))

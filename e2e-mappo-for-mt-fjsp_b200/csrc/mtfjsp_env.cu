@@ -1,0 +1,1202 @@
+// mtfjsp_env.cu -- batched MT-FJSP disjunctive-graph environment for sm_100a (B200).
+//
+// One warp owns one environment instance.  Per launch a warp stages its instance's records from HBM
+// into shared memory with 128-bit coalesced loads, applies the (operation, machine) action, rebuilds
+// the reward and (optionally) the observation, and writes back only the words that changed.
+//
+// What this replaces in the reference (file:line, "SS" = graph-jsp-env/src/graph_jsp_env/
+// disjunctive_graph_jsp_env_singlestep.py):
+//   transition      SS:716-974, 1476-1809; trainer/DGenv_func.py:46-170
+//   reward          SS:1051-1171           reward scaling  algorithm/ppo_trick.py:54-122
+//   observation     SS:1920-2515           job mask        algorithm/ppo_algorithm.py:202-317
+//   machine feats   trainer/parallel_env.py:152-214
+//
+// Numerics: all schedule arithmetic is FP64 in the reference's operand order; this file must be
+// compiled with -fmad=false (no FMA contraction).  np.sum is restated as numpy's pairwise summation
+// (8 accumulators, 128-element leaves) so that energy totals are bit-identical.
+//
+// HBM layout (per handle, B environments; every record is 16-byte aligned):
+//   sd  [B][sd_stride] f64   dynamic doubles: st[N] ft[N] dur[N] psel[N] | mk_prev e_prev trans idle_prev |
+//                            macc[M][3] | w[3] | scaler R[4] mean[4] S[4] n
+//   si  [B][si_stride] i16   dynamic ints:    mach[N] pos[N] rpred[N] cnt[M] | removed_head fresh_co nsched
+//   xs  [B][xs_stride] f64   static doubles:  mind[N] minpt[N] tt[M][M]
+//   t,p [B][N][M]      f64   instance tables, touched only at (op, machine) and in the mfea1 kernel
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/mtfjsp.h"
+
+#define MAX_LEAVES 64
+#define MAX_PROG 128
+#define FULL 0xffffffffu
+
+namespace {
+
+struct Layout {
+    int B, J, M, N, E, left_shift;
+    int sd_stride, si_stride, xs_stride;
+    int o_st, o_ft, o_dur, o_psel, o_scal, o_macc, o_w, o_sc;  // sd offsets (doubles)
+    int o_mach, o_pos, o_rpred, o_cnt, o_misc;                 // si offsets (int16)
+    int o_mind, o_minpt, o_tt;                                 // xs offsets (doubles)
+    int sm_sd, sm_xs, sm_pt, sm_v, sm_leaf, sm_si, sm_off, sm_nxt, sm_tail;  // smem byte offsets per warp
+    int smem_per_warp, warps_per_block;
+};
+
+struct PwPlan {  // numpy pairwise-sum plan for N elements
+    int nleaves, nprog;
+    int leaf_off[MAX_LEAVES];
+    int leaf_len[MAX_LEAVES];
+    signed char prog[MAX_PROG];  // postfix: k >= 0 push leaf k, -1 add
+};
+
+struct Params {
+    Layout L;
+    PwPlan pw;
+    double* sd;
+    int16_t* si;
+    const double* xs;
+    const double* t;
+    const double* p;
+    const double* weights;  // reset only
+    double cfgw[3], divisor, gamma;
+    // step io
+    const int32_t* op;
+    const int32_t* mach;
+    double* reward5;
+    double* scaled4;
+    uint8_t* done;
+    uint8_t* invalid;
+    // obs io
+    void* tfea;
+    void* mfea;
+    float* adj_w;
+    int16_t* adj_src;
+    uint8_t* jmask;
+    int32_t* cand;
+    int mask_mode;
+    // always-written internal mask / candidate buffers (policy kernel, host step)
+    uint8_t* jm_fin;
+    uint8_t* jm_esa;
+    int32_t* cand_int;
+};
+
+enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4 };
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// adjacency value of an arc with weight w leaving op u (SS:2019, 2050-2064); 0 = arc vanishes
+__device__ __forceinline__ double adj_val(double w, bool u_assigned, double dur_u) {
+    long long wi = (long long)w;
+    if (wi == 0) return 0.0;
+    double nd = u_assigned ? dur_u : 1.0;
+    long long v = (long long)((double)wi - nd);
+    return (double)(v + 1);
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_row(OutT* dst, const double* f, int n);
+template <>
+__device__ __forceinline__ void store_row<float>(float* dst, const double* f, int n) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int k = 0; k < n / 4; k++)
+        d4[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
+}
+template <>
+__device__ __forceinline__ void store_row<double>(double* dst, const double* f, int n) {
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int k = 0; k < n / 2; k++) d2[k] = make_double2(f[2 * k], f[2 * k + 1]);
+}
+
+// numpy pairwise sum of a[0..N) following the host-built plan; every lane returns the result
+__device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf, int lane) {
+    const int grp = lane >> 3, k = lane & 7;
+    for (int L0 = 0; L0 < pw.nleaves; L0 += 4) {
+        int Lx = L0 + grp;
+        bool act = Lx < pw.nleaves;
+        int off = act ? pw.leaf_off[Lx] : 0, n = act ? pw.leaf_len[Lx] : 0;
+        double res = 0.0;
+        if (n < 8) {  // whole array shorter than 8 (only when N < 8): plain loop
+            if (k == 0)
+                for (int i = 0; i < n; i++) res += a[off + i];
+        } else {
+            int nb = n - (n & 7);
+            double r = a[off + k];
+            for (int i = 8 + k; i < nb; i += 8) r += a[off + i];
+            // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
+            r = r + __shfl_down_sync(FULL, r, 1, 8);
+            r = r + __shfl_down_sync(FULL, r, 2, 8);
+            r = r + __shfl_down_sync(FULL, r, 4, 8);
+            res = r;
+            if (k == 0)
+                for (int i = nb; i < n; i++) res += a[off + i];
+        }
+        if (act && k == 0) s_leaf[Lx] = res;
+    }
+    __syncwarp();
+    if (pw.nleaves == 1) return s_leaf[0];
+    // combine leaves with the recursion's shape (postfix program); stack lives above the leaves
+    double* stk = s_leaf + MAX_LEAVES;
+    int sp = 0;
+    double top = 0.0;
+    for (int i = 0; i < pw.nprog; i++) {
+        int c = pw.prog[i];
+        if (c >= 0) {
+            if (lane == 0) stk[sp] = s_leaf[c];
+            sp++;
+        } else {
+            __syncwarp();
+            double x = stk[sp - 2], y = stk[sp - 1];
+            __syncwarp();
+            top = x + y;
+            sp--;
+            if (lane == 0) stk[sp - 1] = top;
+        }
+        __syncwarp();
+    }
+    return top;
+}
+
+template <int MODE, typename OutT>
+__global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Layout& L = P.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * L.warps_per_block + warp;
+    if (b >= L.B) return;
+    const int N = L.N, M = L.M, J = L.J;
+    unsigned char* base = smem_raw + (size_t)warp * L.smem_per_warp;
+    double* s_sd = reinterpret_cast<double*>(base + L.sm_sd);
+    double* s_xs = reinterpret_cast<double*>(base + L.sm_xs);
+    double* s_pt = reinterpret_cast<double*>(base + L.sm_pt);  // idle terms, then est_pt
+    double* s_v = reinterpret_cast<double*>(base + L.sm_v);    // per-job ESA key
+    double* s_leaf = reinterpret_cast<double*>(base + L.sm_leaf);
+    int16_t* s_si = reinterpret_cast<int16_t*>(base + L.sm_si);
+    int* s_off = reinterpret_cast<int*>(base + L.sm_off);
+    int16_t* s_nxt = reinterpret_cast<int16_t*>(base + L.sm_nxt);
+    int16_t* s_tail = reinterpret_cast<int16_t*>(base + L.sm_tail);
+
+    double* g_sd = P.sd + (size_t)b * L.sd_stride;
+    int16_t* g_si = P.si + (size_t)b * L.si_stride;
+    const double* g_xs = P.xs + (size_t)b * L.xs_stride;
+
+    // ---- stage records (128-bit, coalesced) ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(g_sd);
+        uint4* dst = reinterpret_cast<uint4*>(s_sd);
+        for (int i = lane; i < L.sd_stride / 2; i += 32) dst[i] = src[i];
+        src = reinterpret_cast<const uint4*>(g_xs);
+        dst = reinterpret_cast<uint4*>(s_xs);
+        for (int i = lane; i < L.xs_stride / 2; i += 32) dst[i] = __ldg(src + i);
+        if (!(MODE & MODE_RESET)) {
+            src = reinterpret_cast<const uint4*>(g_si);
+            dst = reinterpret_cast<uint4*>(s_si);
+            for (int i = lane; i < L.si_stride / 8; i += 32) dst[i] = src[i];
+        }
+    }
+    double* s_st = s_sd + L.o_st;
+    double* s_ft = s_sd + L.o_ft;
+    double* s_dur = s_sd + L.o_dur;
+    double* s_psel = s_sd + L.o_psel;
+    double* s_scal = s_sd + L.o_scal;  // mk_prev, e_prev, trans, idle_prev
+    double* s_macc = s_sd + L.o_macc;
+    double* s_w = s_sd + L.o_w;
+    double* s_sc = s_sd + L.o_sc;  // R[4] mean[4] S[4] n
+    int16_t* s_mach = s_si + L.o_mach;
+    int16_t* s_pos = s_si + L.o_pos;
+    int16_t* s_rpred = s_si + L.o_rpred;
+    int16_t* s_cnt = s_si + L.o_cnt;
+    int16_t* s_misc = s_si + L.o_misc;  // removed_head, fresh_co, nsched
+    const double* s_mind = s_xs + L.o_mind;
+    const double* s_minpt = s_xs + L.o_minpt;
+    const double* s_tt = s_xs + L.o_tt;
+
+    if (MODE & MODE_RESET) {  // load_instance + reset, SS:397-714, 1183-1245
+        __syncwarp();
+        for (int i = lane; i < 4 * N; i += 32) s_sd[L.o_st + i] = 0.0;  // st ft dur psel are contiguous
+        for (int i = lane; i < 3 * M; i += 32) s_macc[i] = 0.0;
+        if (lane < 3) s_w[lane] = P.weights[(size_t)b * 3 + lane];
+        if (lane < 4) s_scal[lane] = 0.0;
+        for (int i = lane; i < N; i += 32) { s_mach[i] = -1; s_pos[i] = -1; s_rpred[i] = -1; }
+        for (int i = lane; i < M; i += 32) s_cnt[i] = 0;
+        if (lane == 0) { s_misc[0] = -1; s_misc[1] = -1; s_misc[2] = 0; }
+        for (int i = L.o_misc + 3 + lane; i < L.si_stride; i += 32) s_si[i] = 0;
+    }
+    __syncwarp();
+
+    int a = -1, m = -1;
+    bool valid = false, done = false;
+    double mkv = 0.0, env = 0.0;
+    double idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;  // step results kept in registers for the reward epilogue
+
+    if (MODE & MODE_STEP) {
+        a = P.op[b];
+        m = P.mach[b];
+        const int nsched0 = s_misc[2];
+        double d = 0.0, pa = 0.0;
+        valid = (a >= 0) && (a < N) && (m >= 0) && (m < M) && (nsched0 < N);
+        if (valid) valid = (s_mach[a] < 0) && (((a % M) == 0) || (s_mach[a - 1] >= 0));
+        if (valid) {
+            d = __ldg(P.t + ((size_t)b * N + a) * M + m);
+            pa = __ldg(P.p + ((size_t)b * N + a) * M + m);
+            valid = !(d < 0);
+        }
+        if (valid) {
+            const bool first = (a % M) == 0;
+            const int ja = a / M;
+            // job-arc refresh at step start (SS:1502): transient markers of the previous step expire
+            int rem_head = -1, fresh = -1;
+            const double arr_a = first ? 0.0 : s_ft[a - 1] + s_tt[s_mach[a - 1] * M + m];  // DGenv_func.py:46-66
+            const int len = s_cnt[m];
+            const double ttmm = s_tt[m * M + m];
+            double st = arr_a;
+            int where = 0, prev = -1, next = -1;
+            if (len > 0) {
+                // one pass over the ops of machine m: arrival of each, first feasible slot, route tail
+                const double lbft = arr_a + d;
+                unsigned best = 0xffffffffu;
+                int lastop = -1;
+                for (int v0 = 0; v0 < N; v0 += 32) {
+                    int v = v0 + lane;
+                    unsigned key = 0xffffffffu;
+                    if (v < N && s_mach[v] == m) {
+                        int k = s_pos[v], rp = s_rpred[v];
+                        if (k == len - 1) lastop = v;
+                        if (L.left_shift) {
+                            bool vfirst = (v % M) == 0;
+                            double nst = vfirst ? 0.0 : s_ft[v - 1] + s_tt[s_mach[v - 1] * M + m];
+                            bool ok;
+                            if (k == 0) {
+                                ok = (lbft <= nst);  // SS:1548 (route head has no machine in-arc)
+                            } else {
+                                double val = s_ft[rp] + ((rp / M == v / M) ? ttmm : 0.0);
+                                nst = fmax(nst, val);
+                                ok = !(lbft > nst) && !((nst - s_ft[rp]) < d);  // SS:1597-1601
+                            }
+                            if (ok) key = ((unsigned)k << 16) | (unsigned)v;
+                        }
+                    }
+                    best = min(best, __reduce_min_sync(FULL, key));
+                }
+                lastop = __reduce_max_sync(FULL, lastop);
+                if (best != 0xffffffffu) {
+                    where = (int)(best >> 16);
+                    next = (int)(best & 0xffffu);
+                    if (where > 0) {
+                        prev = s_rpred[next];
+                        double y = s_ft[prev] + ((prev / M == ja) ? ttmm : 0.0);  // SS:1619
+                        st = (y > arr_a) ? y : arr_a;
+                        if (next == prev + 1 && (next % M) != 0) rem_head = next;  // SS:1660
+                    }
+                } else {  // _append_at_the_end, SS:1689-1775
+                    where = len;
+                    prev = lastop;
+                    double y = s_ft[prev] + ((prev / M == ja) ? ttmm : 0.0);
+                    st = (y > arr_a) ? y : arr_a;
+                }
+                if (prev >= 0 && prev == a - 1 && !first) fresh = a;
+            }
+            __syncwarp();
+            // ---- apply: shift route positions behind the slot, link the op in ----
+            for (int v = lane; v < N; v += 32)
+                if (s_mach[v] == m && s_pos[v] >= where) {
+                    int16_t np_ = (int16_t)(s_pos[v] + 1);
+                    s_pos[v] = np_;
+                    g_si[L.o_pos + v] = np_;
+                }
+            __syncwarp();
+            if (lane == 0) {
+                s_mach[a] = (int16_t)m; s_pos[a] = (int16_t)where; s_rpred[a] = (int16_t)prev;
+                if (next >= 0) s_rpred[next] = (int16_t)a;
+                s_cnt[m] = (int16_t)(len + 1);
+                s_misc[0] = (int16_t)rem_head; s_misc[1] = (int16_t)fresh; s_misc[2] = (int16_t)(nsched0 + 1);
+                s_st[a] = st; s_ft[a] = st + d; s_dur[a] = d; s_psel[a] = pa;
+                g_si[L.o_mach + a] = (int16_t)m; g_si[L.o_pos + a] = (int16_t)where; g_si[L.o_rpred + a] = (int16_t)prev;
+                if (next >= 0) g_si[L.o_rpred + next] = (int16_t)a;
+                g_si[L.o_cnt + m] = (int16_t)(len + 1);
+                g_si[L.o_misc + 0] = (int16_t)rem_head; g_si[L.o_misc + 1] = (int16_t)fresh;
+                g_si[L.o_misc + 2] = (int16_t)(nsched0 + 1);
+                g_sd[L.o_st + a] = st; g_sd[L.o_ft + a] = st + d; g_sd[L.o_dur + a] = d; g_sd[L.o_psel + a] = pa;
+            }
+            __syncwarp();
+            const int nsched = nsched0 + 1;
+            done = (nsched == N);
+            // ---- idle time: sequential sum in (machine, route) order, DGenv_func.py:144-170 ----
+            {
+                int carry = 0;
+                for (int m0 = 0; m0 < M; m0 += 32) {
+                    int mm = m0 + lane;
+                    int c = (mm < M) ? (int)s_cnt[mm] : 0;
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int n_ = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += n_;
+                    }
+                    if (mm < M) s_off[mm] = carry + inc - c;
+                    carry += __shfl_sync(FULL, inc, 31);
+                }
+                __syncwarp();
+                for (int v = lane; v < N; v += 32) {
+                    int mv = s_mach[v];
+                    if (mv >= 0) {
+                        int rp = s_rpred[v];
+                        double term = (rp < 0) ? (s_st[v] - 0.0) : (s_st[v] - s_ft[rp]);
+                        s_pt[s_off[mv] + s_pos[v]] = term * 1.0;
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll 4
+            for (int g = 0; g < nsched; g++) idle = idle + s_pt[g];
+            __syncwarp();
+            nt = first ? 0.0 : s_tt[s_mach[a - 1] * M + m];  // SS:872-877
+            trans = s_scal[2] + nt;
+            ec = pa * d;
+        }
+        __syncwarp();
+    }
+
+    // ---- per-job walk: scheduled prefix, estimator chain (SS:1964-1995), ESA key (ppo_algorithm.py:280) ----
+    for (int j = lane; j < J; j += 32) {
+        const int jb = j * M;
+        double cur = 0.0, rm = 0.0;
+        int nx = 0;
+        while (nx < M && s_mach[jb + nx] >= 0) {
+            cur = s_ft[jb + nx];
+            rm = fmax(rm, cur);
+            nx++;
+        }
+        for (int c = nx; c < M; c++) {
+            s_st[jb + c] = (c == 0) ? 0.0 : cur;
+            cur = ((c == 0) ? 0.0 : cur) + s_mind[jb + c];
+            s_ft[jb + c] = cur;
+        }
+        s_nxt[j] = (int16_t)nx;
+        s_v[j] = (nx == M) ? INFINITY : rm;
+    }
+    __syncwarp();
+    // est_pt, makespan estimate, energy estimate (SS:894-896)
+    {
+        double mx = -INFINITY;
+        for (int v = lane; v < N; v += 32) {
+            s_pt[v] = (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_minpt[v];
+            mx = fmax(mx, s_ft[v]);
+        }
+        __syncwarp();
+        if (MODE & (MODE_STEP | MODE_RESET)) {
+            mkv = warp_max(mx);
+            env = pairwise_sum(s_pt, P.pw, s_leaf, lane);
+        }
+    }
+
+    if (MODE & MODE_RESET) {
+        if (lane == 0) { s_scal[0] = mkv; s_scal[1] = env; s_scal[2] = 0.0; s_scal[3] = 0.0; }  // SS:697-705
+        __syncwarp();
+        // write back the env part of sd (everything except the scaler block) and the whole si record;
+        // st/ft in smem now hold estimates for unscheduled ops, so zeros are written explicitly
+        for (int i = lane; i < 4 * N; i += 32) g_sd[L.o_st + i] = 0.0;
+        for (int i = L.o_scal + lane; i < L.o_sc; i += 32) g_sd[i] = s_sd[i];
+        uint4* dst = reinterpret_cast<uint4*>(g_si);
+        const uint4* src = reinterpret_cast<const uint4*>(s_si);
+        for (int i = lane; i < L.si_stride / 8; i += 32) dst[i] = src[i];
+    }
+
+    if ((MODE & MODE_STEP)) {
+        if (valid) {
+            const double mk_prev = s_scal[0], e_prev = s_scal[1], trans_prev = s_scal[2], idle_prev = s_scal[3];
+            // wrk_reward_function, SS:1066-1132
+            const double r_t = 1.0 * mk_prev - mkv;
+            double r_pt = 1.0 * e_prev - env;
+            r_pt = r_pt / (double)N;
+            const double r_tt = 1.0 * trans_prev - trans;
+            const double r_idle = 1.0 * idle_prev - idle;
+            const double total = P.cfgw[0] * r_t + P.cfgw[1] * (r_pt + 1.0 * r_idle) + P.cfgw[2] * r_tt * 1.0;
+            __syncwarp();
+            if (lane == 0) {
+                // machine accumulators, SS:2323-2338
+                s_macc[m * 3 + 0] += ec / (double)N;
+                s_macc[m * 3 + 1] += nt;
+                s_macc[m * 3 + 2] += idle - idle_prev;
+                s_scal[0] = mkv; s_scal[1] = env; s_scal[2] = trans; s_scal[3] = idle;  // SS:932-936
+            }
+            // reward scaling, ppo_trick.py:73-88,115-119 (lanes 0..3 own one component each)
+            double scaled = 0.0;
+            if (lane < 4) {
+                const double x = lane == 0 ? r_t : lane == 1 ? r_idle : lane == 2 ? r_pt : r_tt;  // parallel_env.py:255
+                double R = P.gamma * s_sc[lane] + x;
+                double nn = s_sc[12] + 1.0;
+                double mean, S = s_sc[8 + lane], sd_;
+                if (nn == 1.0) {
+                    mean = R;
+                    sd_ = fabs(R);
+                } else {
+                    double old = s_sc[4 + lane];
+                    mean = old + (R - old) / nn;
+                    S = S + (R - old) * (R - mean);
+                    sd_ = sqrt(S / nn);
+                }
+                scaled = x / (sd_ + 1e-8);
+                __syncwarp(0xf);
+                s_sc[lane] = R; s_sc[4 + lane] = mean; s_sc[8 + lane] = S;
+                if (lane == 0) s_sc[12] = nn;
+                if (P.scaled4) P.scaled4[(size_t)b * 4 + lane] = scaled;
+            }
+            __syncwarp();
+            // selective write-back of the doubles that changed: scalars, macc[m], scaler
+            if (lane < 20) {
+                int idx = lane < 4 ? L.o_scal + lane : lane < 7 ? L.o_macc + m * 3 + (lane - 4) : L.o_sc + (lane - 7);
+                g_sd[idx] = s_sd[idx];
+            }
+            if (lane == 0) {
+                if (P.reward5) {
+                    double* r5 = P.reward5 + (size_t)b * 5;
+                    r5[0] = total / P.divisor; r5[1] = r_t; r5[2] = r_idle; r5[3] = r_pt; r5[4] = r_tt;
+                }
+                if (P.done) P.done[b] = done ? 1 : 0;
+                if (P.invalid) P.invalid[b] = 0;
+            }
+        } else {
+            if (lane < 5 && P.reward5) P.reward5[(size_t)b * 5 + lane] = 0.0;
+            if (lane < 4 && P.scaled4) P.scaled4[(size_t)b * 4 + lane] = 0.0;
+            if (lane == 0) {
+                if (P.done) P.done[b] = (s_misc[2] == N) ? 1 : 0;
+                if (P.invalid) P.invalid[b] = 1;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- job mask + candidates (always refreshed into the handle's internal buffers) ----
+    {
+        bool first_missing = false, unfinished = false;
+        for (int j0 = 0; j0 < J; j0 += 32) {
+            int j = j0 + lane;
+            int nx = (j < J) ? (int)s_nxt[j] : M;
+            first_missing |= __any_sync(FULL, j < J && nx == 0);
+            unfinished |= __any_sync(FULL, j < J && nx < M);
+        }
+        double mn = INFINITY;
+        for (int j = lane; j < J; j += 32) mn = fmin(mn, s_v[j]);
+        mn = warp_min(mn);
+        for (int j = lane; j < J; j += 32) {
+            int nx = s_nxt[j];
+            uint8_t fin = (nx == M) ? 1 : 0;
+            uint8_t esa = fin;
+            if (first_missing) esa = (nx >= 1) ? 1 : 0;
+            else if (unfinished) esa = (s_v[j] != mn) ? 1 : 0;
+            int c = j * M + (nx < M - 1 ? nx : M - 1);
+            P.jm_fin[(size_t)b * J + j] = fin;
+            P.jm_esa[(size_t)b * J + j] = esa;
+            P.cand_int[(size_t)b * J + j] = c;
+            if (MODE & MODE_OBS) {
+                if (P.jmask) P.jmask[(size_t)b * J + j] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+                if (P.cand) P.cand[(size_t)b * J + j] = c;
+            }
+        }
+    }
+
+    if (MODE & MODE_OBS) {
+        const int rem_head = s_misc[0], fresh = s_misc[1];
+        OutT* tf = reinterpret_cast<OutT*>(P.tfea);
+        const double w0 = s_w[0], w1 = s_w[1], w2 = s_w[2];
+        for (int v = lane; v < N; v += 32) {
+            const int mv = s_mach[v];
+            const bool sch = mv >= 0, vfirst = (v % M) == 0;
+            const int rp = sch ? (int)s_rpred[v] : -1;
+            const bool has_job = !vfirst && v != rem_head;
+            const bool co = has_job && rp == v - 1;
+            const bool has_m = rp >= 0 && !co;
+            if (sch && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
+            if (tf) {  // SS:2246-2277
+                double f[12];
+                f[0] = s_st[v]; f[1] = s_ft[v]; f[2] = s_pt[v];
+                f[3] = sch ? 1.0 : 0.0;
+                f[4] = (double)((vfirst ? 1 : 0) + (has_job ? 1 : 0) + (has_m ? 1 : 0));
+                f[5] = sch ? (double)(mv + 1) : 0.0;
+                f[6] = sch ? s_dur[v] : 0.0;
+                f[7] = sch ? s_psel[v] : 0.0;
+                f[8] = (double)(v / M + 1);
+                f[9] = w0; f[10] = w1; f[11] = w2;
+                store_row<OutT>(tf + ((size_t)b * N + v) * 12, f, 12);
+            }
+            if (P.adj_w) {  // SS:2019-2073 in compact ELL form
+                double wj = 0.0, wm = 0.0;
+                int src = -1;
+                if (has_job) {
+                    const int u = v - 1, mu = s_mach[u];
+                    double w;
+                    if (fresh == v) w = s_dur[u] + s_tt[mu * M + mv] + (s_st[v] - s_ft[u]);  // SS:1764 / 1644
+                    else if (s_dur[u] != 0.0) w = s_dur[u] + ((mu >= 0 && sch) ? s_tt[mu * M + mv] : 0.0);  // SS:1392-1422
+                    else w = 1.0;                                                                              // SS:625,642
+                    wj = adj_val(w, mu >= 0, s_dur[u]);
+                }
+                if (has_m) {
+                    double w = s_dur[rp] + ((rp / M == v / M) ? s_tt[mv * M + mv] : 0.0) + (s_st[v] - s_ft[rp]);
+                    wm = adj_val(w, true, s_dur[rp]);
+                    if (wm != 0.0) src = rp;
+                }
+                reinterpret_cast<float2*>(P.adj_w)[(size_t)b * N + v] = make_float2((float)wj, (float)wm);
+                P.adj_src[(size_t)b * N + v] = (int16_t)src;
+            }
+        }
+        __syncwarp();
+        if (P.mfea) {  // SS:2315-2354
+            OutT* mf = reinterpret_cast<OutT*>(P.mfea);
+            for (int mm = lane; mm < M; mm += 32) {
+                double f[8];
+                const int c = s_cnt[mm];
+                f[0] = c > 0 ? s_ft[s_tail[mm]] : 0.0;
+                f[1] = s_macc[mm * 3 + 0]; f[2] = s_macc[mm * 3 + 1]; f[3] = s_macc[mm * 3 + 2];
+                f[4] = (double)c;
+                f[5] = w0; f[6] = w1; f[7] = w2;
+                store_row<OutT>(mf + ((size_t)b * M + mm) * 8, f, 8);
+            }
+        }
+    }
+}
+
+// ---- static tables: min feasible duration / energy per op, edge id per machine ----
+__global__ void load_kernel(Layout L, const double* __restrict__ t, const double* __restrict__ p,
+                            const double* __restrict__ tt, const int32_t* __restrict__ edge, int W, double* xs,
+                            int8_t* edge_id) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)L.B * L.N;
+    if (gid < total) {
+        size_t b = gid / L.N;
+        int i = (int)(gid % L.N);
+        const double* tr = t + gid * L.M;
+        const double* pr = p + gid * L.M;
+        double mn = INFINITY, mnpt = INFINITY;
+        for (int m = 0; m < L.M; m++) {  // SS:1932-1950
+            double tv = tr[m], ptv = tv * fabs(pr[m]);
+            if (!(tv < 0) && tv < mn) mn = tv;
+            if (!(ptv < 0) && ptv < mnpt) mnpt = ptv;
+        }
+        xs[b * L.xs_stride + L.o_mind + i] = mn;
+        xs[b * L.xs_stride + L.o_minpt + i] = mnpt;
+    }
+    size_t ntt = (size_t)L.B * L.M * L.M;
+    if (gid < ntt) {
+        size_t b = gid / (L.M * L.M);
+        int r = (int)(gid % (L.M * L.M));
+        xs[b * L.xs_stride + L.o_tt + r] = tt[gid];
+    }
+    if (gid < (size_t)L.B * L.M) {
+        size_t b = gid / L.M;
+        int m = (int)(gid % L.M);
+        int id = 0;
+        for (int g = 0; g < L.E && id == 0; g++)
+            for (int k = 0; k < W; k++)
+                if (edge[(b * L.E + g) * W + k] == m) { id = g + 1; break; }
+        edge_id[gid] = (int8_t)id;
+    }
+}
+
+__global__ void scaler_kernel(Layout L, double* sd, int full) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int per = full ? 13 : 4;
+    if (gid < (size_t)L.B * per) {
+        size_t b = gid / per;
+        int k = (int)(gid % per);
+        sd[b * L.sd_stride + L.o_sc + k] = 0.0;
+    }
+}
+
+// numpy pairwise sum of up to M (<= 64) values held in registers/local array
+__device__ __forceinline__ double np_sum_small(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r += a[i];
+        return r;
+    }
+    double r[8];
+    for (int i = 0; i < 8; i++) r[i] = a[i];
+    int nb = n - (n & 7), i;
+    for (i = 8; i < nb; i += 8)
+        for (int k = 0; k < 8; k++) r[k] += a[i + k];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+// cal_cur_task_machine_feature, trainer/parallel_env.py:152-214.  One thread per env.
+template <typename OutT>
+__global__ void mfea1_kernel(Layout L, const double* __restrict__ t, const double* __restrict__ p,
+                             const double* __restrict__ xs, const int16_t* __restrict__ si,
+                             const int8_t* __restrict__ edge_id, const int32_t* __restrict__ op, OutT* out,
+                             uint8_t* mmask) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.B) return;
+    const int M = L.M, N = L.N;
+    int a = op[b];
+    if (a < 0 || a >= N) {
+        for (int m = 0; m < M; m++) {
+            for (int k = 0; k < 6; k++) out[((size_t)b * M + m) * 6 + k] = (OutT)0;
+            if (mmask) mmask[(size_t)b * M + m] = 1;
+        }
+        return;
+    }
+    const double* tr = t + ((size_t)b * N + a) * M;
+    const double* pr = p + ((size_t)b * N + a) * M;
+    double tv[64], ptv[64], pv[64];
+    int nt = 0, npt = 0, npp = 0;
+    for (int m = 0; m < M; m++) {
+        double tm = tr[m], pm = pr[m], ptm = tm * fabs(pm);
+        if (tm > 0) tv[nt++] = tm;
+        if (ptm > 0) ptv[npt++] = ptm;
+        if (pm > 0) pv[npp++] = pm;
+    }
+    double mean_t = np_sum_small(tv, nt) / (double)nt;
+    double mean_pt = np_sum_small(ptv, npt) / (double)npt;
+    double mean_p = np_sum_small(pv, npp) / (double)npp;
+    int pm_row = M - 1;  // int(tfea[a-1][5]) - 1 wraps to the last row while the predecessor is unscheduled
+    if (a % M != 0) {
+        int mp = si[(size_t)b * L.si_stride + L.o_mach + a - 1];
+        if (mp >= 0) pm_row = mp;
+    }
+    const double* ttrow = xs + (size_t)b * L.xs_stride + L.o_tt + pm_row * M;
+    for (int m = 0; m < M; m++) {
+        double tm = tr[m], pm = pr[m], ptm = tm * fabs(pm);
+        int infeasible = !(tm >= 0);
+        OutT* f = out + ((size_t)b * M + m) * 6;
+        f[0] = (OutT)(tm > 0 ? tm : mean_t);
+        f[1] = (OutT)(ptm > 0 ? ptm : mean_pt);
+        f[2] = (OutT)((a % M == 0) ? 0.0 : ttrow[m]);
+        f[3] = (OutT)(1 - infeasible);
+        f[4] = (OutT)(pm > 0 ? pm : mean_p);
+        f[5] = (OutT)edge_id[(size_t)b * M + m];
+        if (mmask) mmask[(size_t)b * M + m] = (uint8_t)infeasible;
+    }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ uint32_t rand_u32(uint64_t seed, uint64_t env, uint64_t step, uint64_t stream) {
+    uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL + (stream << 56)));
+    return (uint32_t)(x >> 32);
+}
+
+// uniform random valid action from the current masks; one thread per env
+__global__ void policy_kernel(Layout L, const double* __restrict__ t, const int16_t* __restrict__ si,
+                              const uint8_t* __restrict__ jm, const int32_t* __restrict__ cand, uint64_t seed,
+                              uint64_t env_offset, int32_t* op, int32_t* mach) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.B) return;
+    const int J = L.J, M = L.M;
+    const uint8_t* mk = jm + (size_t)b * J;
+    int n = 0;
+    for (int j = 0; j < J; j++) n += !mk[j];
+    if (n == 0) { op[b] = -1; mach[b] = -1; return; }
+    uint64_t step = (uint64_t)si[(size_t)b * L.si_stride + L.o_misc + 2];
+    int k = (int)(((uint64_t)rand_u32(seed, env_offset + b, step, 0) * (uint64_t)n) >> 32);
+    int a = -1;
+    for (int j = 0; j < J; j++)
+        if (!mk[j]) {
+            if (k == 0) { a = cand[(size_t)b * J + j]; break; }
+            k--;
+        }
+    const double* tr = t + ((size_t)b * L.N + a) * M;
+    int nf = 0;
+    for (int m = 0; m < M; m++) nf += (tr[m] >= 0);
+    int km = (int)(((uint64_t)rand_u32(seed, env_offset + b, step, 1) * (uint64_t)nf) >> 32);
+    int mm = -1;
+    for (int m = 0; m < M; m++)
+        if (tr[m] >= 0) {
+            if (km == 0) { mm = m; break; }
+            km--;
+        }
+    op[b] = a;
+    mach[b] = mm;
+}
+
+template <typename OutT>
+__global__ void dense_adj_kernel(Layout L, const float* __restrict__ adj_w, const int16_t* __restrict__ adj_src,
+                                 OutT* adj) {
+    // one block per env row-chunk: zero-fill then scatter (<= 3 entries per row)
+    size_t b = blockIdx.x;
+    const int N = L.N;
+    OutT* A = adj + b * (size_t)N * N;
+    for (size_t i = threadIdx.x; i < (size_t)N * N; i += blockDim.x) A[i] = (OutT)0;
+    __syncthreads();
+    for (int v = threadIdx.x; v < N; v += blockDim.x) {
+        A[(size_t)v * N + v] = (OutT)1;
+        float wj = adj_w[(b * N + v) * 2], wm = adj_w[(b * N + v) * 2 + 1];
+        int src = adj_src[b * N + v];
+        if (wj != 0.f) A[(size_t)v * N + v - 1] = (OutT)wj;
+        if (src >= 0) A[(size_t)v * N + src] = (OutT)wm;
+    }
+}
+
+__global__ void export_kernel(Layout L, const double* __restrict__ sd, const int16_t* __restrict__ si, int32_t* mach,
+                              double* st, double* ft, int32_t* routes) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)L.B * L.N) return;
+    size_t b = gid / L.N;
+    int i = (int)(gid % L.N);
+    int mv = si[b * L.si_stride + L.o_mach + i];
+    if (mach) mach[gid] = mv;
+    if (st) st[gid] = mv >= 0 ? sd[b * L.sd_stride + L.o_st + i] : 0.0;
+    if (ft) ft[gid] = mv >= 0 ? sd[b * L.sd_stride + L.o_ft + i] : 0.0;
+    if (routes && mv >= 0) routes[(b * L.M + mv) * L.N + si[b * L.si_stride + L.o_pos + i]] = i;
+}
+
+__global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) p[gid] = v;
+}
+
+__global__ void costs_kernel(Layout L, const double* __restrict__ sd, double* cost4) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= (size_t)L.B) return;
+    const double* s = sd + b * L.sd_stride + L.o_scal;
+    cost4[b * 4 + 0] = s[0];
+    cost4[b * 4 + 1] = s[1] / (double)L.N;
+    cost4[b * 4 + 2] = s[2];
+    cost4[b * 4 + 3] = s[3];
+}
+
+__global__ void export_scaler_kernel(Layout L, const double* __restrict__ sd, double* R, double* mean, double* S,
+                                     int64_t* n) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= (size_t)L.B) return;
+    const double* s = sd + b * L.sd_stride + L.o_sc;
+    for (int k = 0; k < 4; k++) { R[b * 4 + k] = s[k]; mean[b * 4 + k] = s[4 + k]; S[b * 4 + k] = s[8 + k]; }
+    n[b] = (int64_t)s[12];
+}
+
+// info6 = (r, done, mk_s, idle_s, pt_s, tt_s), trainer/parallel_env.py:260
+__global__ void info6_kernel(int B, const double* __restrict__ r5, const double* __restrict__ s4,
+                             const uint8_t* __restrict__ done, double* info6) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    info6[(size_t)b * 6 + 0] = r5[(size_t)b * 5];
+    info6[(size_t)b * 6 + 1] = (double)done[b];
+    for (int k = 0; k < 4; k++) info6[(size_t)b * 6 + 2 + k] = s4[(size_t)b * 4 + k];
+}
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* msg, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess) snprintf(g_err, sizeof g_err, "%s: %s", msg, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+
+int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+void build_plan_rec(int off, int n, PwPlan& pw) {
+    if (n <= 128) {
+        pw.leaf_off[pw.nleaves] = off;
+        pw.leaf_len[pw.nleaves] = n;
+        pw.prog[pw.nprog++] = (signed char)pw.nleaves;
+        pw.nleaves++;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        build_plan_rec(off, n2, pw);
+        build_plan_rec(off + n2, n - n2, pw);
+        pw.prog[pw.nprog++] = -1;
+    }
+}
+
+}  // namespace
+
+struct mtfjsp_env {
+    Layout L;
+    PwPlan pw;
+    int device;
+    double cfgw[3], divisor, gamma;
+    double *sd, *xs, *t, *p;
+    int16_t* si;
+    int8_t* edge_id;
+    uint8_t *jm_fin, *jm_esa;
+    int32_t* cand;
+    // scratch for the host-step / random-step paths
+    int32_t *a_op, *a_mach;
+    double *r5, *s4, *info6;
+    uint8_t *dn, *inv;
+    float* tmp_adj_w;
+    int16_t* tmp_adj_src;
+    bool loaded, reset_done;
+    int64_t launches;
+};
+
+#define CK(call, msg)                                            \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return fail(MTFJSP_E_CUDA, msg, e_); \
+    } while (0)
+
+static Params make_params(mtfjsp_env* h) {
+    Params P;
+    memset(&P, 0, sizeof P);
+    P.L = h->L;
+    P.pw = h->pw;
+    P.sd = h->sd; P.si = h->si; P.xs = h->xs; P.t = h->t; P.p = h->p;
+    P.cfgw[0] = h->cfgw[0]; P.cfgw[1] = h->cfgw[1]; P.cfgw[2] = h->cfgw[2];
+    P.divisor = h->divisor; P.gamma = h->gamma;
+    P.jm_fin = h->jm_fin; P.jm_esa = h->jm_esa; P.cand_int = h->cand;
+    return P;
+}
+
+template <int MODE, typename OutT>
+static int launch_env(mtfjsp_env* h, const Params& P, cudaStream_t s) {
+    const Layout& L = h->L;
+    size_t smem = (size_t)L.smem_per_warp * L.warps_per_block;
+    static thread_local int configured_dev = -1;
+    static thread_local size_t configured_smem = 0;
+    if (configured_dev != h->device || configured_smem < smem) {
+        CK(cudaFuncSetAttribute(env_kernel<MODE, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+           "cudaFuncSetAttribute");
+        configured_dev = h->device;
+        configured_smem = smem;
+    }
+    int blocks = (L.B + L.warps_per_block - 1) / L.warps_per_block;
+    env_kernel<MODE, OutT><<<blocks, L.warps_per_block * 32, smem, s>>>(P);
+    h->launches++;
+    CK(cudaGetLastError(), "env_kernel launch");
+    return MTFJSP_OK;
+}
+
+extern "C" {
+
+const char* mtfjsp_last_error(void) { return g_err; }
+const char* mtfjsp_version(void) { return "mtfjsp-b200 0.1 (sm_100a)"; }
+
+int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, int device) {
+    if (!out) return fail(MTFJSP_E_ARG, "null handle pointer");
+    *out = nullptr;
+    if (B < 1 || J < 1 || M < 2 || M > 64 || E < 1 || (long long)J * M > 4096)
+        return fail(MTFJSP_E_ARG, "size out of range (need B>=1, J>=1, 2<=M<=64, J*M<=4096, E>=1)");
+    CK(cudaSetDevice(device), "cudaSetDevice");
+    mtfjsp_env* h = new (std::nothrow) mtfjsp_env();
+    if (!h) return fail(MTFJSP_E_ARG, "out of host memory");
+    memset(h, 0, sizeof *h);
+    Layout& L = h->L;
+    const int N = J * M;
+    L.B = B; L.J = J; L.M = M; L.N = N; L.E = E; L.left_shift = left_shift ? 1 : 0;
+    L.o_st = 0; L.o_ft = N; L.o_dur = 2 * N; L.o_psel = 3 * N; L.o_scal = 4 * N; L.o_macc = 4 * N + 4;
+    L.o_w = L.o_macc + 3 * M; L.o_sc = L.o_w + 3;
+    L.sd_stride = align_up(L.o_sc + 13, 2);
+    L.o_mach = 0; L.o_pos = N; L.o_rpred = 2 * N; L.o_cnt = 3 * N; L.o_misc = 3 * N + M;
+    L.si_stride = align_up(L.o_misc + 3, 8);
+    L.o_mind = 0; L.o_minpt = N; L.o_tt = 2 * N;
+    L.xs_stride = align_up(2 * N + M * M, 2);
+    int off = 0;
+    L.sm_sd = off; off += L.sd_stride * 8;
+    L.sm_xs = off; off += L.xs_stride * 8;
+    L.sm_pt = off; off += align_up(N, 2) * 8;
+    L.sm_v = off; off += align_up(J, 2) * 8;
+    L.sm_leaf = off; off += (MAX_LEAVES + 32) * 8;
+    L.sm_si = off; off += L.si_stride * 2;
+    L.sm_off = off; off += align_up(M, 4) * 4;
+    L.sm_nxt = off; off += align_up(J, 8) * 2;
+    L.sm_tail = off; off += align_up(M, 8) * 2;
+    L.smem_per_warp = align_up(off, 16);
+    int wpb = 8;
+    while (wpb > 1 && (size_t)wpb * L.smem_per_warp > 200 * 1024) wpb >>= 1;
+    if ((size_t)wpb * L.smem_per_warp > 227 * 1024) { delete h; return fail(MTFJSP_E_ARG, "instance too large for shared memory"); }
+    L.warps_per_block = wpb;
+    h->pw.nleaves = 0; h->pw.nprog = 0;
+    build_plan_rec(0, N, h->pw);
+    h->device = device;
+    h->cfgw[0] = 0.4; h->cfgw[1] = 0.4; h->cfgw[2] = 0.2; h->divisor = 1.0; h->gamma = 0.99;
+    size_t Bs = (size_t)B;
+#define ALLOC(ptr, bytes)                                                      \
+    do {                                                                       \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                  \
+        if (e_ != cudaSuccess) { mtfjsp_destroy(h); return fail(MTFJSP_E_CUDA, "cudaMalloc", e_); } \
+        cudaMemset((ptr), 0, (bytes));                                         \
+    } while (0)
+    ALLOC(h->sd, Bs * L.sd_stride * 8);
+    ALLOC(h->si, Bs * L.si_stride * 2);
+    ALLOC(h->xs, Bs * L.xs_stride * 8);
+    ALLOC(h->t, Bs * N * M * 8);
+    ALLOC(h->p, Bs * N * M * 8);
+    ALLOC(h->edge_id, Bs * M);
+    ALLOC(h->jm_fin, Bs * J);
+    ALLOC(h->jm_esa, Bs * J);
+    ALLOC(h->cand, Bs * J * 4);
+    ALLOC(h->a_op, Bs * 4);
+    ALLOC(h->a_mach, Bs * 4);
+    ALLOC(h->r5, Bs * 5 * 8);
+    ALLOC(h->s4, Bs * 4 * 8);
+    ALLOC(h->info6, Bs * 6 * 8);
+    ALLOC(h->dn, Bs);
+    ALLOC(h->inv, Bs);
+    ALLOC(h->tmp_adj_w, Bs * N * 2 * 4);
+    ALLOC(h->tmp_adj_src, Bs * N * 2);
+#undef ALLOC
+    *out = h;
+    return MTFJSP_OK;
+}
+
+int mtfjsp_destroy(mtfjsp_env* h) {
+    if (!h) return MTFJSP_OK;
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->sd, h->si, h->xs, h->t, h->p, h->edge_id, h->jm_fin, h->jm_esa, h->cand, h->a_op, h->a_mach,
+                    h->r5, h->s4, h->info6, h->dn, h->inv, h->tmp_adj_w, h->tmp_adj_src};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    delete h;
+    return MTFJSP_OK;
+}
+
+int mtfjsp_set_params(mtfjsp_env* h, double w_mk, double w_ec, double w_tt, double scaling_divisor, double gamma) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    if (scaling_divisor == 0.0) return fail(MTFJSP_E_ARG, "scaling_divisor must be non-zero");
+    h->cfgw[0] = w_mk; h->cfgw[1] = w_ec; h->cfgw[2] = w_tt; h->divisor = scaling_divisor; h->gamma = gamma;
+    return MTFJSP_OK;
+}
+
+int mtfjsp_load(mtfjsp_env* h, const double* t, const double* p, const double* tt, const int32_t* edge, int W,
+                void* stream) {
+    if (!h || !t || !p || !tt || !edge || W < 1) return fail(MTFJSP_E_ARG, "mtfjsp_load: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    const Layout& L = h->L;
+    size_t n = (size_t)L.B * L.N * L.M * 8;
+    CK(cudaMemcpyAsync(h->t, t, n, cudaMemcpyDeviceToDevice, s), "copy t");
+    CK(cudaMemcpyAsync(h->p, p, n, cudaMemcpyDeviceToDevice, s), "copy p");
+    size_t total = (size_t)L.B * (size_t)(L.N > L.M * L.M ? L.N : L.M * L.M);
+    load_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L, h->t, h->p, tt, edge, W, h->xs, h->edge_id);
+    h->launches++;
+    CK(cudaGetLastError(), "load_kernel");
+    h->loaded = true;
+    h->reset_done = false;
+    return MTFJSP_OK;
+}
+
+int mtfjsp_scaler_init(mtfjsp_env* h, void* stream) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    size_t n = (size_t)h->L.B * 13;
+    scaler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->L, h->sd, 1);
+    h->launches++;
+    CK(cudaGetLastError(), "scaler_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_scaler_reset(mtfjsp_env* h, void* stream) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    size_t n = (size_t)h->L.B * 4;
+    scaler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->L, h->sd, 0);
+    h->launches++;
+    CK(cudaGetLastError(), "scaler_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_reset(mtfjsp_env* h, const double* weights, void* stream) {
+    if (!h || !weights) return fail(MTFJSP_E_ARG, "mtfjsp_reset: bad argument");
+    if (!h->loaded) return fail(MTFJSP_E_STATE, "mtfjsp_reset before mtfjsp_load");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    Params P = make_params(h);
+    P.weights = weights;
+    int rc = launch_env<MODE_RESET, double>(h, P, (cudaStream_t)stream);
+    if (rc == MTFJSP_OK) h->reset_done = true;
+    return rc;
+}
+
+static int fill_obs(mtfjsp_env* h, Params& P, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src,
+                    uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype) {
+    if (dtype != MTFJSP_F32 && dtype != MTFJSP_F64) return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
+    if (mask_mode != MTFJSP_MASK_ESA && mask_mode != MTFJSP_MASK_FINISHED) return fail(MTFJSP_E_ARG, "bad mask_mode");
+    if ((adj_w == nullptr) != (adj_src == nullptr)) return fail(MTFJSP_E_ARG, "adj_w and adj_src go together");
+    P.tfea = task_fea; P.mfea = mach_fea; P.adj_w = adj_w; P.adj_src = adj_src; P.jmask = job_mask; P.cand = candidate;
+    P.mask_mode = mask_mode;
+    (void)h;
+    return MTFJSP_OK;
+}
+
+int mtfjsp_step(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
+                uint8_t* done, uint8_t* invalid, void* stream) {
+    if (!h || !op || !mach) return fail(MTFJSP_E_ARG, "mtfjsp_step: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_step before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    Params P = make_params(h);
+    P.op = op; P.mach = mach; P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
+    return launch_env<MODE_STEP, double>(h, P, (cudaStream_t)stream);
+}
+
+int mtfjsp_obs(mtfjsp_env* h, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src, uint8_t* job_mask,
+               int32_t* candidate, int mask_mode, int dtype, void* stream) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_obs before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    Params P = make_params(h);
+    int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
+    if (rc) return rc;
+    return dtype == MTFJSP_F64 ? launch_env<MODE_OBS, double>(h, P, (cudaStream_t)stream)
+                               : launch_env<MODE_OBS, float>(h, P, (cudaStream_t)stream);
+}
+
+int mtfjsp_step_obs(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
+                    uint8_t* done, uint8_t* invalid, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src,
+                    uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype, void* stream) {
+    if (!h || !op || !mach) return fail(MTFJSP_E_ARG, "mtfjsp_step_obs: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_step_obs before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    Params P = make_params(h);
+    P.op = op; P.mach = mach; P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
+    int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
+    if (rc) return rc;
+    return dtype == MTFJSP_F64 ? launch_env<MODE_STEP | MODE_OBS, double>(h, P, (cudaStream_t)stream)
+                               : launch_env<MODE_STEP | MODE_OBS, float>(h, P, (cudaStream_t)stream);
+}
+
+int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_mask, int dtype, void* stream) {
+    if (!h || !op || !mfea1) return fail(MTFJSP_E_ARG, "mtfjsp_mfea1: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_mfea1 before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    const Layout& L = h->L;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned blocks = (unsigned)((L.B + 127) / 128);
+    if (dtype == MTFJSP_F64)
+        mfea1_kernel<double><<<blocks, 128, 0, s>>>(L, h->t, h->p, h->xs, h->si, h->edge_id, op, (double*)mfea1, mach_mask);
+    else if (dtype == MTFJSP_F32)
+        mfea1_kernel<float><<<blocks, 128, 0, s>>>(L, h->t, h->p, h->xs, h->si, h->edge_id, op, (float*)mfea1, mach_mask);
+    else
+        return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
+    h->launches++;
+    CK(cudaGetLastError(), "mfea1_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream) {
+    if (!h || !adj) return fail(MTFJSP_E_ARG, "mtfjsp_dense_adj: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_dense_adj before mtfjsp_reset");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = mtfjsp_obs(h, nullptr, nullptr, h->tmp_adj_w, h->tmp_adj_src, nullptr, nullptr, MTFJSP_MASK_ESA, MTFJSP_F32, stream);
+    if (rc) return rc;
+    if (dtype == MTFJSP_F64) dense_adj_kernel<double><<<h->L.B, 256, 0, s>>>(h->L, h->tmp_adj_w, h->tmp_adj_src, (double*)adj);
+    else if (dtype == MTFJSP_F32) dense_adj_kernel<float><<<h->L.B, 256, 0, s>>>(h->L, h->tmp_adj_w, h->tmp_adj_src, (float*)adj);
+    else return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
+    h->launches++;
+    CK(cudaGetLastError(), "dense_adj_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_costs(mtfjsp_env* h, double* cost4, void* stream) {
+    if (!h || !cost4) return fail(MTFJSP_E_ARG, "mtfjsp_costs: bad argument");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    costs_kernel<<<(h->L.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->L, h->sd, cost4);
+    h->launches++;
+    CK(cudaGetLastError(), "costs_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_export_state(mtfjsp_env* h, int32_t* mach, double* st, double* ft, int32_t* routes, void* stream) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    if (routes) {
+        size_t n = (size_t)L.B * L.M * L.N;
+        fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(routes, n, -1);
+        h->launches++;
+    }
+    size_t n = (size_t)L.B * L.N;
+    export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, h->sd, h->si, mach, st, ft, routes);
+    h->launches++;
+    CK(cudaGetLastError(), "export_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_export_scaler(mtfjsp_env* h, double* R, double* mean, double* S, int64_t* n, void* stream) {
+    if (!h || !R || !mean || !S || !n) return fail(MTFJSP_E_ARG, "mtfjsp_export_scaler: bad argument");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    export_scaler_kernel<<<(h->L.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->L, h->sd, R, mean, S, n);
+    h->launches++;
+    CK(cudaGetLastError(), "export_scaler_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_policy_random(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int mask_mode, int32_t* op,
+                         int32_t* mach, void* stream) {
+    if (!h || !op || !mach) return fail(MTFJSP_E_ARG, "mtfjsp_policy_random: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_policy_random before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    const uint8_t* jm = mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin;
+    policy_kernel<<<(h->L.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->L, h->t, h->si, jm, h->cand, seed, env_offset, op, mach);
+    h->launches++;
+    CK(cudaGetLastError(), "policy_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_t* op, int32_t* mach, void* mfea1,
+                       uint8_t* mach_mask, double* reward5, double* scaled4, uint8_t* done, uint8_t* invalid,
+                       void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src, uint8_t* job_mask,
+                       int32_t* candidate, int mask_mode, int dtype, void* stream) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    int32_t* o = op ? op : h->a_op;
+    int32_t* mc = mach ? mach : h->a_mach;
+    int rc = mtfjsp_policy_random(h, seed, env_offset, mask_mode, o, mc, stream);
+    if (rc) return rc;
+    if (mfea1) {
+        rc = mtfjsp_mfea1(h, o, mfea1, mach_mask, dtype, stream);
+        if (rc) return rc;
+    }
+    return mtfjsp_step_obs(h, o, mc, reward5, scaled4, done, invalid, task_fea, mach_fea, adj_w, adj_src, job_mask,
+                           candidate, mask_mode, dtype, stream);
+}
+
+int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_host, double* info6_host,
+                     uint8_t* job_mask_host, int32_t* candidate_host, void* task_fea, void* mach_fea, float* adj_w,
+                     int16_t* adj_src, int mask_mode, int dtype, void* stream) {
+    if (!h || !op_host || !mach_host) return fail(MTFJSP_E_ARG, "mtfjsp_step_host: bad argument");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    CK(cudaMemcpyAsync(h->a_op, op_host, (size_t)L.B * 4, cudaMemcpyHostToDevice, s), "H2D op");
+    CK(cudaMemcpyAsync(h->a_mach, mach_host, (size_t)L.B * 4, cudaMemcpyHostToDevice, s), "H2D mach");
+    int rc = mtfjsp_step_obs(h, h->a_op, h->a_mach, h->r5, h->s4, h->dn, h->inv, task_fea, mach_fea, adj_w, adj_src,
+                             nullptr, nullptr, mask_mode, dtype, stream);
+    if (rc) return rc;
+    if (info6_host) {
+        info6_kernel<<<(L.B + 255) / 256, 256, 0, s>>>(L.B, h->r5, h->s4, h->dn, h->info6);
+        h->launches++;
+        CK(cudaGetLastError(), "info6_kernel");
+        CK(cudaMemcpyAsync(info6_host, h->info6, (size_t)L.B * 48, cudaMemcpyDeviceToHost, s), "D2H info6");
+    }
+    if (job_mask_host)
+        CK(cudaMemcpyAsync(job_mask_host, mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin, (size_t)L.B * L.J,
+                           cudaMemcpyDeviceToHost, s), "D2H job_mask");
+    if (candidate_host)
+        CK(cudaMemcpyAsync(candidate_host, h->cand, (size_t)L.B * L.J * 4, cudaMemcpyDeviceToHost, s), "D2H candidate");
+    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return MTFJSP_OK;
+}
+
+int64_t mtfjsp_launch_count(const mtfjsp_env* h) { return h ? h->launches : 0; }
+
+int64_t mtfjsp_bytes_per_step(const mtfjsp_env* h, int dtype) {
+    if (!h) return 0;
+    // B_step = 8 (action) + 2*B_state + B_out_ell
+    const int64_t N = h->L.N, M = h->L.M, J = h->L.J;
+    int64_t b_state = 18 * N + 42 * M + 8 * J + (N + 7) / 8 + 160;
+    int64_t fe = dtype == MTFJSP_F64 ? 8 : 4;
+    int64_t b_out = 12 * fe * N + 18 * N + 8 * fe * M + 5 * J + 41;
+    return 8 + 2 * b_state + b_out;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+/*
+ * mtfjsp.h -- C ABI of the B200-native batched MT-FJSP disjunctive-graph environment.
+ *
+ * This is the drop-in boundary for the reference's batched environment hot path.  The reference
+ * has no FFI (it is single-process Python); each entry point below names the Python interface it
+ * replaces, so a maintainer can bind it with ctypes.  "SS" abbreviates
+ * graph-jsp-env/src/graph_jsp_env/disjunctive_graph_jsp_env_singlestep.py.
+ *
+ * Conventions
+ *   - one handle per (GPU, env slice); a handle owns B environments of one size (J jobs x M ops per
+ *     job = N operations, M machines, E edge groups);
+ *   - every pointer is a DEVICE pointer unless the function name ends in _host; buffers are
+ *     caller-owned; the library allocates only in mtfjsp_create;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises
+ *     the host, except the *_host entry points, which return after their device->host copy is done;
+ *   - return value: 0 ok, negative = error (MTFJSP_E_*); nothing throws;
+ *   - an invalid (operation, machine) pair does not fail the batch: the env's `invalid` flag is set
+ *     and its state is left untouched (the reference silently corrupts its state, SS:1495-1528);
+ *   - not thread-safe per handle; handles are independent.
+ *   - operation index i = job * M + position, 0-based; machines 0-based.
+ *
+ * Observation element type: MTFJSP_F64 reproduces the reference's float64 numpy outputs bit for bit;
+ * MTFJSP_F32 is the same value rounded once to float (what the reference's networks see after their
+ * `.float()` cast, model/actor_critic.py:134-158).
+ */
+#ifndef MTFJSP_H
+#define MTFJSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mtfjsp_env mtfjsp_env;
+
+enum { MTFJSP_F32 = 0, MTFJSP_F64 = 1 };
+enum { MTFJSP_MASK_FINISHED = 0, MTFJSP_MASK_ESA = 1 };
+enum {
+    MTFJSP_OK = 0,
+    MTFJSP_E_ARG = -1,    /* bad argument (null handle, size out of range, ...) */
+    MTFJSP_E_CUDA = -2,   /* a CUDA runtime call failed; see mtfjsp_last_error */
+    MTFJSP_E_STATE = -3   /* call order violated (e.g. step before load/reset) */
+};
+
+/* Limits of this build: 2 <= M <= 64 machines, 1 <= J, N = J*M <= 4096 operations. */
+
+/* replaces: Parallel_env.__init__ (trainer/parallel_env.py:19-36) + the env constructor arguments
+ * perform_left_shift_if_possible / reward_function='wrk' (trainer/parallel_env.py:110-118). */
+int mtfjsp_create(mtfjsp_env** h, int B, int J, int M, int E, int left_shift, int device);
+int mtfjsp_destroy(mtfjsp_env* h);
+
+/* replaces: configs weight_mk / weight_ec / weight_tt (SS:1119-1121), reward_scaling.scaling_divisor
+ * (SS:1164) and GAMMA of RewardScaling (trainer/parallel_env.py:82).  Defaults 0.4/0.4/0.2, 1, 0.99. */
+int mtfjsp_set_params(mtfjsp_env* h, double w_mk, double w_ec, double w_tt, double scaling_divisor, double gamma);
+
+/* replaces: Parallel_env.get_batch (trainer/parallel_env.py:39-63).
+ * t, p: [B,N,M] f64 (negative = infeasible machine); tt: [B,M,M] f64; edge: [B,E,W] int32 machine ids of
+ * each edge group padded with -1. */
+int mtfjsp_load(mtfjsp_env* h, const double* t, const double* p, const double* tt, const int32_t* edge, int W,
+                void* stream);
+
+/* replaces: Parallel_env.init_RewardScaling_sameBATCH (trainer/parallel_env.py:70-83) and
+ * RewardScaling.reset called per episode by Run.py:283-284. */
+int mtfjsp_scaler_init(mtfjsp_env* h, void* stream);
+int mtfjsp_scaler_reset(mtfjsp_env* h, void* stream);
+
+/* replaces: Parallel_env.init_DGFJSPEnv_state0 / env.reset (trainer/parallel_env.py:87-142, SS:1183-1245).
+ * weights: [B,3] f64 per-env reward weights (mk, ec, tt) -- the reference draws them from python's
+ * global `random` (SS:1253-1270); here they are data. */
+int mtfjsp_reset(mtfjsp_env* h, const double* weights, void* stream);
+
+/* replaces: the transition + reward + reward-scaling half of Parallel_env.DGFJSPEnv_paral_step
+ * (trainer/parallel_env.py:217-261; SS:716-974).
+ * op, mach: [B] int32.  Outputs (any may be NULL): reward5 [B,5] f64 = (r, r_mk, r_idle, r_pt, r_tt);
+ * scaled4 [B,4] f64 = running-std scaled (mk, idle, pt, tt); done [B] u8; invalid [B] u8. */
+int mtfjsp_step(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
+                uint8_t* done, uint8_t* invalid, void* stream);
+
+/* replaces: the observation half of env.step / env.reset (SS:2001-2515) and the job mask + candidate
+ * bookkeeping (algorithm/ppo_algorithm.py:202-317, :1126-1165).
+ * dtype selects the element type of task_fea / mach_fea (MTFJSP_F32 | MTFJSP_F64).  Any output may be NULL.
+ *   task_fea [B,N,12]   (est_st, est_ft, est_pt, scheduled, in_degree, machine+1, t, p, job+1, w0, w1, w2)
+ *   mach_fea [B,M,8]    (ft of last op, sum pt/N, sum transport, sum idle, count, w0, w1, w2)
+ *   adj_w    [B,N,2] f32  adjacency in compact ELL form: row = destination op v; [0] = weight of the arc from
+ *                         its job predecessor v-1, [1] = weight of the arc from its machine predecessor
+ *                         (0 = no such arc; a machine arc that coincides with the job arc is reported in [0]);
+ *                         the diagonal entry is always 1 and not stored
+ *   adj_src  [B,N] i16    source op of the machine-predecessor arc, -1 if none
+ *   job_mask [B,J] u8     1 = job not selectable;  candidate [B,J] i32 = next op of each job
+ *   mask_mode: MTFJSP_MASK_ESA (the reference's rule) or MTFJSP_MASK_FINISHED. */
+int mtfjsp_obs(mtfjsp_env* h, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src, uint8_t* job_mask,
+               int32_t* candidate, int mask_mode, int dtype, void* stream);
+
+/* mtfjsp_step followed by mtfjsp_obs in one kernel launch: the state is read once. */
+int mtfjsp_step_obs(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
+                    uint8_t* done, uint8_t* invalid, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src,
+                    uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype, void* stream);
+
+/* replaces: Parallel_env.cal_cur_task_machine_feature (trainer/parallel_env.py:152-214) and the machine
+ * mask gather of Run.py:262-266, 335-337.  op [B] int32; mfea1 [B,M,6] (dtype); mach_mask [B,M] u8, 1 = infeasible. */
+int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_mask, int dtype, void* stream);
+
+/* compatibility view: dense adjacency adj[b,dst,src], diagonal 1 (SS:2019-2073), element type dtype. */
+int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream);
+
+/* replaces: reading env.makespan_previous_step, total_e1_previous_step/N, trans_t_previous_step,
+ * idle_t_previous_step (Run.py:632-633, trainer/validate.py:273-277).  cost4 [B,4] f64 (mk, pt/N, tt, idle). */
+int mtfjsp_costs(mtfjsp_env* h, double* cost4, void* stream);
+
+/* parity checks / rendering: machine assignment (-1 unassigned) [B,N] i32, start / finish [B,N] f64 (0 while
+ * unscheduled), machine routes [B,M,N] i32 padded with -1 (replaces env.machine_routes, env.G.nodes[...]). */
+int mtfjsp_export_state(mtfjsp_env* h, int32_t* mach, double* st, double* ft, int32_t* routes, void* stream);
+int mtfjsp_export_scaler(mtfjsp_env* h, double* R, double* mean, double* S, int64_t* n, void* stream);
+
+/* Uniform random valid action from the env's current masks: a selectable job (under mask_mode), its candidate
+ * op, and a feasible machine for it; counter-based, keyed by (seed, env_offset + env, ops scheduled so far).
+ * Mirrors tester/pdrs.py Random_task / Random_m (:75-86, :139-156).  op, mach [B] int32 (-1 when done). */
+int mtfjsp_policy_random(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int mask_mode, int32_t* op,
+                         int32_t* mach, void* stream);
+
+/* One whole pass of the environment side of a rollout step in one launch sequence on `stream`:
+ * policy_random -> mfea1 -> step_obs.  mfea1 / mach_mask may be NULL. */
+int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_t* op, int32_t* mach, void* mfea1,
+                       uint8_t* mach_mask, double* reward5, double* scaled4, uint8_t* done, uint8_t* invalid,
+                       void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src, uint8_t* job_mask,
+                       int32_t* candidate, int mask_mode, int dtype, void* stream);
+
+/* Host-buffer form of mtfjsp_step_obs, the call a host-side rollout loop (Run.py:411-443) makes:
+ * actions come from (pinned) host memory, the step info the host consumes comes back --
+ * info6 [B,6] f64 = (r, done, mk_s, idle_s, pt_s, tt_s) exactly as trainer/parallel_env.py:260,
+ * job_mask [B,J] u8 and candidate [B,J] i32 -- while the observation tensors stay on the device
+ * (device pointers, may be NULL) for the encoder.  Synchronises `stream` before returning. */
+int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_host, double* info6_host,
+                     uint8_t* job_mask_host, int32_t* candidate_host, void* task_fea, void* mach_fea, float* adj_w,
+                     int16_t* adj_src, int mask_mode, int dtype, void* stream);
+
+/* Number of kernel launches issued through this handle so far (bench.py reports it). */
+int64_t mtfjsp_launch_count(const mtfjsp_env* h);
+/* Algorithmic bytes per env-step of the fused step+obs kernel for this handle's sizes. */
+int64_t mtfjsp_bytes_per_step(const mtfjsp_env* h, int dtype);
+const char* mtfjsp_last_error(void);
+const char* mtfjsp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTFJSP_H */

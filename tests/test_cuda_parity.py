@@ -1,0 +1,269 @@
+"""Parity tests proper: the sm_100a path, called through the C ABI, against
+  (a) the committed reference dumps and the shipped result CSV rows (tests/golden),
+  (b) the CPU oracle on the same seeded inputs at sizes it finishes in seconds,
+  (c) size-independent schedule invariants at BASELINE.json's full batch sizes.
+FP64 outputs are compared bit for bit; F32 observations must equal the oracle's FP64 value rounded once."""
+import glob
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle.mtfjsp_oracle import OracleEnv  # noqa: E402
+from tests.test_oracle_golden import check_replay  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
+eq = np.testing.assert_array_equal
+
+
+def _adapter():
+    from tests import cuda_adapter
+
+    return cuda_adapter
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name", [os.path.basename(p) for p in sorted(glob.glob(os.path.join(GOLD, "replay_*.npz")))])
+def test_replay_matches_reference_dump(name, fused):
+    ad = _adapter()
+    check_replay(lambda B, J, M, E, ls: ad.NumpyEnvAdapter(B, J, M, E, left_shift=ls, fused=fused), os.path.join(GOLD, name))
+
+
+def test_pdr_rows_match_shipped_csv():
+    ad = _adapter()
+    g = np.load(os.path.join(GOLD, "pdr_golden.npz"))
+    gold, ops, mch = g["gold"], g["ops"], g["mch"]
+    R, S, N = ops.shape
+    env = ad.NumpyEnvAdapter(S, 6, 6, 2, left_shift=False)
+    env.load(g["t"], g["p"], g["transT"], g["edge"])
+    env.scaler_init()
+    w = np.tile(np.array([0.4, 0.4, 0.2]), (S, 1))
+    for r in range(R):
+        env.reset(w)
+        for s in range(N):
+            r5, s4, done, inv = env.step(ops[r, :, s], mch[r, :, s])
+            assert not inv.any()
+        assert done.all()
+        eq(env.costs(), gold[r], err_msg=str(g["rule_names"][r]))
+
+
+def _mk(B, J, M, E, seed, left_shift=True, dtype=torch.float64, mask_mode=1, scale=1.0, first_env=0):
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    d = ins.synthetic_instances(first_env, B, J, M, E, seed)
+    t, tt = d["t"] * scale, d["transT"] * scale
+    w = ins.random_weights(first_env, B, seed)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=left_shift, obs_dtype=dtype, mask_mode=mask_mode)
+    env.load(t, d["p"], tt, d["edge"])
+    env.scaler_init()
+    env.reset(w)
+    ora = OracleEnv(B, J, M, E, left_shift=left_shift, nthreads=8)
+    ora.load(t, d["p"], tt, d["edge"])
+    ora.scaler_init()
+    ora.reset(w)
+    return env, ora, d, w
+
+
+def _ell_to_dense(adj_w, adj_src):
+    B, N, _ = adj_w.shape
+    A = np.zeros((B, N, N))
+    ar = np.arange(N)
+    A[:, ar, ar] = 1.0
+    bj, vj = np.nonzero(adj_w[:, :, 0])
+    A[bj, vj, vj - 1] = adj_w[bj, vj, 0]
+    bm, vm = np.nonzero(adj_src >= 0)
+    A[bm, vm, adj_src[bm, vm]] = adj_w[bm, vm, 1]
+    return A
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, J, M, E, left_shift, mask_mode, scale, episodes
+    (512, 6, 6, 2, True, 1, 1.0, 2),
+    (512, 6, 6, 2, True, 0, 1.0, 1),
+    (256, 6, 6, 2, False, 0, 1.0, 1),
+    (256, 6, 6, 2, True, 0, 0.02, 1),
+    (128, 10, 10, 3, True, 1, 1.0, 1),
+    (128, 10, 10, 3, True, 0, 1.0, 1),
+    (64, 3, 4, 2, True, 0, 1.0, 2),
+    (33, 2, 2, 1, True, 0, 1.0, 1),
+    (40, 20, 5, 2, True, 0, 1.0, 1),
+    (24, 5, 33, 4, True, 0, 1.0, 1),
+    (16, 30, 20, 5, True, 0, 1.0, 1),
+    (16, 30, 20, 5, True, 1, 1.0, 1),
+    (8, 40, 8, 2, True, 0, 0.05, 1),
+])
+def test_random_rollout_matches_oracle_every_step(cfg):
+    B, J, M, E, ls, mm, scale, episodes = cfg
+    N = J * M
+    env, ora, d, w = _mk(B, J, M, E, seed=1000 + J * M, left_shift=ls, mask_mode=mm, scale=scale)
+    ob = ora.obs(mm)
+    env.obs(mm)
+    eq(env.task_fea.cpu().numpy(), ob["task_fea"])
+    eq(env.job_mask.cpu().numpy(), ob["job_mask"])
+    for ep in range(episodes):
+        if ep > 0:
+            w2 = ins.random_weights(0, B, 77 + ep)
+            env.reset(w2); ora.reset(w2)
+            env.scaler_reset(); ora.scaler_reset()
+        for s in range(N):
+            env.random_step(seed=42 + ep, env_offset=0, mask_mode=mm)
+            op, mc = env.op.cpu().numpy(), env.mach.cpu().numpy()
+            # the device policy draws the same counter-based action as the oracle's policy
+            m1, mmask = ora.mfea1(op)
+            r5, s4, done, inv = ora.step(op, mc)
+            assert not inv.any(), (s, op[inv.astype(bool)], mc[inv.astype(bool)])
+            ob = ora.obs(mm)
+            eq(env.invalid.cpu().numpy(), inv)
+            eq(env.mfea1_buf.cpu().numpy(), m1)
+            eq(env.mach_mask.cpu().numpy(), mmask)
+            eq(env.reward5.cpu().numpy(), r5)
+            eq(env.scaled4.cpu().numpy(), s4)
+            eq(env.done.cpu().numpy(), done)
+            eq(env.task_fea.cpu().numpy(), ob["task_fea"])
+            eq(env.mach_fea.cpu().numpy(), ob["mach_fea"])
+            eq(env.job_mask.cpu().numpy(), ob["job_mask"])
+            eq(env.candidate.cpu().numpy(), ob["candidate"])
+            if s % 7 == 0 or s == N - 1:
+                eq(_ell_to_dense(env.adj_w.cpu().numpy().astype(np.float64), env.adj_src.cpu().numpy().astype(np.int64)),
+                   ora.dense_adj())
+                st = {k: v.cpu().numpy() for k, v in env.export_state().items()}
+                so = ora.export_state()
+                for k in so:
+                    eq(st[k], so[k], err_msg=k)
+        assert env.done.cpu().numpy().all()
+        eq(env.costs().cpu().numpy(), ora.costs())
+        sc, so = env.export_scaler(), ora.export_scaler()
+        for k in so:
+            eq(sc[k].cpu().numpy(), so[k], err_msg=k)
+
+
+def test_oracle_policy_replays_device_actions():
+    """oracle_rollout_random (the CPU baseline loop) draws exactly the actions the device policy draws."""
+    B, J, M, E = 256, 6, 6, 2
+    env, ora, d, w = _mk(B, J, M, E, seed=5)
+    acts = []
+    for s in range(J * M):
+        env.random_step(seed=9, env_offset=0)
+        acts.append(np.stack([env.op.cpu().numpy(), env.mach.cpu().numpy()], 1))
+    out = ora.rollout_random(J * M, seed=9, env_offset=0, mask_mode=1, record_actions=True)
+    eq(out["actions"], np.stack(acts))
+    eq(env.task_fea.cpu().numpy(), out["task_fea"])
+    eq(env.reward5.cpu().numpy(), out["reward5"])
+
+
+def test_f32_observations_are_the_rounded_f64_values():
+    B, J, M, E = 256, 6, 6, 2
+    env, ora, d, w = _mk(B, J, M, E, seed=11, dtype=torch.float32)
+    for s in range(J * M):
+        env.random_step(seed=3)
+        op, mc = env.op.cpu().numpy(), env.mach.cpu().numpy()
+        m1, _ = ora.mfea1(op)
+        ora.step(op, mc)
+        ob = ora.obs(1)
+        eq(env.task_fea.cpu().numpy(), ob["task_fea"].astype(np.float32))
+        eq(env.mach_fea.cpu().numpy(), ob["mach_fea"].astype(np.float32))
+        eq(env.mfea1_buf.cpu().numpy(), m1.astype(np.float32))
+    eq(env.dense_adj(torch.float32).cpu().numpy(), ora.dense_adj().astype(np.float32))
+
+
+def test_invalid_actions_are_flagged_and_leave_state_untouched():
+    B, J, M, E = 64, 3, 3, 1
+    env, ora, d, w = _mk(B, J, M, E, seed=5)
+    dev = env.device
+    i32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.int32)).to(dev)
+    before = {k: v.cpu().numpy() for k, v in env.export_state().items()}
+    feas = np.argmax(d["t"][:, 0] >= 0, axis=1)
+    for op, mc in ((np.full(B, 1), feas), (np.full(B, 99), feas), (np.zeros(B), np.full(B, 7)), (np.full(B, -1), feas)):
+        env.step(i32(op), i32(mc))
+        assert env.invalid.cpu().numpy().all()
+        eq(env.reward5.cpu().numpy(), 0.0)
+    after = {k: v.cpu().numpy() for k, v in env.export_state().items()}
+    for k in before:
+        eq(before[k], after[k])
+    env.step(i32(np.zeros(B)), i32(feas))
+    assert not env.invalid.cpu().numpy().any()
+    env.step(i32(np.zeros(B)), i32(feas))
+    assert env.invalid.cpu().numpy().all()
+    infeas = np.argmax(d["t"][:, 1] < 0, axis=1)
+    env.step(i32(np.ones(B)), i32(infeas))
+    eq(env.invalid.cpu().numpy().astype(bool), (d["t"][:, 1] < 0).any(axis=1))
+
+
+def test_step_before_reset_is_a_state_error():
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    lib = importlib.import_module("e2e-mappo-for-mt-fjsp_b200._lib")
+    env = envm.BatchedMTFJSPEnv(4, 3, 3, 1)
+    with pytest.raises(lib.MTFJSPError):
+        env.step(env.op, env.mach)
+
+
+@pytest.mark.parametrize("cfg", [(65536, 6, 6, 2), (16384, 10, 10, 3), (4096, 30, 20, 5)])
+def test_full_size_rollout_invariants(cfg):
+    """BASELINE.json sizes: schedule invariants + telescoping rewards + a replay-checked random subset."""
+    B, J, M, E = cfg
+    N = J * M
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    d = ins.synthetic_instances(0, B, J, M, E, 1000 + N)
+    w = ins.random_weights(0, B, 1000 + N)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    env.reset(w)
+    c0 = env.costs().clone()
+    rsum = torch.zeros((B, 5), dtype=torch.float64, device=env.device)
+    rng = np.random.default_rng(0)
+    sub = np.sort(rng.choice(B, 1024 if N <= 100 else 128, replace=False))
+    acts = np.zeros((N, len(sub), 2), dtype=np.int32)
+    for s in range(N):
+        env.random_step(seed=123, env_offset=0)
+        rsum += env.reward5
+        acts[s, :, 0] = env.op.cpu().numpy()[sub]
+        acts[s, :, 1] = env.mach.cpu().numpy()[sub]
+        assert int(env.invalid.sum().item()) == 0
+        assert int(env.done.sum().item()) == (B if s == N - 1 else 0)
+    c1 = env.costs()
+    # rewards telescope to (initial estimate - final cost) per component (SS:1066-1088)
+    tot = rsum.cpu().numpy()
+    np.testing.assert_allclose(tot[:, 1], (c0[:, 0] - c1[:, 0]).cpu().numpy(), rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(tot[:, 3], (c0[:, 1] - c1[:, 1]).cpu().numpy(), rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(tot[:, 4], -c1[:, 2].cpu().numpy(), rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(tot[:, 2], -c1[:, 3].cpu().numpy(), rtol=1e-9, atol=1e-6)
+    st = {k: v.cpu().numpy() for k, v in env.export_state().items()}
+    mach, stt, ftt, routes = st["mach"], st["st"], st["ft"], st["routes"]
+    assert (mach >= 0).all()
+    t = d["t"]
+    dur = np.take_along_axis(t, mach[:, :, None].astype(np.int64), axis=2)[:, :, 0]
+    assert (dur > 0).all()
+    eq(ftt, stt + dur)                                    # ft = st + dur, machine feasible
+    s2, f2 = stt.reshape(B, J, M), ftt.reshape(B, J, M)
+    assert (s2[:, :, 1:] >= f2[:, :, :-1]).all()          # job precedence
+    assert ((routes >= 0).sum(axis=(1, 2)) == N).all()    # every op on exactly one route
+    for m in range(M):                                    # no overlap on a machine, route order = time order
+        r = routes[:, m, :]
+        ok = r >= 0
+        rs = np.where(ok, np.take_along_axis(stt, np.maximum(r, 0).astype(np.int64), 1), np.inf)
+        rf = np.where(ok, np.take_along_axis(ftt, np.maximum(r, 0).astype(np.int64), 1), np.inf)
+        nxt_ok = ok[:, 1:]
+        assert (rs[:, 1:][nxt_ok] >= rf[:, :-1][nxt_ok]).all()
+        mm_ = np.where(ok, np.take_along_axis(mach, np.maximum(r, 0).astype(np.int64), 1), m)
+        assert (mm_ == m).all()
+    eq(c1[:, 0].cpu().numpy(), ftt.max(axis=1))           # final makespan is the true one
+    # replay the recorded actions of a random subset on the oracle: bit-exact schedules and costs
+    ora = OracleEnv(len(sub), J, M, E, left_shift=True, nthreads=8)
+    ora.load(t[sub], d["p"][sub], d["transT"][sub], d["edge"][sub])
+    ora.scaler_init()
+    ora.reset(w[sub])
+    for s in range(N):
+        r5, s4, done, inv = ora.step(acts[s, :, 0], acts[s, :, 1])
+        assert not inv.any()
+    so = ora.export_state()
+    eq(mach[sub], so["mach"]); eq(stt[sub], so["st"]); eq(ftt[sub], so["ft"]); eq(routes[sub], so["routes"])
+    eq(c1.cpu().numpy()[sub], ora.costs())
+    eq(env.reward5.cpu().numpy()[sub], r5)
+    eq(env.scaled4.cpu().numpy()[sub], s4)
+    ob = ora.obs(1)
+    eq(env.task_fea.cpu().numpy()[sub], ob["task_fea"].astype(np.float32))
