@@ -129,22 +129,19 @@ __device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf
         int Lx = L0 + grp;
         bool act = Lx < pw.nleaves;
         int off = act ? pw.leaf_off[Lx] : 0, n = act ? pw.leaf_len[Lx] : 0;
-        double res = 0.0;
-        if (n < 8) {  // whole array shorter than 8 (only when N < 8): plain loop
-            if (k == 0)
-                for (int i = 0; i < n; i++) res += a[off + i];
-        } else {
-            int nb = n - (n & 7);
-            double r = a[off + k];
+        const int nb = (n >= 8) ? n - (n & 7) : 0;
+        double r = 0.0;
+        if (n >= 8) {
+            r = a[off + k];
             for (int i = 8 + k; i < nb; i += 8) r += a[off + i];
-            // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
-            r = r + __shfl_down_sync(FULL, r, 1, 8);
-            r = r + __shfl_down_sync(FULL, r, 2, 8);
-            r = r + __shfl_down_sync(FULL, r, 4, 8);
-            res = r;
-            if (k == 0)
-                for (int i = nb; i < n; i++) res += a[off + i];
         }
+        // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); every lane takes part in the shuffles
+        r = r + __shfl_down_sync(FULL, r, 1, 8);
+        r = r + __shfl_down_sync(FULL, r, 2, 8);
+        r = r + __shfl_down_sync(FULL, r, 4, 8);
+        double res = r;  // n < 8 (only when N < 8): r is 0 and the loop below is the plain sum
+        if (k == 0)
+            for (int i = nb; i < n; i++) res += a[off + i];
         if (act && k == 0) s_leaf[Lx] = res;
     }
     __syncwarp();
