@@ -1,0 +1,26 @@
+"""Short driver for ncu captures: config-2 workload (J6M6E2, 65,536 envs), a few rollout steps.
+usage: ncu ... python profiles/prof_step.py [workload] [steps]"""
+import importlib
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "A"]
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+pkg = importlib.import_module("e2e-mappo-for-mt-fjsp_b200")
+envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+J, M, E, B = wl["J"], wl["M"], wl["E"], wl["B"]
+d = pkg.instances.synthetic_instances(0, B, J, M, E, wl["seed"])
+w = pkg.instances.random_weights(0, B, wl["seed"])
+env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
+env.load(d["t"], d["p"], d["transT"], d["edge"])
+env.scaler_init()
+env.reset(w)
+for s in range(steps):
+    env.random_step(seed=1)
+torch.cuda.synchronize()
+print("done", env.launch_count)
