@@ -18,7 +18,8 @@
 // HBM layout (per handle, B environments; every record is 16-byte aligned):
 //   sd  [B][sd_stride] f64   dynamic doubles: st[N] ft[N] dur[N] psel[N] | mk_prev e_prev trans idle_prev |
 //                            macc[M][3] | w[3] | scaler R[4] mean[4] S[4] n
-//   si  [B][si_stride] i16   dynamic ints:    mach[N] pos[N] rpred[N] cnt[M] | removed_head fresh_co nsched
+//                            (for an unscheduled op st/ft hold the current estimate, dur = 0, psel = min energy)
+//   si  [B][si_stride] i16   dynamic ints:    mach[N] pos[N] rpred[N] cnt[M] | removed_head fresh_co nsched | nxt[J]
 //   xs  [B][xs_stride] f64   static doubles:  mind[N] minpt[N] tt[M][M]
 //   t,p [B][N][M]      f64   instance tables, touched only at (op, machine) and in the mfea1 kernel
 #include <cuda_runtime.h>
@@ -43,7 +44,7 @@ struct Layout {
     int B, J, M, N, E, left_shift;
     int sd_stride, si_stride, xs_stride;
     int o_st, o_ft, o_dur, o_psel, o_scal, o_macc, o_w, o_sc;  // sd offsets (doubles)
-    int o_mach, o_pos, o_rpred, o_cnt, o_misc;                 // si offsets (int16)
+    int o_mach, o_pos, o_rpred, o_cnt, o_misc, o_nxt;          // si offsets (int16)
     int o_mind, o_minpt, o_tt;                                 // xs offsets (doubles)
     int sm_sd, sm_xs, sm_pt, sm_v, sm_leaf, sm_si, sm_off, sm_nxt, sm_tail;  // smem byte offsets per warp
     int smem_per_warp, warps_per_block;
@@ -328,7 +329,14 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 g_si[L.o_cnt + m] = (int16_t)(len + 1);
                 g_si[L.o_misc + 0] = (int16_t)rem_head; g_si[L.o_misc + 1] = (int16_t)fresh;
                 g_si[L.o_misc + 2] = (int16_t)(nsched0 + 1);
+                g_si[L.o_nxt + ja] = (int16_t)((a % M) + 1);
                 g_sd[L.o_st + a] = st; g_sd[L.o_ft + a] = st + d; g_sd[L.o_dur + a] = d; g_sd[L.o_psel + a] = pa;
+                double cur = st + d;  // estimator chain of the remaining ops of this job (SS:1964-1995)
+                for (int c = (a % M) + 1; c < M; c++) {
+                    g_sd[L.o_st + ja * M + c] = cur;
+                    cur = cur + s_mind[ja * M + c];
+                    g_sd[L.o_ft + ja * M + c] = cur;
+                }
             }
             __syncwarp();
             const int nsched = nsched0 + 1;
@@ -405,9 +413,14 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
     if (MODE & MODE_RESET) {
         if (lane == 0) { s_scal[0] = mkv; s_scal[1] = env; s_scal[2] = 0.0; s_scal[3] = 0.0; }  // SS:697-705
         __syncwarp();
-        // write back the env part of sd (everything except the scaler block) and the whole si record;
-        // st/ft in smem now hold estimates for unscheduled ops, so zeros are written explicitly
-        for (int i = lane; i < 4 * N; i += 32) g_sd[L.o_st + i] = 0.0;
+        // write back the env part of sd (everything except the scaler block) and the whole si record.
+        // State invariant: an unscheduled op carries its estimate in st/ft, dur = 0 and psel = min energy.
+        for (int i = lane; i < N; i += 32) {
+            g_sd[L.o_st + i] = s_st[i];
+            g_sd[L.o_ft + i] = s_ft[i];
+            g_sd[L.o_dur + i] = 0.0;
+            g_sd[L.o_psel + i] = s_minpt[i];
+        }
         for (int i = L.o_scal + lane; i < L.o_sc; i += 32) g_sd[i] = s_sd[i];
         uint4* dst = reinterpret_cast<uint4*>(g_si);
         const uint4* src = reinterpret_cast<const uint4*>(s_si);
@@ -572,6 +585,8 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
 // Size-specialised kernel: (J, M) are compile-time, G lanes cooperate on one environment and a warp
 // carries 32/G environments, so the scalar phases (placement decision, idle sum, reward, FP64 divisions of
 // the reward scaler) are issued once for 32/G instances.  Same HBM records and arithmetic as env_kernel.
+// It relies on the state invariant kept by reset and step: unscheduled ops carry their current estimate
+// in st/ft (only the stepped job's chain changes per step), dur = 0 and psel = min feasible energy.
 // =====================================================================================================
 constexpr int calign(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -580,15 +595,16 @@ struct Spec {
     static constexpr int J = J_, M = M_, G = G_, N = J_ * M_, EPW = 32 / G_, WARPS = WARPS_;
     static_assert(J_ <= G_ && M_ <= G_, "one lane per job and per machine");
     static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 13, 2);
-    static constexpr int SI = calign(3 * N + M + 3, 8);
+    static constexpr int SI = calign(3 * N + M + 3 + J, 8);
     static constexpr int XS = calign(2 * N + M * M, 2);
+    static constexpr int TT = calign(M * M, 2);  // only the transport table is staged from xs
     static constexpr int O_ST = 0, O_FT = N, O_DUR = 2 * N, O_PSEL = 3 * N, O_SCAL = 4 * N, O_MACC = 4 * N + 4,
                          O_W = O_MACC + 3 * M, O_SC = O_W + 3;
-    static constexpr int O_MACH = 0, O_POS = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M;
+    static constexpr int O_MACH = 0, O_POS = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
     static constexpr int O_MIND = 0, O_MINPT = N, O_TT = 2 * N;
-    static constexpr int B_SD = SD * 8, B_XS = XS * 8, B_PT = calign(N, 2) * 8, B_SI = SI * 2,
+    static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 2) * 8, B_SI = SI * 2,
                          B_TAIL = calign(M, 8) * 2, B_LEAF = (N > 128) ? (MAX_LEAVES + 32) * 8 : 0;
-    static constexpr int RAW = calign(B_SD + B_XS + B_PT + B_LEAF + B_SI + B_TAIL, 16);
+    static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_LEAF + B_SI + B_TAIL, 16);
     // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
     static constexpr int ENV_BYTES = (G_ == 8) ? (RAW + ((64 - RAW % 128) + 128) % 128) : RAW;
     static constexpr int ITER = (N + G - 1) / G;
@@ -626,6 +642,14 @@ __device__ __forceinline__ int gmax_i(int v) {
     return v;
 }
 
+// adj_val without the 64-bit integer round trip: trunc() is exact for |w| < 2^53
+__device__ __forceinline__ double adj_val_t(double w, bool u_assigned, double dur_u) {
+    const double wi = trunc(w);
+    if (wi == 0.0) return 0.0;
+    const double nd = u_assigned ? dur_u : 1.0;
+    return trunc(wi - nd) + 1.0;
+}
+
 template <class S, int MODE, typename OutT>
 __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_constant__ Params P) {
     constexpr int J = S::J, M = S::M, N = S::N, G = S::G, EPW = S::EPW, ITER = S::ITER;
@@ -641,70 +665,69 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
 
     unsigned char* base = smem_raw + (size_t)(warp * EPW + ge) * S::ENV_BYTES;
     double* s_sd = reinterpret_cast<double*>(base);
-    double* s_xs = reinterpret_cast<double*>(base + S::B_SD);
-    double* s_pt = reinterpret_cast<double*>(base + S::B_SD + S::B_XS);
-    double* s_leaf = reinterpret_cast<double*>(base + S::B_SD + S::B_XS + S::B_PT);
-    int16_t* s_si = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_XS + S::B_PT + S::B_LEAF);
-    int16_t* s_tail = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_XS + S::B_PT + S::B_LEAF + S::B_SI);
+    const double* __restrict__ s_tt = reinterpret_cast<const double*>(base + S::B_SD);
+    double* __restrict__ s_pt = reinterpret_cast<double*>(base + S::B_SD + S::B_TT);
+    double* s_leaf = reinterpret_cast<double*>(base + S::B_SD + S::B_TT + S::B_PT);
+    int16_t* __restrict__ s_si = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF);
+    int16_t* __restrict__ s_tail = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF + S::B_SI);
 
     double* g_sd = P.sd + (size_t)bc * S::SD;
     int16_t* g_si = P.si + (size_t)bc * S::SI;
     const double* g_xs = P.xs + (size_t)bc * S::XS;
 
-    // ---- stage the three records: 16-byte async copies, G lanes per record ----
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(g_sd);
-        uint4* dst = reinterpret_cast<uint4*>(s_sd);
-#pragma unroll 4
-        for (int i = gl; i < S::SD / 2; i += G) cp_async16(dst + i, src + i);
-        src = reinterpret_cast<const uint4*>(g_xs);
-        dst = reinterpret_cast<uint4*>(s_xs);
-#pragma unroll 4
-        for (int i = gl; i < S::XS / 2; i += G) cp_async16(dst + i, src + i);
-        src = reinterpret_cast<const uint4*>(g_si);
-        dst = reinterpret_cast<uint4*>(s_si);
-#pragma unroll 4
-        for (int i = gl; i < S::SI / 8; i += G) cp_async16(dst + i, src + i);
-    }
-    // action + instance entries are independent of the staged records: issue their loads meanwhile
+    // the action is the head of a dependent chain (op -> t[op][m], mind row of its job): issue it first
     int a = 0, m = 0;
     if (MODE & MODE_STEP) {
         a = __ldg(P.op + bc);
         m = __ldg(P.mach + bc);
     }
+    // ---- stage the records: 16-byte async copies, G lanes per record ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(g_sd);
+        uint4* dst = reinterpret_cast<uint4*>(s_sd);
+#pragma unroll 4
+        for (int i = gl; i < S::SD / 2; i += G) cp_async16(dst + i, src + i);
+        src = reinterpret_cast<const uint4*>(g_xs + S::O_TT);
+        dst = reinterpret_cast<uint4*>(base + S::B_SD);
+#pragma unroll 4
+        for (int i = gl; i < S::TT / 2; i += G) cp_async16(dst + i, src + i);
+        src = reinterpret_cast<const uint4*>(g_si);
+        dst = reinterpret_cast<uint4*>(s_si);
+#pragma unroll 4
+        for (int i = gl; i < S::SI / 8; i += G) cp_async16(dst + i, src + i);
+    }
     bool valid = (MODE & MODE_STEP) && active && a >= 0 && a < N && m >= 0 && m < M;
     const int ac = valid ? a : 0, mc = valid ? m : 0;
-    double d = 0.0, pa = 0.0;
+    const int apos = ac % M, ja = ac / M;
+    double d = 0.0, pa = 0.0, mind_r = 0.0;
     if (MODE & MODE_STEP) {
         d = __ldg(P.t + ((size_t)bc * N + ac) * M + mc);
         pa = __ldg(P.p + ((size_t)bc * N + ac) * M + mc);
+        if (gl < M) mind_r = __ldg(g_xs + S::O_MIND + ja * M + gl);  // lane c: min duration of op (ja, c)
     }
     cp_async_wait_all();
     __syncwarp();
 
-    double* s_st = s_sd + S::O_ST;
-    double* s_ft = s_sd + S::O_FT;
-    double* s_dur = s_sd + S::O_DUR;
-    double* s_psel = s_sd + S::O_PSEL;
-    double* s_scal = s_sd + S::O_SCAL;
-    double* s_macc = s_sd + S::O_MACC;
-    double* s_w = s_sd + S::O_W;
-    double* s_sc = s_sd + S::O_SC;
-    int16_t* s_mach = s_si + S::O_MACH;
-    int16_t* s_pos = s_si + S::O_POS;
-    int16_t* s_rpred = s_si + S::O_RPRED;
-    int16_t* s_cnt = s_si + S::O_CNT;
-    int16_t* s_misc = s_si + S::O_MISC;
-    const double* s_mind = s_xs + S::O_MIND;
-    const double* s_minpt = s_xs + S::O_MINPT;
-    const double* s_tt = s_xs + S::O_TT;
+    double* __restrict__ s_st = s_sd + S::O_ST;
+    double* __restrict__ s_ft = s_sd + S::O_FT;
+    double* __restrict__ s_dur = s_sd + S::O_DUR;
+    double* __restrict__ s_psel = s_sd + S::O_PSEL;
+    double* __restrict__ s_scal = s_sd + S::O_SCAL;
+    double* __restrict__ s_macc = s_sd + S::O_MACC;
+    const double* __restrict__ s_w = s_sd + S::O_W;
+    double* __restrict__ s_sc = s_sd + S::O_SC;
+    int16_t* __restrict__ s_mach = s_si + S::O_MACH;
+    int16_t* __restrict__ s_pos = s_si + S::O_POS;
+    int16_t* __restrict__ s_rpred = s_si + S::O_RPRED;
+    int16_t* __restrict__ s_cnt = s_si + S::O_CNT;
+    int16_t* __restrict__ s_misc = s_si + S::O_MISC;
+    int16_t* __restrict__ s_nxt = s_si + S::O_NXT;
 
     bool done = false;
-    double mkv = 0.0, en = 0.0, idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;
+    double idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;
 
     if (MODE & MODE_STEP) {
         const int nsched0 = s_misc[2];
-        const int apos = ac % M, ja = ac / M;
         const bool first = apos == 0;
         const int aprev = first ? ac : ac - 1;
         valid = valid && nsched0 < N && (s_mach[ac] < 0) && (first || s_mach[aprev] >= 0) && !(d < 0);
@@ -762,6 +785,20 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
             }
             if (prev >= 0 && prev == ac - 1 && !first) fresh = ac;
         }
+        // estimator chain of the job's remaining ops (SS:1964-1995): lane c ends up with op (ja, c)
+        double my_st = 0.0, my_ft = 0.0;
+        {
+            double cur = st + d;
+#pragma unroll
+            for (int c = 1; c < M; c++) {
+                const double mdc = __shfl_sync(FULL, mind_r, c, G);
+                if (c > apos) {
+                    const double s0 = cur;
+                    cur = cur + mdc;
+                    if (gl == c) { my_st = s0; my_ft = cur; }
+                }
+            }
+        }
         __syncwarp();
         if (valid) {
 #pragma unroll
@@ -773,6 +810,11 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
                     g_si[S::O_POS + v] = np_;
                 }
             }
+            if (gl > apos && gl < M) {
+                const int idx = ja * M + gl;
+                s_st[idx] = my_st; s_ft[idx] = my_ft;
+                g_sd[S::O_ST + idx] = my_st; g_sd[S::O_FT + idx] = my_ft;
+            }
         }
         __syncwarp();
         if (valid && gl == 0) {
@@ -780,12 +822,14 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
             if (next >= 0) s_rpred[next] = (int16_t)ac;
             s_cnt[mc] = (int16_t)(len + 1);
             s_misc[0] = (int16_t)rem_head; s_misc[1] = (int16_t)fresh; s_misc[2] = (int16_t)(nsched0 + 1);
+            s_nxt[ja] = (int16_t)(apos + 1);
             s_st[ac] = st; s_ft[ac] = st + d; s_dur[ac] = d; s_psel[ac] = pa;
             g_si[S::O_MACH + ac] = (int16_t)mc; g_si[S::O_POS + ac] = (int16_t)where; g_si[S::O_RPRED + ac] = (int16_t)prev;
             if (next >= 0) g_si[S::O_RPRED + next] = (int16_t)ac;
             g_si[S::O_CNT + mc] = (int16_t)(len + 1);
             g_si[S::O_MISC + 0] = (int16_t)rem_head; g_si[S::O_MISC + 1] = (int16_t)fresh;
             g_si[S::O_MISC + 2] = (int16_t)(nsched0 + 1);
+            g_si[S::O_NXT + ja] = (int16_t)(apos + 1);
             g_sd[S::O_ST + ac] = st; g_sd[S::O_FT + ac] = st + d; g_sd[S::O_DUR + ac] = d; g_sd[S::O_PSEL + ac] = pa;
         }
         __syncwarp();
@@ -828,44 +872,32 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
         __syncwarp();
     }
 
-    // ---- per-job walk (lane j of the group): scheduled prefix, estimator chain, ESA key ----
-    int nx = 0;
-    double vj = INFINITY, jmx = -INFINITY;
-    if (gl < J) {
-        const int jb = gl * M;
-        double cur = 0.0, rm = 0.0;
-#pragma unroll
-        for (int c = 0; c < M; c++) {
-            if (s_mach[jb + c] >= 0) {  // scheduled ops form a prefix of the job
-                cur = s_ft[jb + c];
-                rm = fmax(rm, cur);
-                nx = c + 1;
-            } else {
-                const double st0 = (c == 0) ? 0.0 : cur;
-                s_st[jb + c] = st0;
-                cur = st0 + s_mind[jb + c];
-                s_ft[jb + c] = cur;
-            }
-            jmx = fmax(jmx, cur);
-        }
-        vj = (nx == M) ? INFINITY : rm;
-    }
-    __syncwarp();
+    // ---- estimated energy per op (SS:1995, 2175); lanes keep their own ops in registers ----
     double ept[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; it++) {
         const int v = gl + it * G;
         ept[it] = 0.0;
         if (v < N) {
-            ept[it] = (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_minpt[v];
-            s_pt[v] = ept[it];
+            ept[it] = (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_psel[v];
+            if (MODE & MODE_STEP) s_pt[v] = ept[it];
         }
+    }
+    // per job (lane j): ops scheduled so far, ESA key = finish of its last scheduled op, row maximum
+    int nx = 0;
+    double vj = INFINITY, jmx = -INFINITY;
+    if (gl < J) {
+        nx = s_nxt[gl];
+        const double lastft = s_ft[gl * M + (nx > 0 ? nx - 1 : 0)];
+        vj = (nx == M) ? INFINITY : (nx > 0 ? lastft : 0.0);
+        jmx = s_ft[gl * M + M - 1];  // times are non-decreasing along a job (t >= 0, tt >= 0)
     }
     __syncwarp();
 
     if (MODE & MODE_STEP) {
-        mkv = gmax_d<G>(jmx);  // SS:894 (estimates are non-decreasing along a job; jmx is the row maximum)
-        if constexpr (N <= 128) {  // one numpy leaf: 8 accumulators, then the tail
+        const double mkv = gmax_d<G>(jmx);  // SS:894
+        double en;
+        if constexpr (N <= 128) {  // one numpy leaf: 8 accumulators, then the tail (SS:896)
             constexpr int NB = (N >= 8) ? N - (N & 7) : 0;
             const int k = gl & 7;
             double r = 0.0;
@@ -935,13 +967,14 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
         if (valid) {  // selective write-back: 4 scalars, macc[m][3], 13 scaler words
 #pragma unroll
             for (int i = gl; i < 20; i += G) {
-                const int idx = i < 4 ? S::O_SCAL + i : i < 7 ? S::O_MACC + mc * 3 + (i - 4) : S::O_SC + (i - 7);
-                g_sd[idx] = s_sd[idx];
+                if (i < 4) g_sd[S::O_SCAL + i] = s_scal[i];
+                else if (i < 7) g_sd[S::O_MACC + mc * 3 + (i - 4)] = s_macc[mc * 3 + (i - 4)];
+                else g_sd[S::O_SC + (i - 7)] = s_sc[i - 7];
             }
         }
     }
 
-    // ---- job mask + candidates ----
+    // ---- job mask + candidates (ppo_algorithm.py:202-317) ----
     {
         const unsigned bal0 = __ballot_sync(FULL, gl < J && nx == 0);
         const unsigned bal1 = __ballot_sync(FULL, gl < J && nx < M);
@@ -967,7 +1000,7 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
     if (MODE & MODE_OBS) {
         const int rem_head = s_misc[0], fresh = s_misc[1];
         OutT* tf = reinterpret_cast<OutT*>(P.tfea);
-        const double w0 = s_w[0], w1 = s_w[1], w2 = s_w[2];
+        const OutT w0 = (OutT)s_w[0], w1 = (OutT)s_w[1], w2 = (OutT)s_w[2];
 #pragma unroll
         for (int it = 0; it < ITER; it++) {
             const int v = gl + it * G;
@@ -979,32 +1012,41 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
                 const bool co = has_job && rp == v - 1;
                 const bool has_m = rp >= 0 && !co;
                 if (sch && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
+                const double stv = s_st[v], ftv = s_ft[v], durv = s_dur[v];
                 if (tf && active) {  // SS:2246-2277
-                    double f[12];
-                    f[0] = s_st[v]; f[1] = s_ft[v]; f[2] = ept[it];
-                    f[3] = sch ? 1.0 : 0.0;
-                    f[4] = (double)((vfirst ? 1 : 0) + (has_job ? 1 : 0) + (has_m ? 1 : 0));
-                    f[5] = sch ? (double)(mv + 1) : 0.0;
-                    f[6] = sch ? s_dur[v] : 0.0;
-                    f[7] = sch ? s_psel[v] : 0.0;
-                    f[8] = (double)(v / M + 1);
-                    f[9] = w0; f[10] = w1; f[11] = w2;
-                    store_row<OutT>(tf + ((size_t)b * N + v) * 12, f, 12);
+                    const int indeg = (vfirst ? 1 : 0) + (has_job ? 1 : 0) + (has_m ? 1 : 0);
+                    OutT* row = tf + ((size_t)b * N + v) * 12;
+                    if constexpr (sizeof(OutT) == 4) {
+                        float4* r4 = reinterpret_cast<float4*>(row);
+                        r4[0] = make_float4((float)stv, (float)ftv, (float)ept[it], sch ? 1.f : 0.f);
+                        r4[1] = make_float4((float)indeg, (float)(mv + 1), (float)durv, sch ? (float)s_psel[v] : 0.f);
+                        r4[2] = make_float4((float)(v / M + 1), w0, w1, w2);
+                    } else {
+                        double2* r2 = reinterpret_cast<double2*>(row);
+                        r2[0] = make_double2(stv, ftv);
+                        r2[1] = make_double2(ept[it], sch ? 1.0 : 0.0);
+                        r2[2] = make_double2((double)indeg, (double)(mv + 1));
+                        r2[3] = make_double2(durv, sch ? s_psel[v] : 0.0);
+                        r2[4] = make_double2((double)(v / M + 1), w0);
+                        r2[5] = make_double2(w1, w2);
+                    }
                 }
                 if (P.adj_w && active) {  // SS:2019-2073 in compact ELL form
                     double wj = 0.0, wm = 0.0;
                     int src = -1;
                     if (has_job) {
                         const int u = v - 1, mu = s_mach[u];
+                        const double du = s_dur[u];
                         double w;
-                        if (fresh == v) w = s_dur[u] + s_tt[mu * M + mv] + (s_st[v] - s_ft[u]);
-                        else if (s_dur[u] != 0.0) w = s_dur[u] + ((mu >= 0 && sch) ? s_tt[mu * M + mv] : 0.0);
-                        else w = 1.0;
-                        wj = adj_val(w, mu >= 0, s_dur[u]);
+                        if (fresh == v) w = du + s_tt[mu * M + mv] + (stv - s_ft[u]);                 // SS:1764 / 1644
+                        else if (du != 0.0) w = du + ((mu >= 0 && sch) ? s_tt[mu * M + mv] : 0.0);   // SS:1392-1422
+                        else w = 1.0;                                                                  // SS:625,642
+                        wj = adj_val_t(w, mu >= 0, du);
                     }
                     if (has_m) {
-                        const double w = s_dur[rp] + ((rp / M == v / M) ? s_tt[mv * M + mv] : 0.0) + (s_st[v] - s_ft[rp]);
-                        wm = adj_val(w, true, s_dur[rp]);
+                        const double dr = s_dur[rp];
+                        const double w = dr + ((rp / M == v / M) ? s_tt[mv * M + mv] : 0.0) + (stv - s_ft[rp]);
+                        wm = adj_val_t(w, true, dr);
                         if (wm != 0.0) src = rp;
                     }
                     reinterpret_cast<float2*>(P.adj_w)[(size_t)b * N + v] = make_float2((float)wj, (float)wm);
@@ -1020,7 +1062,7 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
             f[0] = c > 0 ? s_ft[s_tail[gl]] : 0.0;
             f[1] = s_macc[gl * 3 + 0]; f[2] = s_macc[gl * 3 + 1]; f[3] = s_macc[gl * 3 + 2];
             f[4] = (double)c;
-            f[5] = w0; f[6] = w1; f[7] = w2;
+            f[5] = s_w[0]; f[6] = s_w[1]; f[7] = s_w[2];
             store_row<OutT>(mf + ((size_t)b * M + gl) * 8, f, 8);
         }
     }
@@ -1387,7 +1429,8 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     L.o_w = L.o_macc + 3 * M; L.o_sc = L.o_w + 3;
     L.sd_stride = align_up(L.o_sc + 13, 2);
     L.o_mach = 0; L.o_pos = N; L.o_rpred = 2 * N; L.o_cnt = 3 * N; L.o_misc = 3 * N + M;
-    L.si_stride = align_up(L.o_misc + 3, 8);
+    L.o_nxt = L.o_misc + 3;
+    L.si_stride = align_up(L.o_nxt + J, 8);
     L.o_mind = 0; L.o_minpt = N; L.o_tt = 2 * N;
     L.xs_stride = align_up(2 * N + M * M, 2);
     int off = 0;
