@@ -1226,6 +1226,124 @@ __global__ void policy_kernel(Layout L, const double* __restrict__ t, const int1
     mach[b] = mm;
 }
 
+// Size-templated pre-step kernel: (optionally) the random policy and the candidate-machine features of the
+// chosen op in one pass; the op's t / p rows are read once into registers.  One thread per env.
+template <int M, typename OutT, bool POLICY>
+__global__ void __launch_bounds__(128) prestep_kernel(Layout L, const double* __restrict__ t, const double* __restrict__ p,
+                                                      const double* __restrict__ xs, const int16_t* __restrict__ si,
+                                                      const int8_t* __restrict__ edge_id, const uint8_t* __restrict__ jm,
+                                                      const int32_t* __restrict__ cand, uint64_t seed, uint64_t env_offset,
+                                                      int32_t* op, int32_t* mach, OutT* out, uint8_t* mmask) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.B) return;
+    const int N = L.N, J = L.J;
+    int a;
+    uint64_t step = 0;
+    if (POLICY) {
+        const uint8_t* mk = jm + (size_t)b * J;
+        int n = 0;
+        for (int j = 0; j < J; j++) n += !mk[j];
+        if (n == 0) { op[b] = -1; mach[b] = -1; return; }
+        step = (uint64_t)si[(size_t)b * L.si_stride + L.o_misc + 2];
+        int k = (int)(((uint64_t)rand_u32(seed, env_offset + b, step, 0) * (uint64_t)n) >> 32);
+        a = -1;
+        for (int j = 0; j < J; j++)
+            if (!mk[j]) {
+                if (k == 0) { a = cand[(size_t)b * J + j]; break; }
+                k--;
+            }
+        op[b] = a;
+    } else {
+        a = op[b];
+    }
+    const bool bad = a < 0 || a >= N;
+    const int ar = bad ? 0 : a;
+    double tr[M], pr[M];
+    {
+        const double* trow = t + ((size_t)b * N + ar) * M;
+        const double* prow = p + ((size_t)b * N + ar) * M;
+        if constexpr (M % 2 == 0) {
+#pragma unroll
+            for (int m = 0; m < M; m += 2) {
+                const double2 tv = __ldg(reinterpret_cast<const double2*>(trow + m));
+                const double2 pv = __ldg(reinterpret_cast<const double2*>(prow + m));
+                tr[m] = tv.x; tr[m + 1] = tv.y; pr[m] = pv.x; pr[m + 1] = pv.y;
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < M; m++) { tr[m] = __ldg(trow + m); pr[m] = __ldg(prow + m); }
+        }
+    }
+    if (POLICY) {
+        int nf = 0;
+#pragma unroll
+        for (int m = 0; m < M; m++) nf += (tr[m] >= 0);
+        int km = (int)(((uint64_t)rand_u32(seed, env_offset + b, step, 1) * (uint64_t)nf) >> 32);
+        int mm = -1;
+#pragma unroll
+        for (int m = 0; m < M; m++)
+            if (tr[m] >= 0) {
+                if (km == 0 && mm < 0) mm = m;
+                km--;
+            }
+        mach[b] = mm;
+    }
+    if (!out) return;
+    if (bad) {
+        for (int k = 0; k < M * 6; k++) out[(size_t)b * M * 6 + k] = (OutT)0;
+        if (mmask)
+            for (int m = 0; m < M; m++) mmask[(size_t)b * M + m] = 1;
+        return;
+    }
+    // means over the positive entries, numpy pairwise order on the compacted row (parallel_env.py:177-184)
+    double ct[M], cpt[M], cp[M];
+    int nt = 0, npt = 0, npp = 0;
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        const double ptm = tr[m] * fabs(pr[m]);
+        if (tr[m] > 0) ct[nt++] = tr[m];
+        if (ptm > 0) cpt[npt++] = ptm;
+        if (pr[m] > 0) cp[npp++] = pr[m];
+    }
+    const double mean_t = np_sum_small(ct, nt) / (double)nt;
+    const double mean_pt = np_sum_small(cpt, npt) / (double)npt;
+    const double mean_p = np_sum_small(cp, npp) / (double)npp;
+    int pm_row = M - 1;  // int(tfea[a-1][5]) - 1 wraps to the last row while the predecessor is unscheduled
+    if (a % M != 0) {
+        const int mp = si[(size_t)b * L.si_stride + L.o_mach + a - 1];
+        if (mp >= 0) pm_row = mp;
+    }
+    const double* ttrow = xs + (size_t)b * L.xs_stride + L.o_tt + pm_row * M;
+    OutT f[M * 6];
+    uint8_t msk[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        const double tm = tr[m], pm = pr[m], ptm = tm * fabs(pm);
+        const int infeasible = !(tm >= 0);
+        f[m * 6 + 0] = (OutT)(tm > 0 ? tm : mean_t);
+        f[m * 6 + 1] = (OutT)(ptm > 0 ? ptm : mean_pt);
+        f[m * 6 + 2] = (OutT)((a % M == 0) ? 0.0 : __ldg(ttrow + m));
+        f[m * 6 + 3] = (OutT)(1 - infeasible);
+        f[m * 6 + 4] = (OutT)(pm > 0 ? pm : mean_p);
+        f[m * 6 + 5] = (OutT)edge_id[(size_t)b * M + m];
+        msk[m] = (uint8_t)infeasible;
+    }
+    OutT* o = out + (size_t)b * M * 6;
+    if constexpr ((M * 6 * sizeof(OutT)) % 16 == 0) {
+        constexpr int PER = 16 / sizeof(OutT);
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+        for (int k = 0; k < M * 6 / PER; k++) o4[k] = *reinterpret_cast<const uint4*>(&f[k * PER]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < M * 6; k++) o[k] = f[k];
+    }
+    if (mmask) {
+#pragma unroll
+        for (int m = 0; m < M; m++) mmask[(size_t)b * M + m] = msk[m];
+    }
+}
+
 template <typename OutT>
 __global__ void dense_adj_kernel(Layout L, const float* __restrict__ adj_w, const int16_t* __restrict__ adj_src,
                                  OutT* adj) {
@@ -1406,6 +1524,34 @@ static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
         if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 4>, MODE, OutT>(h, P, s);
     }
     return launch_env<MODE, OutT>(h, P, s);
+}
+
+// pre-step dispatch: returns 1 if a size-templated kernel was launched, 0 if the size has none, <0 on error
+template <bool POLICY>
+static int launch_prestep(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, const uint8_t* jm, int32_t* op,
+                          int32_t* mach, void* out, uint8_t* mmask, int dtype, cudaStream_t s) {
+    if (h->force_generic) return 0;
+    const Layout& L = h->L;
+    const unsigned blocks = (unsigned)((L.B + 127) / 128);
+#define PRESTEP(MM)                                                                                                  \
+    if (L.M == MM) {                                                                                                 \
+        if (dtype == MTFJSP_F64)                                                                                     \
+            prestep_kernel<MM, double, POLICY><<<blocks, 128, 0, s>>>(L, h->t, h->p, h->xs, h->si, h->edge_id, jm,    \
+                                                                     h->cand, seed, env_offset, op, mach,            \
+                                                                     (double*)out, mmask);                           \
+        else                                                                                                         \
+            prestep_kernel<MM, float, POLICY><<<blocks, 128, 0, s>>>(L, h->t, h->p, h->xs, h->si, h->edge_id, jm,     \
+                                                                    h->cand, seed, env_offset, op, mach, (float*)out, \
+                                                                    mmask);                                          \
+        h->launches++;                                                                                               \
+        CK(cudaGetLastError(), "prestep_kernel");                                                                    \
+        return 1;                                                                                                    \
+    }
+    PRESTEP(6)
+    PRESTEP(10)
+    PRESTEP(20)
+#undef PRESTEP
+    return 0;
 }
 
 extern "C" {
@@ -1606,6 +1752,11 @@ int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_ma
     CK(cudaSetDevice(h->device), "cudaSetDevice");
     const Layout& L = h->L;
     cudaStream_t s = (cudaStream_t)stream;
+    if (dtype != MTFJSP_F32 && dtype != MTFJSP_F64) return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
+    {
+        int rc = launch_prestep<false>(h, 0, 0, nullptr, const_cast<int32_t*>(op), nullptr, mfea1, mach_mask, dtype, s);
+        if (rc != 0) return rc < 0 ? rc : MTFJSP_OK;
+    }
     unsigned blocks = (unsigned)((L.B + 127) / 128);
     if (dtype == MTFJSP_F64)
         mfea1_kernel<double><<<blocks, 128, 0, s>>>(L, h->t, h->p, h->xs, h->si, h->edge_id, op, (double*)mfea1, mach_mask);
@@ -1686,11 +1837,19 @@ int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_
     if (!h) return fail(MTFJSP_E_ARG, "null handle");
     int32_t* o = op ? op : h->a_op;
     int32_t* mc = mach ? mach : h->a_mach;
-    int rc = mtfjsp_policy_random(h, seed, env_offset, mask_mode, o, mc, stream);
-    if (rc) return rc;
-    if (mfea1) {
-        rc = mtfjsp_mfea1(h, o, mfea1, mach_mask, dtype, stream);
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_random_step before mtfjsp_reset");
+    if (dtype != MTFJSP_F32 && dtype != MTFJSP_F64) return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    int rc = launch_prestep<true>(h, seed, env_offset, mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin, o, mc, mfea1,
+                                  mach_mask, dtype, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+        rc = mtfjsp_policy_random(h, seed, env_offset, mask_mode, o, mc, stream);
         if (rc) return rc;
+        if (mfea1) {
+            rc = mtfjsp_mfea1(h, o, mfea1, mach_mask, dtype, stream);
+            if (rc) return rc;
+        }
     }
     return mtfjsp_step_obs(h, o, mc, reward5, scaled4, done, invalid, task_fea, mach_fea, adj_w, adj_src, job_mask,
                            candidate, mask_mode, dtype, stream);
