@@ -160,14 +160,14 @@ def run_ours(args, wl):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    pkg = importlib.import_module("e2e-mappo-for-mt-fjsp_b200")
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
-    ins = pkg.instances
+    sh = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.sharding")
     J, M, E, B = wl["J"], wl["M"], wl["E"], args.batch or wl["B"]
     N = J * M
-    first = rank * B  # weak scaling: env i of the job lives on rank i // B
-    d = ins.synthetic_instances(first, B, J, M, E, wl["seed"])
-    w = torch.as_tensor(ins.random_weights(first, B, wl["seed"])).to(dev)
+    # weak scaling: B envs per GPU, env i of the B*world job lives on rank i // B (contiguous slices)
+    first, count, d, w = sh.make_shard(B * world, rank, world, J, M, E, wl["seed"])
+    assert count == B and first == rank * B
+    w = torch.as_tensor(w).to(dev)
     env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32, mask_mode=envm.MASK_ESA)
     env.load(d["t"], d["p"], d["transT"], d["edge"])
     env.scaler_init()
@@ -205,10 +205,7 @@ def run_ours(args, wl):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = env.launch_count - l0
-    if world > 1:
-        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
+    ms = sh.max_over_ranks(ms, dev)
     value = B * world * K / (ms * 1e-3)
 
     # ---- dominant kernel alone: fused step+obs launches replaying recorded actions (device resident) ----
@@ -259,13 +256,11 @@ def run_ours(args, wl):
     e2e_steps(Ke)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_s = float(tm.item())
+    e2e_s = sh.max_over_ranks(e2e_s, dev)
     e2e_val = B * world * Ke / e2e_s
     assert float(info6[:, 1].sum()) in (0.0, float(B))
     clocks = sampler.stop() if sampler else None
+    stats = sh.reduce_episode_stats(env.costs(), device=dev)  # the rollout side's only other exchange (6 doubles)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -280,7 +275,7 @@ def run_ours(args, wl):
             "config": {"workload": wl["name"], "envs_per_gpu": B, "jobs": J, "machines": M, "edges": E, "obs_dtype": "f32",
                        "mask_mode": "ESA", "left_shift": True, "parallelism": "env-slices x%d (no data-path collective)" % world,
                        "l2": "working set %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (B * (bytes_step + 2000) / 1e6),
-                       "launches_per_step": 3},
+                       "launches_per_step": 2, "kernels": "prestep_kernel (policy + candidate-machine features), env_kernel_s (step + reward + obs + mask)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * (48 + 5 * J),
                     "api": "mtfjsp_step_host (C ABI, pinned host buffers; observation tensors stay on the device)",
                     "steps": Ke},
@@ -290,6 +285,7 @@ def run_ours(args, wl):
                          "bytes_per_env_step": bytes_step, "peak_source": peak_src,
                          "steps_per_s_kernel_only": B / (k_us * 1e-6)},
             "clocks": clocks,
+            "episode_stats": {k: float(v) for k, v in stats.items()},
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -301,7 +297,7 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=360)
+    ap.add_argument("--steps", type=int, default=3600)
     ap.add_argument("--warmup", type=int, default=36)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))

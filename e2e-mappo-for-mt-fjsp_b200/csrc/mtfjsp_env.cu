@@ -601,7 +601,7 @@ struct Spec {
     static constexpr int O_ST = 0, O_FT = N, O_DUR = 2 * N, O_PSEL = 3 * N, O_SCAL = 4 * N, O_MACC = 4 * N + 4,
                          O_W = O_MACC + 3 * M, O_SC = O_W + 3;
     static constexpr int O_MACH = 0, O_POS = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
-    static constexpr int O_MIND = 0, O_MINPT = N, O_TT = 2 * N;
+    static constexpr int O_MIND = 0, O_TT = 2 * N;
     static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 2) * 8, B_SI = SI * 2,
                          B_TAIL = calign(M, 8) * 2, B_LEAF = (N > 128) ? (MAX_LEAVES + 32) * 8 : 0;
     static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_LEAF + B_SI + B_TAIL, 16);
@@ -1380,14 +1380,17 @@ __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
     if (gid < n) p[gid] = v;
 }
 
-__global__ void costs_kernel(Layout L, const double* __restrict__ sd, double* cost4) {
+__global__ void costs_kernel(Layout L, const double* __restrict__ sd, double* cost4, double* total_e1) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= (size_t)L.B) return;
     const double* s = sd + b * L.sd_stride + L.o_scal;
-    cost4[b * 4 + 0] = s[0];
-    cost4[b * 4 + 1] = s[1] / (double)L.N;
-    cost4[b * 4 + 2] = s[2];
-    cost4[b * 4 + 3] = s[3];
+    if (cost4) {
+        cost4[b * 4 + 0] = s[0];
+        cost4[b * 4 + 1] = s[1] / (double)L.N;
+        cost4[b * 4 + 2] = s[2];
+        cost4[b * 4 + 3] = s[3];
+    }
+    if (total_e1) total_e1[b] = s[1];
 }
 
 __global__ void export_scaler_kernel(Layout L, const double* __restrict__ sd, double* R, double* mean, double* S,
@@ -1783,10 +1786,10 @@ int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream) {
     return MTFJSP_OK;
 }
 
-int mtfjsp_costs(mtfjsp_env* h, double* cost4, void* stream) {
-    if (!h || !cost4) return fail(MTFJSP_E_ARG, "mtfjsp_costs: bad argument");
+int mtfjsp_costs(mtfjsp_env* h, double* cost4, double* total_e1, void* stream) {
+    if (!h || (!cost4 && !total_e1)) return fail(MTFJSP_E_ARG, "mtfjsp_costs: bad argument");
     CK(cudaSetDevice(h->device), "cudaSetDevice");
-    costs_kernel<<<(h->L.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->L, h->sd, cost4);
+    costs_kernel<<<(h->L.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->L, h->sd, cost4, total_e1);
     h->launches++;
     CK(cudaGetLastError(), "costs_kernel");
     return MTFJSP_OK;

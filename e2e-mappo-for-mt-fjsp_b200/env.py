@@ -157,10 +157,11 @@ class BatchedMTFJSPEnv:
         check(self._lib.mtfjsp_dense_adj(self._h, _ptr(adj), F64 if dtype == torch.float64 else F32, _stream()), "mtfjsp_dense_adj")
         return adj
 
-    def costs(self):
+    def costs(self, with_total_e1=False):
         c = torch.empty((self.B, 4), dtype=torch.float64, device=self.device)
-        check(self._lib.mtfjsp_costs(self._h, _ptr(c), _stream()), "mtfjsp_costs")
-        return c
+        e1 = torch.empty((self.B,), dtype=torch.float64, device=self.device) if with_total_e1 else None
+        check(self._lib.mtfjsp_costs(self._h, _ptr(c), _ptr(e1), _stream()), "mtfjsp_costs")
+        return (c, e1) if with_total_e1 else c
 
     def export_state(self):
         dev, B, N, M = self.device, self.B, self.N, self.M

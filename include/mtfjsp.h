@@ -105,8 +105,9 @@ int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_ma
 int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream);
 
 /* replaces: reading env.makespan_previous_step, total_e1_previous_step/N, trans_t_previous_step,
- * idle_t_previous_step (Run.py:632-633, trainer/validate.py:273-277).  cost4 [B,4] f64 (mk, pt/N, tt, idle). */
-int mtfjsp_costs(mtfjsp_env* h, double* cost4, void* stream);
+ * idle_t_previous_step (Run.py:632-633, trainer/validate.py:273-277).  cost4 [B,4] f64 (mk, pt/N, tt, idle);
+ * total_e1 [B] f64 = the undivided total_e1_previous_step.  Either may be NULL. */
+int mtfjsp_costs(mtfjsp_env* h, double* cost4, double* total_e1, void* stream);
 
 /* parity checks / rendering: machine assignment (-1 unassigned) [B,N] i32, start / finish [B,N] f64 (0 while
  * unscheduled), machine routes [B,M,N] i32 padded with -1 (replaces env.machine_routes, env.G.nodes[...]). */
