@@ -1,0 +1,84 @@
+// mtfjsp_encoder.cu -- encoder-side kernels for sm_100a: batched adjacency aggregation over the compact ELL
+// adjacency the env kernel emits (no [B*N, B*N] COO matrix, no cuSPARSE).
+//
+// Replaces (reference file:line):
+//   model/actor_critic.py:139-140, 155-156   dense adj -> to_sparse -> aggr_obs block-diagonal COO   (eliminated)
+//   model/gcn_mlp.py:125                     torch.mm(Adj.double(), h.double())                       weighted neighbour sum, FP64
+//   model/gcn_mlp.py:133-149                 degree via a second SpMM with ones                       fused (slot count)
+//   model/gcn_mlp.py:192                     torch.sparse.mm(graph_pool, h)                           per-env mean over nodes
+//
+// Numerics follow the reference: products and the row sum are FP64, accumulated in ascending source index (the
+// order of a coalesced COO row), divided by the in-degree including self, then rounded once to FP32.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mtfjsp.h"
+
+namespace {
+
+// one thread per (row, 4 channels): out[row] = (h[row] + wj*h[row-1] + wm*h[src]) / deg
+__global__ void __launch_bounds__(256) aggregate_kernel(const float4* __restrict__ h, const float2* __restrict__ adj_w,
+                                                        const int16_t* __restrict__ adj_src, float4* __restrict__ out,
+                                                        long long rows, int N, int C4) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * C4) return;
+    const long long row = idx / C4;
+    const int c = (int)(idx - row * C4);
+    const int v = (int)(row % N);
+    const long long base = row - v;  // first row of this env
+    const float2 w = __ldg(adj_w + row);
+    const int src = __ldg(adj_src + row);
+    // up to three (source, weight) pairs in ascending source order: v-1 < v always; src anywhere
+    int s[3];
+    double ww[3];
+    int n = 0;
+    const bool hj = w.x != 0.f, hm = src >= 0;
+    if (hm && src < v - 1) { s[n] = src; ww[n++] = (double)w.y; }
+    if (hj) { s[n] = v - 1; ww[n++] = (double)w.x; }
+    if (hm && src == v - 1 && !hj) { s[n] = src; ww[n++] = (double)w.y; }
+    s[n] = v; ww[n++] = 1.0;
+    if (hm && src > v) { s[n] = src; ww[n++] = (double)w.y; }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int k = 0; k < n; k++) {
+        const float4 x = __ldg(h + (base + s[k]) * C4 + c);
+        a0 += ww[k] * (double)x.x; a1 += ww[k] * (double)x.y; a2 += ww[k] * (double)x.z; a3 += ww[k] * (double)x.w;
+    }
+    const double deg = (double)n;
+    out[idx] = make_float4((float)(a0 / deg), (float)(a1 / deg), (float)(a2 / deg), (float)(a3 / deg));
+}
+
+// per-env mean over the N node rows (graph_pool average): one block per env, thread per channel
+__global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict__ out, int N, int C) {
+    const long long b = blockIdx.x;
+    const float inv = 1.0f / (float)N;  // the reference multiplies each row by the float32 value 1/N and sums
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int v = 0; v < N; v++) acc += inv * h[(b * N + v) * C + c];
+        out[b * C + c] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_src, float* out, int64_t B, int N,
+                         int C, void* stream) {
+    if (!h || !adj_w || !adj_src || !out || B < 1 || N < 1 || C < 4 || (C % 4) != 0) return MTFJSP_E_ARG;
+    const long long rows = (long long)B * N;
+    const int C4 = C / 4;
+    const long long total = rows * C4;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(h),
+                                                               reinterpret_cast<const float2*>(adj_w), adj_src,
+                                                               reinterpret_cast<float4*>(out), rows, N, C4);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, void* stream) {
+    if (!h || !out || B < 1 || N < 1 || C < 1) return MTFJSP_E_ARG;
+    graph_mean_kernel<<<(unsigned)B, C < 128 ? 32 * ((C + 31) / 32) : 128, 0, (cudaStream_t)stream>>>(h, out, N, C);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+"""GNN encoder + actor heads of the MAPPO rollout on the device.
+
+Forward-only mirrors of the reference networks that consume the environment's native observation layout directly
+(compact ELL adjacency, F32 feature rows), with the reference's state_dict key names so shipped checkpoints load:
+
+    JobActor      <- model/actor_critic.py:26-296   Operation_Actor_JointAction_selfCritic
+                     (GIN-style encoder model/gcn_mlp.py:109-197, 204-249; MLPActor / MLPCritic :322-434)
+    MachineActor  <- model/actor_critic.py:299-498  Machine_Actor_JointAction_selfGAT_selfCritic
+                     (GAT layer model/gat.py:68-159 over the fixed 2-node graph [[1,1],[0,1]])
+
+What runs where (round 1): the neighbour aggregation (reference: dense adj -> COO -> FP64 cuSPARSE SpMM -> second
+SpMM for the degree) is the hand-written `mtfjsp_enc_aggregate` kernel over ELL; graph pooling is
+`mtfjsp_enc_graph_mean`; the 2x2 GAT attention is closed-form elementwise math; the dense per-node projections are
+plain library GEMMs (`torch.nn.functional.linear` -> cuBLAS) and BatchNorm uses batch statistics exactly as the
+reference does (its modules are never put in eval mode).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def aggregate(h, adj_w, adj_src):
+    """out[b,v] = (h[b,v] + w_job*h[b,v-1] + w_mach*h[b,src]) / in_degree (FP64 accumulate); h [B,N,C] f32."""
+    B, N, Cc = h.shape
+    h = h.contiguous()
+    out = torch.empty_like(h)
+    check(_lib.lib().mtfjsp_enc_aggregate(_ptr(h), _ptr(adj_w), _ptr(adj_src), _ptr(out), B, N, Cc, _stream()),
+          "mtfjsp_enc_aggregate")
+    return out
+
+
+def graph_mean(h):
+    B, N, Cc = h.shape
+    h = h.contiguous()
+    out = torch.empty((B, Cc), dtype=h.dtype, device=h.device)
+    check(_lib.lib().mtfjsp_enc_graph_mean(_ptr(h), _ptr(out), B, N, Cc, _stream()), "mtfjsp_enc_graph_mean")
+    return out
+
+
+def job_actor_keys(hidden=128, in_dim=12):
+    """state_dict layout of the reference job actor (read off the shipped tester/IoTJ_MAPPO/*.pth)."""
+    H = hidden
+    k = {"_input": (H,)}
+    for l, din in ((0, in_dim), (1, H)):
+        p = "encoder.feature_extract.mlps.%d." % l
+        k[p + "linears.0.weight"] = (H, din); k[p + "linears.0.bias"] = (H,)
+        for i in (1, 2):
+            k[p + "linears.%d.weight" % i] = (H, H); k[p + "linears.%d.bias" % i] = (H,)
+        for i in (0, 1):
+            for n, s in (("weight", (H,)), ("bias", (H,)), ("running_mean", (H,)), ("running_var", (H,)),
+                         ("num_batches_tracked", ())):
+                k[p + "batch_norms.%d.%s" % (i, n)] = s
+    for name, d in (("encoder.feature_extract.bn.", in_dim), ("encoder.feature_extract.batch_norms.0.", H),
+                    ("encoder.feature_extract.batch_norms.1.", H)):
+        for n, s in (("weight", (d,)), ("bias", (d,)), ("running_mean", (d,)), ("running_var", (d,)),
+                     ("num_batches_tracked", ())):
+            k[name + n] = s
+    k["o_policy.linears.0.weight"] = (H, 3 * H); k["o_policy.linears.0.bias"] = (H,)
+    k["o_policy.linears.1.weight"] = (H, H); k["o_policy.linears.1.bias"] = (H,)
+    k["o_policy.linears.2.weight"] = (1, H); k["o_policy.linears.2.bias"] = (1,)
+    k["job_critic.linears.0.weight"] = (H, H); k["job_critic.linears.0.bias"] = (H,)
+    k["job_critic.linears.1.weight"] = (H, H); k["job_critic.linears.1.bias"] = (H,)
+    k["job_critic.linears.2.weight"] = (2, H); k["job_critic.linears.2.bias"] = (2,)
+    return k
+
+
+def machine_actor_keys(hidden=128):
+    H = hidden
+    k = {}
+    for n, s in (("weight", (H,)), ("bias", (H,)), ("running_mean", (H,)), ("running_var", (H,)), ("num_batches_tracked", ())):
+        k["bn." + n] = s
+    k["m_fea_1_fcl.weight"] = (H, 6); k["m_fea_2_fcl.weight"] = (H, 8)
+    k["gat_layer.W"] = (H, H); k["gat_layer.a"] = (1, 2 * H, 1)
+    k["fcl_pooling.weight"] = (H, H)
+    k["m_policy.linears.0.weight"] = (H, 3 * H); k["m_policy.linears.0.bias"] = (H,)
+    k["m_policy.linears.1.weight"] = (H, H); k["m_policy.linears.1.bias"] = (H,)
+    k["m_policy.linears.2.weight"] = (1, H); k["m_policy.linears.2.bias"] = (1,)
+    k["machine_critic.linears.0.weight"] = (H, H); k["machine_critic.linears.0.bias"] = (H,)
+    k["machine_critic.linears.1.weight"] = (H, H); k["machine_critic.linears.1.bias"] = (H,)
+    k["machine_critic.linears.2.weight"] = (2, H); k["machine_critic.linears.2.bias"] = (2,)
+    return k
+
+
+def seeded_state_dict(keys: dict, seed: int):
+    """Deterministic weights for parity fixtures: the same call feeds the reference module (in the build container)
+    and this module (on the GPU box), so no checkpoint has to be shipped with the tests."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+    for name, shape in keys.items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(0, dtype=torch.int64)
+        elif name.endswith("running_var"):
+            sd[name] = torch.ones(shape, dtype=torch.float32)
+        elif name.endswith("running_mean"):
+            sd[name] = torch.zeros(shape, dtype=torch.float32)
+        elif ".batch_norms." in name or name.startswith("bn.") or ".bn." in name:
+            v = rs.uniform(0.5, 1.5, size=shape) if name.endswith("weight") else rs.uniform(-0.2, 0.2, size=shape)
+            sd[name] = torch.tensor(v, dtype=torch.float32)
+        else:
+            fan_in = shape[-1] if len(shape) > 1 else max(shape[0], 1)
+            if name == "gat_layer.a":
+                fan_in = shape[1]
+            sd[name] = torch.tensor(rs.standard_normal(size=shape) / np.sqrt(fan_in), dtype=torch.float32)
+    return sd
+
+
+def _bn_train(x, w, b, eps=1e-5):
+    """BatchNorm1d with batch statistics (the reference never leaves train mode)."""
+    return F.batch_norm(x, None, None, w, b, True, 0.0, eps)
+
+
+class _Params:
+    def __init__(self, keys, state_dict, device):
+        missing = [k for k in keys if k not in state_dict]
+        extra = [k for k in state_dict if k not in keys]
+        if missing or extra:
+            raise KeyError("state_dict mismatch: missing %s unexpected %s" % (missing, extra))
+        self.p = {}
+        for k, shape in keys.items():
+            t = torch.as_tensor(state_dict[k])
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError("%s: shape %s, expected %s" % (k, tuple(t.shape), tuple(shape)))
+            self.p[k] = t.to(device=device, dtype=torch.float32 if t.is_floating_point() else t.dtype).contiguous()
+
+    def __getitem__(self, k):
+        return self.p[k]
+
+
+class JobActor:
+    """Forward of Operation_Actor_JointAction_selfCritic (model/actor_critic.py:104-296) on native observations."""
+
+    def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None):
+        self.J, self.M, self.N, self.H = n_job, n_machine, n_job * n_machine, hidden
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.w = _Params(job_actor_keys(hidden, in_dim), state_dict, self.device)
+
+    def _mlp(self, l, x):  # gcn_mlp.py:238-249
+        w = self.w
+        p = "encoder.feature_extract.mlps.%d." % l
+        h = x
+        for i in (0, 1):
+            h = F.linear(h, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i])
+            h = F.relu(_bn_train(h, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i]))
+        return F.linear(h, w[p + "linears.2.weight"], w[p + "linears.2.bias"])
+
+    def encode(self, task_fea, adj_w, adj_src):
+        """GraphCNN.forward (gcn_mlp.py:160-197): two rounds of aggregate -> MLP -> BN -> ReLU, then mean pooling.
+        task_fea [B,N,12] f32, adj_w [B,N,2] f32, adj_src [B,N] i16 -> (pooled [B,H], nodes [B,N,H])."""
+        B = task_fea.shape[0]
+        w = self.w
+        h = task_fea.to(torch.float32)
+        for l in (0, 1):
+            pooled = aggregate(h, adj_w, adj_src)                                   # gcn_mlp.py:125-149
+            z = self._mlp(l, pooled.reshape(B * self.N, -1))
+            z = F.relu(_bn_train(z, w["encoder.feature_extract.batch_norms.%d.weight" % l],
+                                 w["encoder.feature_extract.batch_norms.%d.bias" % l]))   # gcn_mlp.py:154-157
+            h = z.reshape(B, self.N, self.H)
+        return graph_mean(h), h                                                    # gcn_mlp.py:192
+
+    def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None):
+        """-> task_index [B], action_index [B] (job), log_a [B], prob [B,J], h_g_o_pooled [B,H], job_v [B,2]."""
+        w = self.w
+        B = task_fea.shape[0]
+        pooled, nodes = self.encode(task_fea, adj_w, adj_src)
+        cand = candidate.long()
+        cf = torch.gather(nodes, 1, cand.unsqueeze(-1).expand(-1, self.J, self.H))     # actor_critic.py:197-207
+        gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
+        x = torch.cat((cf, pooled.unsqueeze(-2).expand_as(cf), gm), dim=-1)              # actor_critic.py:244-247
+        s = torch.tanh(F.linear(x, w["o_policy.linears.0.weight"], w["o_policy.linears.0.bias"]))
+        s = torch.tanh(F.linear(s, w["o_policy.linears.1.weight"], w["o_policy.linears.1.bias"]))
+        s = F.linear(s, w["o_policy.linears.2.weight"], w["o_policy.linears.2.bias"]).squeeze(-1)
+        s = s.masked_fill(mask_operation.bool(), float("-inf"))                          # actor_critic.py:266-268
+        prob = F.softmax(s, dim=-1)
+        if greedy:                                                                       # agent_func.py greedy / sample
+            a = prob.argmax(dim=-1)
+        else:
+            a = torch.multinomial(prob, 1, generator=generator).squeeze(-1)
+        log_a = torch.log(prob.gather(1, a.unsqueeze(-1)).squeeze(-1))
+        task_index = cand.gather(1, a.unsqueeze(-1)).squeeze(-1)
+        v = torch.tanh(F.linear(pooled, w["job_critic.linears.0.weight"], w["job_critic.linears.0.bias"]))
+        v = torch.tanh(F.linear(v, w["job_critic.linears.1.weight"], w["job_critic.linears.1.bias"]))
+        job_v = F.linear(v, w["job_critic.linears.2.weight"], w["job_critic.linears.2.bias"])
+        return task_index, a, log_a, prob, pooled, job_v
+
+
+class MachineActor:
+    """Forward of Machine_Actor_JointAction_selfGAT_selfCritic (model/actor_critic.py:359-498)."""
+
+    def __init__(self, state_dict, n_machine, hidden=128, device=None):
+        self.M, self.H = n_machine, hidden
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.w = _Params(machine_actor_keys(hidden), state_dict, self.device)
+
+    def _gat(self, h1, h2):
+        """GATLayer.forward (gat.py:82-159) on the fixed 2-node graph: node 1 attends to {1, 2}, node 2 to itself."""
+        W, a = self.w["gat_layer.W"], self.w["gat_layer.a"]
+        H = self.H
+        t1, t2 = h1 @ W, h2 @ W
+        a_src, a_dst = a[0, :H, 0], a[0, H:, 0]
+        e11 = F.leaky_relu(t1 @ a_src + t1 @ a_dst, 0.2)
+        e12 = F.leaky_relu(t1 @ a_src + t2 @ a_dst, 0.2)
+        att = torch.softmax(torch.stack((e11, e12), dim=-1), dim=-1)
+        return att[..., 0:1] * t1 + att[..., 1:2] * t2, t2
+
+    def forward(self, machine_fea_1, machine_fea_2, h_pooled_o, machine_mask):
+        """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] f32, h_pooled_o [B,H], machine_mask [B,M] (1 = infeasible)
+        -> mch_prob [B,M], h_pooled [B,H], machine_v [B,2]."""
+        w = self.w
+        B = machine_fea_1.shape[0]
+        h1 = F.linear(machine_fea_1.to(torch.float32), w["m_fea_1_fcl.weight"]).reshape(B * self.M, self.H)
+        h2 = F.linear(machine_fea_2.to(torch.float32), w["m_fea_2_fcl.weight"]).reshape(B * self.M, self.H)
+        h1, h2 = self._gat(h1, h2)
+        h1, h2 = self._gat(F.elu(h1), F.elu(h2))
+        h1, h2 = self._gat(F.elu(h1), F.elu(h2))
+        hm = torch.stack((h1, h2), dim=1).mean(dim=-2)                                   # actor_critic.py:420
+        nodes = _bn_train(hm, w["bn.weight"], w["bn.bias"]).reshape(B, self.M, self.H)   # actor_critic.py:434
+        pooled = nodes.mean(dim=1)
+        x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
+        s = torch.tanh(F.linear(x, w["m_policy.linears.0.weight"], w["m_policy.linears.0.bias"]))
+        s = torch.tanh(F.linear(s, w["m_policy.linears.1.weight"], w["m_policy.linears.1.bias"]))
+        s = F.linear(s, w["m_policy.linears.2.weight"], w["m_policy.linears.2.bias"]).squeeze(-1) * 10
+        s = s.masked_fill(machine_mask.reshape(B, self.M).bool(), float("-inf"))
+        prob = F.softmax(s, dim=-1)
+        v = torch.tanh(F.linear(pooled, w["machine_critic.linears.0.weight"], w["machine_critic.linears.0.bias"]))
+        v = torch.tanh(F.linear(v, w["machine_critic.linears.1.weight"], w["machine_critic.linears.1.bias"]))
+        machine_v = F.linear(v, w["machine_critic.linears.2.weight"], w["machine_critic.linears.2.bias"])
+        return prob, pooled, machine_v

@@ -136,6 +136,15 @@ int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_
                      uint8_t* job_mask_host, int32_t* candidate_host, void* task_fea, void* mach_fea, float* adj_w,
                      int16_t* adj_src, int mask_mode, int dtype, void* stream);
 
+/* ---- encoder side --------------------------------------------------------------------------
+ * replaces: actor_critic.py:139-140 (dense adj -> sparse COO), gcn_mlp.py:125 (FP64 SpMM A*h) and :133-149 (degree
+ * SpMM): out[b,v,:] = (h[b,v,:] + adj_w[b,v,0]*h[b,v-1,:] + adj_w[b,v,1]*h[b,adj_src[b,v],:]) / in_degree, FP64
+ * accumulate, FP32 in/out.  h, out: [B,N,C] f32 (C % 4 == 0); adj_w / adj_src as written by mtfjsp_obs. */
+int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_src, float* out, int64_t B, int N,
+                         int C, void* stream);
+/* replaces: gcn_mlp.py:192 graph mean pooling; h [B,N,C] f32 -> out [B,C] f32. */
+int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, void* stream);
+
 /* Number of kernel launches issued through this handle so far (bench.py reports it). */
 int64_t mtfjsp_launch_count(const mtfjsp_env* h);
 /* Algorithmic bytes per env-step of the fused step+obs kernel for this handle's sizes. */
