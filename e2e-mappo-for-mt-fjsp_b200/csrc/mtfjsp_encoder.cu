@@ -19,7 +19,9 @@ namespace {
 // one thread per (row, 4 channels): out[row] = (h[row] + wj*h[row-1] + wm*h[src]) / deg
 __global__ void __launch_bounds__(256) aggregate_kernel(const float4* __restrict__ h, const float2* __restrict__ adj_w,
                                                         const int16_t* __restrict__ adj_src, float4* __restrict__ out,
-                                                        long long rows, int N, int C4) {
+                                                        long long rows, int N, int C4,
+                                                        const float4* __restrict__ in_scale,
+                                                        const float4* __restrict__ in_shift, int in_relu) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * C4) return;
     const long long row = idx / C4;
@@ -39,8 +41,14 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float4* __restrict
     s[n] = v; ww[n++] = 1.0;
     if (hm && src > v) { s[n] = src; ww[n++] = (double)w.y; }
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_scale) { sc = __ldg(in_scale + c); sh = __ldg(in_shift + c); }
     for (int k = 0; k < n; k++) {
-        const float4 x = __ldg(h + (base + s[k]) * C4 + c);
+        float4 x = __ldg(h + (base + s[k]) * C4 + c);
+        if (in_scale) {  // BatchNorm (+ReLU) of the producing layer, folded into the gather
+            x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+            if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        }
         a0 += ww[k] * (double)x.x; a1 += ww[k] * (double)x.y; a2 += ww[k] * (double)x.z; a3 += ww[k] * (double)x.w;
     }
     const double deg = (double)n;
@@ -48,12 +56,18 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float4* __restrict
 }
 
 // per-env mean over the N node rows (graph_pool average): one block per env, thread per channel
-__global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict__ out, int N, int C) {
+__global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict__ out, int N, int C,
+                                  const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu) {
     const long long b = blockIdx.x;
     const float inv = 1.0f / (float)N;  // the reference multiplies each row by the float32 value 1/N and sums
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float acc = 0.f;
-        for (int v = 0; v < N; v++) acc += inv * h[(b * N + v) * C + c];
+        const float sc = in_scale ? in_scale[c] : 1.f, sh = in_scale ? in_shift[c] : 0.f;
+        for (int v = 0; v < N; v++) {
+            float x = h[(b * N + v) * C + c];
+            if (in_scale) { x = x * sc + sh; if (in_relu) x = fmaxf(x, 0.f); }
+            acc += inv * x;
+        }
         out[b * C + c] = acc;
     }
 }
@@ -63,21 +77,27 @@ __global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict
 extern "C" {
 
 int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_src, float* out, int64_t B, int N,
-                         int C, void* stream) {
+                         int C, const float* in_scale, const float* in_shift, int in_relu, void* stream) {
     if (!h || !adj_w || !adj_src || !out || B < 1 || N < 1 || C < 4 || (C % 4) != 0) return MTFJSP_E_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
     const long long rows = (long long)B * N;
     const int C4 = C / 4;
     const long long total = rows * C4;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(h),
                                                                reinterpret_cast<const float2*>(adj_w), adj_src,
-                                                               reinterpret_cast<float4*>(out), rows, N, C4);
+                                                               reinterpret_cast<float4*>(out), rows, N, C4,
+                                                               reinterpret_cast<const float4*>(in_scale),
+                                                               reinterpret_cast<const float4*>(in_shift), in_relu);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 
-int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, void* stream) {
+int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, const float* in_scale,
+                          const float* in_shift, int in_relu, void* stream) {
     if (!h || !out || B < 1 || N < 1 || C < 1) return MTFJSP_E_ARG;
-    graph_mean_kernel<<<(unsigned)B, C < 128 ? 32 * ((C + 31) / 32) : 128, 0, (cudaStream_t)stream>>>(h, out, N, C);
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
+    graph_mean_kernel<<<(unsigned)B, C < 128 ? 32 * ((C + 31) / 32) : 128, 0, (cudaStream_t)stream>>>(h, out, N, C, in_scale,
+                                                                                                   in_shift, in_relu);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 

@@ -1,0 +1,251 @@
+// mtfjsp_gemm.cu -- fused per-node linear layer of the GNN encoder on the 5th-gen tensor cores (sm_100a).
+//
+//   Z[r, :] = act(X[r, :] * in_scale + in_shift) @ W^T + bias          (act = ReLU or identity; affine optional)
+//   stats  += (column sums of Z, column sums of Z^2)                   (FP64, for the BatchNorm that follows)
+//
+// Replaces, per layer of model/gcn_mlp.py:238-249 (Linear -> BatchNorm1d(batch stats) -> ReLU chain) and the outer
+// BatchNorm of :154-157: the cuBLAS sgemm, the separate BatchNorm statistics pass and the separate normalise+ReLU pass.
+// The normalisation of layer i is applied in the *prologue* of layer i+1 (scale/shift per input column), its
+// statistics are accumulated in the *epilogue* of layer i, so every activation is written once and read once.
+//
+// Mechanics: one persistent CTA per SM, 128 threads.  W (128 x K, K-major = nn.Linear layout) is converted to TF32
+// and parked in shared memory in the UMMA no-swizzle K-major core-matrix layout once; per 128-row tile the CTA
+// stages X the same way (prologue math in registers), one elected thread issues K/8 `tcgen05.mma.kind::tf32`
+// (M=128, N=128, K=8) accumulating in TMEM, `tcgen05.commit` arrives on an mbarrier, then each warp pulls its
+// 32 TMEM lanes with `tcgen05.ld.32x32b.x32`, adds the bias, transposes through shared memory and writes 128-byte
+// coalesced rows while accumulating the column statistics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mtfjsp.h"
+
+namespace {
+
+constexpr int TILE_M = 128, TILE_N = 128, STG_LD = 129;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes, rows 16 B apart;
+// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= 1ull << 46;  // descriptor version for sm_100
+    return d;         // layout_type (bits 61-63) = 0: no swizzle
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TILE_N >> 3) << 17) | ((TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate));
+}
+
+#define TMEM_LD32(taddr, r)                                                                                          \
+    asm volatile(                                                                                                    \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"  \
+        "%29,%30,%31}, [%32];"                                                                                       \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+        : "r"(taddr))
+
+// stage a [128 x KP] f32 block (row-major in global, leading dimension ld, `valid_rows` rows, `K` real columns) into
+// the UMMA layout: element (r, k) at (r/8)*SBO + (k/4)*128 + (r%8)*16 + (k%4)*4.  A warp iteration covers
+// 8 rows x 64 bytes: 2 full sectors per row in global, 512 contiguous bytes in shared memory.
+template <bool AFFINE>
+__device__ __forceinline__ void stage_block(float* sdst, const float* __restrict__ g, long long row0, long long rows,
+                                            int K, int KP, int ld, const float* s_scale, const float* s_shift,
+                                            bool relu, int warp, int lane) {
+    const int sbo = (KP / 4) * 128;
+    const int r = lane >> 2, c = lane & 3;
+    const int quads = KP / 16;
+    for (int it = warp; it < 16 * quads; it += 4) {
+        const int grp = it / quads, q = it - grp * quads;
+        const long long row = row0 + grp * 8 + r;
+        const int k = q * 16 + c * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows && k < K) v = __ldg(reinterpret_cast<const float4*>(g + row * ld + k));
+        if (AFFINE) {
+            if (row < rows && k < K) {
+                v.x = v.x * s_scale[k] + s_shift[k]; v.y = v.y * s_scale[k + 1] + s_shift[k + 1];
+                v.z = v.z * s_scale[k + 2] + s_shift[k + 2]; v.w = v.w * s_scale[k + 3] + s_shift[k + 3];
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            }
+        }
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+        *reinterpret_cast<float4*>(reinterpret_cast<char*>(sdst) + grp * sbo + (q * 4 + c) * 128 + r * 16) = v;
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K, int KP,
+                                                             const float* __restrict__ W, const float* __restrict__ bias,
+                                                             const float* __restrict__ in_scale,
+                                                             const float* __restrict__ in_shift, int in_relu,
+                                                             float* __restrict__ Z, double* __restrict__ stats,
+                                                             long long num_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sW = reinterpret_cast<float*>(smem);
+    float* sA = reinterpret_cast<float*>(smem + (size_t)TILE_N * KP * 4);
+    float* sStg = reinterpret_cast<float*>(smem + (size_t)(TILE_N + TILE_M) * KP * 4);
+    float* s_bias = sStg + TILE_M * STG_LD;
+    float* s_scale = s_bias + TILE_N;
+    float* s_shift = s_scale + 128;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool affine = in_scale != nullptr;
+
+    s_bias[tid] = bias ? bias[tid] : 0.f;
+    if (affine && tid < K) { s_scale[tid] = in_scale[tid]; s_shift[tid] = in_shift[tid]; }
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // TMEM: 128 columns x 128 lanes of FP32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // weights: [128 out, K in] row-major = K-major B operand
+    stage_block<false>(sW, W, 0, TILE_N, K, KP, K, nullptr, nullptr, false, warp, lane);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t sbo = (uint32_t)(KP / 4) * 128u;
+    const uint32_t aW = smem_u32(sW), aA = smem_u32(sA);
+
+    double csum[4] = {0, 0, 0, 0}, csq[4] = {0, 0, 0, 0};  // lane owns columns lane + 32 j
+    uint32_t parity = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long row0 = tile * TILE_M;
+        if (affine) stage_block<true>(sA, X, row0, rows, K, KP, K, s_scale, s_shift, in_relu != 0, warp, lane);
+        else stage_block<false>(sA, X, row0, rows, K, KP, K, nullptr, nullptr, false, warp, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int k = 0; k < KP / 8; k++) {  // one MMA consumes 8 TF32 = two 16-byte chunks = 256 bytes of K
+                const uint64_t ad = make_desc(aA + k * 256, 128, sbo);
+                const uint64_t bd = make_desc(aW + k * 256, 128, sbo);
+                umma_tf32(tmem_base, ad, bd, k > 0 ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(s_bar))
+                         : "memory");
+        }
+        mbar_wait(smem_u32(s_bar), parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue: TMEM -> registers (+bias) -> padded shared tile -> coalesced rows + column statistics ----
+        const int rloc = warp * 32 + lane;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32);
+            TMEM_LD32(taddr, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j++) sStg[rloc * STG_LD + cc * 32 + j] = __uint_as_float(r[j]) + s_bias[cc * 32 + j];
+        }
+        __syncwarp();
+        for (int rr = 0; rr < 32; rr++) {
+            const long long row = row0 + warp * 32 + rr;
+            if (row < rows) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float v = sStg[(warp * 32 + rr) * STG_LD + lane + 32 * j];
+                    Z[row * TILE_N + lane + 32 * j] = v;
+                    csum[j] += (double)v;
+                    csq[j] += (double)v * (double)v;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM and the staging tiles are reused by the next tile
+    }
+    if (stats) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            atomicAdd(stats + lane + 32 * j, csum[j]);
+            atomicAdd(stats + TILE_N + lane + 32 * j, csq[j]);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+}
+
+// BatchNorm1d with batch statistics folded into a per-column affine: scale = gamma / sqrt(var + eps),
+// shift = beta - mean * scale (biased variance, as torch uses for normalisation in training mode)
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double inv_rows, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float* scale, float* shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = stats[c] * inv_rows;
+    double var = stats[C + c] * inv_rows - mean * mean;
+    if (var < 0) var = 0;
+    const double sc = (double)gamma[c] / sqrt(var + (double)eps);
+    scale[c] = (float)sc;
+    shift[c] = (float)((double)beta[c] - mean * sc);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
+                           const float* in_shift, int in_relu, float* Z, double* stats, void* stream) {
+    if (!X || !W || !Z || rows < 1 || K < 4 || K > 128 || (K % 4) != 0) return MTFJSP_E_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
+    const int KP = (K + 15) / 16 * 16;
+    const size_t smem = (size_t)(TILE_N + TILE_M) * KP * 4 + (size_t)TILE_M * STG_LD * 4 + (TILE_N + 256) * 4 + 64;
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MTFJSP_E_CUDA;
+        configured = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (rows + TILE_M - 1) / TILE_M;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    linear_tf32_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(X, rows, K, KP, W, bias, in_scale, in_shift, in_relu, Z,
+                                                                  stats, tiles);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,
+                           float* scale, float* shift, int C, void* stream) {
+    if (!stats || !gamma || !beta || !scale || !shift || rows < 1 || C < 1) return MTFJSP_E_ARG;
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, 1.0 / (double)rows, gamma, beta, eps, scale,
+                                                                        shift, C);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+}  // extern "C"

@@ -34,22 +34,49 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def aggregate(h, adj_w, adj_src):
-    """out[b,v] = (h[b,v] + w_job*h[b,v-1] + w_mach*h[b,src]) / in_degree (FP64 accumulate); h [B,N,C] f32."""
+def _optr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def aggregate(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False):
+    """out[b,v] = (x[b,v] + w_job*x[b,v-1] + w_mach*x[b,src]) / in_degree (FP64 accumulate); h [B,N,C] f32;
+    x = relu?(h*in_scale+in_shift) when an input affine is given (the producing layer's BatchNorm, folded in)."""
     B, N, Cc = h.shape
     h = h.contiguous()
     out = torch.empty_like(h)
-    check(_lib.lib().mtfjsp_enc_aggregate(_ptr(h), _ptr(adj_w), _ptr(adj_src), _ptr(out), B, N, Cc, _stream()),
-          "mtfjsp_enc_aggregate")
+    check(_lib.lib().mtfjsp_enc_aggregate(_ptr(h), _ptr(adj_w), _ptr(adj_src), _ptr(out), B, N, Cc, _optr(in_scale),
+                                          _optr(in_shift), int(relu), _stream()), "mtfjsp_enc_aggregate")
     return out
 
 
-def graph_mean(h):
+def graph_mean(h, in_scale=None, in_shift=None, relu=False):
     B, N, Cc = h.shape
     h = h.contiguous()
     out = torch.empty((B, Cc), dtype=h.dtype, device=h.device)
-    check(_lib.lib().mtfjsp_enc_graph_mean(_ptr(h), _ptr(out), B, N, Cc, _stream()), "mtfjsp_enc_graph_mean")
+    check(_lib.lib().mtfjsp_enc_graph_mean(_ptr(h), _ptr(out), B, N, Cc, _optr(in_scale), _optr(in_shift), int(relu),
+                                           _stream()), "mtfjsp_enc_graph_mean")
     return out
+
+
+def linear_tf32(x, weight, bias, in_scale=None, in_shift=None, relu=False, stats=None):
+    """Z = act(x*in_scale+in_shift) @ weight.T + bias on tcgen05 tensor cores (TF32 operands, FP32 accumulate);
+    stats [256] f64 accumulates column sums / sums of squares of Z.  x [rows,K] f32, weight [128,K]."""
+    rows, K = x.shape
+    assert weight.shape == (128, K) and x.dtype == torch.float32
+    z = torch.empty((rows, 128), dtype=torch.float32, device=x.device)
+    check(_lib.lib().mtfjsp_enc_linear_tf32(_ptr(x.contiguous()), rows, K, _ptr(weight), _optr(bias), _optr(in_scale),
+                                            _optr(in_shift), int(relu), _ptr(z), _optr(stats), _stream()),
+          "mtfjsp_enc_linear_tf32")
+    return z
+
+
+def bn_finalize(stats, rows, gamma, beta, eps=1e-5):
+    Cc = gamma.shape[0]
+    scale = torch.empty(Cc, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty_like(scale)
+    check(_lib.lib().mtfjsp_enc_bn_finalize(_ptr(stats), rows, _ptr(gamma), _ptr(beta), eps, _ptr(scale), _ptr(shift), Cc,
+                                            _stream()), "mtfjsp_enc_bn_finalize")
+    return scale, shift
 
 
 def job_actor_keys(hidden=128, in_dim=12):
@@ -144,10 +171,17 @@ class _Params:
 class JobActor:
     """Forward of Operation_Actor_JointAction_selfCritic (model/actor_critic.py:104-296) on native observations."""
 
-    def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None):
+    def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None, precision="fp32"):
+        """precision "fp32": library FP32 GEMMs, bit-for-bit the reference's arithmetic types;
+        "tf32": the fused tcgen05 layer kernel (hidden must be 128) -- BatchNorm folded into prologue/epilogue."""
         self.J, self.M, self.N, self.H = n_job, n_machine, n_job * n_machine, hidden
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.w = _Params(job_actor_keys(hidden, in_dim), state_dict, self.device)
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        if precision == "tf32" and hidden != 128:
+            raise ValueError("the tcgen05 layer kernel is built for hidden = 128")
+        self.precision = precision
 
     def _mlp(self, l, x):  # gcn_mlp.py:238-249
         w = self.w
@@ -164,6 +198,8 @@ class JobActor:
         B = task_fea.shape[0]
         w = self.w
         h = task_fea.to(torch.float32)
+        if self.precision == "tf32":
+            return self._encode_tf32(h, adj_w, adj_src)
         for l in (0, 1):
             pooled = aggregate(h, adj_w, adj_src)                                   # gcn_mlp.py:125-149
             z = self._mlp(l, pooled.reshape(B * self.N, -1))
@@ -172,6 +208,30 @@ class JobActor:
             h = z.reshape(B, self.N, self.H)
         return graph_mean(h), h                                                    # gcn_mlp.py:192
 
+    def _encode_tf32(self, h, adj_w, adj_src):
+        """Same network on the fused tensor-core layer: every activation is written once and read once; the
+        BatchNorm of a layer is applied by its consumer (next layer's prologue, next aggregation, pooling)."""
+        w = self.w
+        B = h.shape[0]
+        rows = B * self.N
+        sc = sh = None
+        for l in (0, 1):
+            pooled = aggregate(h, adj_w, adj_src, sc, sh, relu=sc is not None).reshape(rows, -1)
+            p = "encoder.feature_extract.mlps.%d." % l
+            z, isc, ish = pooled, None, None
+            for i in (0, 1, 2):
+                stats = torch.zeros(256, dtype=torch.float64, device=h.device)
+                z = linear_tf32(z, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i], isc, ish,
+                                relu=isc is not None, stats=stats)
+                if i < 2:
+                    isc, ish = bn_finalize(stats, rows, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i])
+                else:
+                    sc, sh = bn_finalize(stats, rows, w["encoder.feature_extract.batch_norms.%d.weight" % l],
+                                         w["encoder.feature_extract.batch_norms.%d.bias" % l])
+            h = z.reshape(B, self.N, self.H)
+        self._pending = (sc, sh)  # outer BatchNorm + ReLU of the last layer, applied by the consumers below
+        return graph_mean(h, sc, sh, relu=True), h
+
     def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None):
         """-> task_index [B], action_index [B] (job), log_a [B], prob [B,J], h_g_o_pooled [B,H], job_v [B,2]."""
         w = self.w
@@ -179,6 +239,9 @@ class JobActor:
         pooled, nodes = self.encode(task_fea, adj_w, adj_src)
         cand = candidate.long()
         cf = torch.gather(nodes, 1, cand.unsqueeze(-1).expand(-1, self.J, self.H))     # actor_critic.py:197-207
+        if self.precision == "tf32":
+            sc, sh = self._pending
+            cf = torch.relu(cf * sc + sh)
         gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
         x = torch.cat((cf, pooled.unsqueeze(-2).expand_as(cf), gm), dim=-1)              # actor_critic.py:244-247
         s = torch.tanh(F.linear(x, w["o_policy.linears.0.weight"], w["o_policy.linears.0.bias"]))

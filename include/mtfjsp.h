@@ -141,9 +141,21 @@ int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_
  * SpMM): out[b,v,:] = (h[b,v,:] + adj_w[b,v,0]*h[b,v-1,:] + adj_w[b,v,1]*h[b,adj_src[b,v],:]) / in_degree, FP64
  * accumulate, FP32 in/out.  h, out: [B,N,C] f32 (C % 4 == 0); adj_w / adj_src as written by mtfjsp_obs. */
 int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_src, float* out, int64_t B, int N,
-                         int C, void* stream);
-/* replaces: gcn_mlp.py:192 graph mean pooling; h [B,N,C] f32 -> out [B,C] f32. */
-int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, void* stream);
+                         int C, const float* in_scale, const float* in_shift, int in_relu, void* stream);
+/* replaces: gcn_mlp.py:192 graph mean pooling; h [B,N,C] f32 -> out [B,C] f32.
+ * Both take an optional per-column affine (+ReLU) applied to h on the fly: the BatchNorm of the producing layer
+ * (gcn_mlp.py:154-157) folded into its consumer.  in_scale / in_shift [C] f32 or both NULL. */
+int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, const float* in_scale,
+                          const float* in_shift, int in_relu, void* stream);
+/* replaces: one Linear (+ the BatchNorm statistics pass, + the previous BatchNorm/ReLU apply pass) of
+ * gcn_mlp.py:238-249 on the tensor cores (tcgen05.mma kind::tf32, FP32 accumulate in TMEM):
+ * Z[rows,128] = act(X[rows,K]*in_scale+in_shift) @ W[128,K]^T + bias; stats[0:128] += column sums of Z,
+ * stats[128:256] += column sums of Z^2 (FP64; may be NULL).  4 <= K <= 128, K % 4 == 0. */
+int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
+                           const float* in_shift, int in_relu, float* Z, double* stats, void* stream);
+/* BatchNorm1d with batch statistics as a per-column affine: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
+int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,
+                           float* scale, float* shift, int C, void* stream);
 
 /* Number of kernel launches issued through this handle so far (bench.py reports it). */
 int64_t mtfjsp_launch_count(const mtfjsp_env* h);

@@ -22,8 +22,8 @@ def test_state_dict_layout_matches_shipped_checkpoints():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("H", [128, 32])
-def test_actor_forward_matches_reference_modules(H):
+@pytest.mark.parametrize("H,precision", [(128, "fp32"), (32, "fp32"), (128, "tf32")])
+def test_actor_forward_matches_reference_modules(H, precision):
     torch = pytest.importorskip("torch")
     enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
@@ -36,11 +36,13 @@ def test_actor_forward_matches_reference_modules(H):
     env.scaler_init()
     env.reset(g["weights"][0])
     env.obs(1)
-    job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 11), J, M, hidden=H)
+    job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 11), J, M, hidden=H, precision=precision)
     mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 12), M, hidden=H)
     dev = env.device
     i32 = lambda x: torch.as_tensor(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
-    close = lambda a, b, name: np.testing.assert_allclose(a.cpu().numpy(), b, rtol=2e-4, atol=2e-5, err_msg=name)
+    # fp32: the reference's own arithmetic; tf32: 10-bit-mantissa operands through 6 GEMMs and 6 batch norms
+    rt, at = (2e-4, 2e-5) if precision == "fp32" else (3e-2, 5e-3)
+    close = lambda a, b, name: np.testing.assert_allclose(a.cpu().numpy(), b, rtol=rt, atol=at, err_msg=name)
     cur = -1
     for tag in ("init", "s05", "s20", "s34"):
         k = "H%d_%s_" % (H, tag)
@@ -55,7 +57,8 @@ def test_actor_forward_matches_reference_modules(H):
         close(prob, e[k + "prob"], "job prob " + tag)
         close(pooled, e[k + "pooled"], "job pooled " + tag)
         close(jv, e[k + "job_v"], "job value " + tag)
-        np.testing.assert_array_equal(ti.cpu().numpy(), e[k + "task_index"])
+        if precision == "fp32":
+            np.testing.assert_array_equal(ti.cpu().numpy(), e[k + "task_index"])
         nxt = g["actions"][0, s + 1]
         m1, mmask = env.mfea1(i32(nxt[:, 0]))
         np.testing.assert_array_equal(mmask.cpu().numpy().astype(bool), e[k + "mmask"])
@@ -87,3 +90,40 @@ def test_aggregate_kernel_matches_dense_fp64_reference():
         np.testing.assert_allclose(out.cpu().numpy(), ref.float().cpu().numpy(), rtol=1e-6, atol=1e-6)
         pm = enc.graph_mean(h)
         np.testing.assert_allclose(pm.cpu().numpy(), h.mean(1).cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,rows,affine", [(128, 128, False), (128, 1000, True), (12, 333, False), (12, 4096 + 17, True),
+                                           (128, 128 * 300 + 5, True), (64, 777, True)])
+def test_tcgen05_linear_matches_fp32_matmul(K, rows, affine):
+    """Fused linear layer on the tensor cores (TF32 operands, FP32 accumulate) against an FP64 matmul of the
+    TF32-rounded operands (tight) and against plain FP32 (TF32 tolerance, 10-bit mantissa)."""
+    torch = pytest.importorskip("torch")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(K * 1000 + rows)
+    x = torch.randn(rows, K, device="cuda", generator=g)
+    W = torch.randn(128, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(128, device="cuda", generator=g)
+    sc = sh = None
+    xin = x
+    if affine:
+        sc = torch.rand(K, device="cuda", generator=g) + 0.5
+        sh = torch.randn(K, device="cuda", generator=g) * 0.3
+        xin = torch.relu(x * sc + sh)
+    stats = torch.zeros(256, dtype=torch.float64, device="cuda")
+    z = enc.linear_tf32(x, W, b, sc, sh, relu=affine, stats=stats)
+    torch.cuda.synchronize()
+
+    def tf32(t):  # round-to-nearest-away on the 13 dropped mantissa bits (cvt.rna.tf32.f32)
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    ref_t = (tf32(xin).double() @ tf32(W).double().T + b.double())
+    ref_f = xin.double() @ W.double().T + b.double()
+    np.testing.assert_allclose(z.double().cpu().numpy(), ref_t.cpu().numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(z.double().cpu().numpy(), ref_f.cpu().numpy(), rtol=5e-3, atol=5e-3)
+    np.testing.assert_allclose(stats[:128].cpu().numpy(), z.double().sum(0).cpu().numpy(), rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(stats[128:].cpu().numpy(), (z.double() ** 2).sum(0).cpu().numpy(), rtol=1e-9, atol=1e-7)
+    scale, shift = enc.bn_finalize(stats, rows, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"))
+    bn = torch.nn.functional.batch_norm(z, None, None, None, None, True, 0.0, 1e-5)
+    np.testing.assert_allclose((z * scale + shift).cpu().numpy(), bn.cpu().numpy(), rtol=1e-3, atol=1e-4)
