@@ -78,32 +78,50 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 // stage a [128 x KP] f32 block (row-major in global, leading dimension ld, `valid_rows` rows, `K` real columns) into
 // the UMMA layout: element (r, k) at (r/8)*SBO + (k/4)*128 + (r%8)*16 + (k%4)*4.  A warp iteration covers
 // 8 rows x 64 bytes: 2 full sectors per row in global, 512 contiguous bytes in shared memory.
-template <bool AFFINE>
+template <bool AFFINE, int NWARPS>
 __device__ __forceinline__ void stage_block(float* sdst, const float* __restrict__ g, long long row0, long long rows,
                                             int K, int KP, int ld, const float* s_scale, const float* s_shift,
                                             bool relu, int warp, int lane) {
     const int sbo = (KP / 4) * 128;
     const int r = lane >> 2, c = lane & 3;
     const int quads = KP / 16;
-    for (int it = warp; it < 16 * quads; it += 4) {
-        const int grp = it / quads, q = it - grp * quads;
-        const long long row = row0 + grp * 8 + r;
-        const int k = q * 16 + c * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows && k < K) v = __ldg(reinterpret_cast<const float4*>(g + row * ld + k));
-        if (AFFINE) {
-            if (row < rows && k < K) {
-                v.x = v.x * s_scale[k] + s_shift[k]; v.y = v.y * s_scale[k + 1] + s_shift[k + 1];
-                v.z = v.z * s_scale[k + 2] + s_shift[k + 2]; v.w = v.w * s_scale[k + 3] + s_shift[k + 3];
-                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            }
+    const int total = 16 * quads;
+    constexpr int U = 8;  // loads in flight per thread
+    for (int it0 = warp; it0 < total; it0 += NWARPS * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int it = it0 + u * NWARPS;
+            const int grp = it / quads, q = it - grp * quads;
+            const long long row = row0 + grp * 8 + r;
+            const int k = q * 16 + c * 4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < total && row < rows && k < K) v[u] = __ldg(reinterpret_cast<const float4*>(g + row * ld + k));
         }
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-        *reinterpret_cast<float4*>(reinterpret_cast<char*>(sdst) + grp * sbo + (q * 4 + c) * 128 + r * 16) = v;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int it = it0 + u * NWARPS;
+            if (it >= total) break;
+            const int grp = it / quads, q = it - grp * quads;
+            const long long row = row0 + grp * 8 + r;
+            const int k = q * 16 + c * 4;
+            float4 x = v[u];
+            if (AFFINE) {
+                if (row < rows && k < K) {
+                    x.x = x.x * s_scale[k] + s_shift[k]; x.y = x.y * s_scale[k + 1] + s_shift[k + 1];
+                    x.z = x.z * s_scale[k + 2] + s_shift[k + 2]; x.w = x.w * s_scale[k + 3] + s_shift[k + 3];
+                    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                }
+            }
+            x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
+            *reinterpret_cast<float4*>(reinterpret_cast<char*>(sdst) + grp * sbo + (q * 4 + c) * 128 + r * 16) = x;
+        }
     }
 }
 
-__global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K, int KP,
+constexpr int GEMM_WARPS = 8;  // warps 0-3 own the TMEM lanes (epilogue); all 8 stage operands
+
+__global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K, int KP,
                                                              const float* __restrict__ W, const float* __restrict__ bias,
                                                              const float* __restrict__ in_scale,
                                                              const float* __restrict__ in_shift, int in_relu,
@@ -122,7 +140,7 @@ __global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __rest
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool affine = in_scale != nullptr;
 
-    s_bias[tid] = bias ? bias[tid] : 0.f;
+    if (tid < TILE_N) s_bias[tid] = bias ? bias[tid] : 0.f;
     if (affine && tid < K) { s_scale[tid] = in_scale[tid]; s_shift[tid] = in_shift[tid]; }
     if (tid == 0) {
         mbar_init(smem_u32(s_bar), 1);
@@ -133,7 +151,7 @@ __global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __rest
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // weights: [128 out, K in] row-major = K-major B operand
-    stage_block<false>(sW, W, 0, TILE_N, K, KP, K, nullptr, nullptr, false, warp, lane);
+    stage_block<false, GEMM_WARPS>(sW, W, 0, TILE_N, K, KP, K, nullptr, nullptr, false, warp, lane);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -145,8 +163,8 @@ __global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __rest
     uint32_t parity = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long row0 = tile * TILE_M;
-        if (affine) stage_block<true>(sA, X, row0, rows, K, KP, K, s_scale, s_shift, in_relu != 0, warp, lane);
-        else stage_block<false>(sA, X, row0, rows, K, KP, K, nullptr, nullptr, false, warp, lane);
+        if (affine) stage_block<true, GEMM_WARPS>(sA, X, row0, rows, K, KP, K, s_scale, s_shift, in_relu != 0, warp, lane);
+        else stage_block<false, GEMM_WARPS>(sA, X, row0, rows, K, KP, K, nullptr, nullptr, false, warp, lane);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
         __syncthreads();
         if (tid == 0) {
@@ -164,6 +182,7 @@ __global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __rest
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- epilogue: TMEM -> registers (+bias) -> padded shared tile -> coalesced rows + column statistics ----
         const int rloc = warp * 32 + lane;
+        if (warp < 4) {
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
             uint32_t r[32];
@@ -186,10 +205,11 @@ __global__ void __launch_bounds__(128, 1) linear_tf32_kernel(const float* __rest
                 }
             }
         }
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // TMEM and the staging tiles are reused by the next tile
     }
-    if (stats) {
+    if (stats && warp < 4) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             atomicAdd(stats + lane + 32 * j, csum[j]);
@@ -235,7 +255,7 @@ int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (rows + TILE_M - 1) / TILE_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    linear_tf32_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(X, rows, K, KP, W, bias, in_scale, in_shift, in_relu, Z,
+    linear_tf32_kernel<<<grid, GEMM_WARPS * 32, smem, (cudaStream_t)stream>>>(X, rows, K, KP, W, bias, in_scale, in_shift, in_relu, Z,
                                                                   stats, tiles);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
