@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int TILE_M = 128, TILE_N = 128, STG_LD = 129;
+constexpr int TILE_M = 128, TILE_N = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float to_tf32(float x) {
@@ -119,23 +119,35 @@ __device__ __forceinline__ void stage_block(float* sdst, const float* __restrict
     }
 }
 
-constexpr int GEMM_WARPS = 8;  // warps 0-3 own the TMEM lanes (epilogue); all 8 stage operands
+constexpr int GEMM_WARPS = 8;   // warps 0-3: epilogue (they own TMEM lanes 0-127); warps 4-7: operand staging + MMA issue
+constexpr int STG_W = 33;       // per-warp 32 x 32 transpose tile, padded
 
-__global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K, int KP,
-                                                             const float* __restrict__ W, const float* __restrict__ bias,
-                                                             const float* __restrict__ in_scale,
-                                                             const float* __restrict__ in_shift, int in_relu,
-                                                             float* __restrict__ Z, double* __restrict__ stats,
-                                                             long long num_tiles) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warp-specialised, double-buffered: while the epilogue warps drain TMEM buffer b (tile i) to HBM, the producer
+// warps stage tile i+1 into the other shared-memory buffer and its MMAs fill the other TMEM buffer.
+//   full[b]       (count 1)  tcgen05.commit of tile i's MMAs: TMEM[b] is ready AND smem A[b] may be overwritten
+//   tmem_empty[b] (count 4)  the four epilogue warps have pulled TMEM[b] into registers
+__global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K,
+                                                                         int KP, const float* __restrict__ W,
+                                                                         const float* __restrict__ bias,
+                                                                         const float* __restrict__ in_scale,
+                                                                         const float* __restrict__ in_shift, int in_relu,
+                                                                         float* __restrict__ Z, double* __restrict__ stats,
+                                                                         long long num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    const size_t blk = (size_t)TILE_M * KP * 4;
     float* sW = reinterpret_cast<float*>(smem);
-    float* sA = reinterpret_cast<float*>(smem + (size_t)TILE_N * KP * 4);
-    float* sStg = reinterpret_cast<float*>(smem + (size_t)(TILE_N + TILE_M) * KP * 4);
-    float* s_bias = sStg + TILE_M * STG_LD;
+    float* sA0 = reinterpret_cast<float*>(smem + blk);
+    float* sA1 = reinterpret_cast<float*>(smem + 2 * blk);
+    float* sStg = reinterpret_cast<float*>(smem + 3 * blk);
+    float* s_bias = sStg + 4 * 32 * STG_W;
     float* s_scale = s_bias + TILE_N;
     float* s_shift = s_scale + 128;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool affine = in_scale != nullptr;
@@ -143,81 +155,99 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     if (tid < TILE_N) s_bias[tid] = bias ? bias[tid] : 0.f;
     if (affine && tid < K) { s_scale[tid] = in_scale[tid]; s_shift[tid] = in_shift[tid]; }
     if (tid == 0) {
-        mbar_init(smem_u32(s_bar), 1);
+        mbar_init(smem_u32(s_bar + 0), 1);
+        mbar_init(smem_u32(s_bar + 1), 1);
+        mbar_init(smem_u32(s_bar + 2), 4);
+        mbar_init(smem_u32(s_bar + 3), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // TMEM: 128 columns x 128 lanes of FP32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(128));
+    if (warp == 0) {  // TMEM: 2 x 128 columns x 128 lanes of FP32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // weights: [128 out, K in] row-major = K-major B operand
+    // weights: [128 out, K in] row-major = K-major B operand, staged once per CTA
     stage_block<false, GEMM_WARPS>(sW, W, 0, TILE_N, K, KP, K, nullptr, nullptr, false, warp, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     const uint32_t sbo = (uint32_t)(KP / 4) * 128u;
-    const uint32_t aW = smem_u32(sW), aA = smem_u32(sA);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2);
 
-    double csum[4] = {0, 0, 0, 0}, csq[4] = {0, 0, 0, 0};  // lane owns columns lane + 32 j
-    uint32_t parity = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long row0 = tile * TILE_M;
-        if (affine) stage_block<true, GEMM_WARPS>(sA, X, row0, rows, K, KP, K, s_scale, s_shift, in_relu != 0, warp, lane);
-        else stage_block<false, GEMM_WARPS>(sA, X, row0, rows, K, KP, K, nullptr, nullptr, false, warp, lane);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int k = 0; k < KP / 8; k++) {  // one MMA consumes 8 TF32 = two 16-byte chunks = 256 bytes of K
-                const uint64_t ad = make_desc(aA + k * 256, 128, sbo);
-                const uint64_t bd = make_desc(aW + k * 256, 128, sbo);
-                umma_tf32(tmem_base, ad, bd, k > 0 ? 1u : 0u);
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(s_bar))
-                         : "memory");
-        }
-        mbar_wait(smem_u32(s_bar), parity);
-        parity ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: TMEM -> registers (+bias) -> padded shared tile -> coalesced rows + column statistics ----
-        const int rloc = warp * 32 + lane;
-        if (warp < 4) {
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32);
-            TMEM_LD32(taddr, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; j++) sStg[rloc * STG_LD + cc * 32 + j] = __uint_as_float(r[j]) + s_bias[cc * 32 + j];
-        }
-        __syncwarp();
-        for (int rr = 0; rr < 32; rr++) {
-            const long long row = row0 + warp * 32 + rr;
-            if (row < rows) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float v = sStg[(warp * 32 + rr) * STG_LD + lane + 32 * j];
-                    Z[row * TILE_N + lane + 32 * j] = v;
-                    csum[j] += (double)v;
-                    csq[j] += (double)v * (double)v;
+    if (warp >= 4) {
+        // ================= producers =================
+        const int pw = warp - 4;
+        long long i = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+            const int buf = (int)(i & 1);
+            const uint32_t prev_par = (uint32_t)(((i >> 1) - 1) & 1);
+            if (i >= 2) mbar_wait(bar_full + buf * 8, prev_par);  // MMAs of tile i-2 have consumed A[buf]
+            float* sA = buf ? sA1 : sA0;
+            const long long row0 = tile * TILE_M;
+            if (affine) stage_block<true, 4>(sA, X, row0, rows, K, KP, K, s_scale, s_shift, in_relu != 0, pw, lane);
+            else stage_block<false, 4>(sA, X, row0, rows, K, KP, K, nullptr, nullptr, false, pw, lane);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+            asm volatile("bar.sync 1, 128;" ::: "memory");                // the four producer warps
+            if (tid == 128) {
+                if (i >= 2) mbar_wait(bar_empty + buf * 8, prev_par);     // epilogue of tile i-2 has drained TMEM[buf]
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+                for (int k = 0; k < KP / 8; k++) {  // one MMA consumes 8 TF32 = two 16-byte chunks = 256 bytes of K
+                    umma_tf32(tmem_base + buf * TILE_N, make_desc(aA + k * 256, 128, sbo), make_desc(aW + k * 256, 128, sbo),
+                              k > 0 ? 1u : 0u);
                 }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_full + buf * 8)
+                             : "memory");
             }
         }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // TMEM and the staging tiles are reused by the next tile
-    }
-    if (stats && warp < 4) {
+    } else {
+        // ================= epilogue =================
+        float* stg = sStg + warp * 32 * STG_W;
+        double csum[4] = {0, 0, 0, 0}, csq[4] = {0, 0, 0, 0};  // lane owns column cc*32 + lane
+        long long i = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+            const int buf = (int)(i & 1);
+            mbar_wait(bar_full + buf * 8, (uint32_t)((i >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row0 = tile * TILE_M + warp * 32;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            atomicAdd(stats + lane + 32 * j, csum[j]);
-            atomicAdd(stats + TILE_N + lane + 32 * j, csq[j]);
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TILE_N + cc * 32);
+                TMEM_LD32(taddr, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == 3) {  // this warp no longer needs TMEM[buf]
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) mbar_arrive(bar_empty + buf * 8);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) stg[lane * STG_W + j] = __uint_as_float(r[j]) + s_bias[cc * 32 + j];
+                __syncwarp();
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr++) {
+                    const long long row = row0 + rr;
+                    if (row < rows) {
+                        const float v = stg[rr * STG_W + lane];
+                        Z[row * TILE_N + cc * 32 + lane] = v;
+                        csum[cc] += (double)v;
+                        csq[cc] += (double)v * (double)v;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (stats) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                atomicAdd(stats + j * 32 + lane, csum[j]);
+                atomicAdd(stats + TILE_N + j * 32 + lane, csq[j]);
+            }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
 }
 
 // BatchNorm1d with batch statistics folded into a per-column affine: scale = gamma / sqrt(var + eps),
@@ -243,7 +273,7 @@ int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, 
     if (!X || !W || !Z || rows < 1 || K < 4 || K > 128 || (K % 4) != 0) return MTFJSP_E_ARG;
     if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
     const int KP = (K + 15) / 16 * 16;
-    const size_t smem = (size_t)(TILE_N + TILE_M) * KP * 4 + (size_t)TILE_M * STG_LD * 4 + (TILE_N + 256) * 4 + 64;
+    const size_t smem = (size_t)3 * TILE_M * KP * 4 + (size_t)4 * 32 * STG_W * 4 + (TILE_N + 256) * 4 + 64;
     static thread_local size_t configured = 0;
     if (configured < smem) {
         if (cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
