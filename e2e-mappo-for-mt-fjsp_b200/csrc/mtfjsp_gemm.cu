@@ -119,6 +119,52 @@ __device__ __forceinline__ void stage_block(float* sdst, const float* __restrict
     }
 }
 
+// Producer-side staging of one A tile, split in two: (1) every 16-byte piece goes global -> shared with cp.async
+// (a whole 128 x K tile is in flight at once, no register staging); (2) once landed, the issuing thread rounds its
+// own pieces to TF32 in place and applies the folded BatchNorm (+ReLU) of the producing layer.
+template <int KP>
+__device__ __forceinline__ void tile_issue(float* sdst, const float* __restrict__ g, long long row0, long long rows, int K,
+                                           int pw, int lane) {
+    constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll 8
+    for (int it = pw; it < TOTAL; it += 4) {
+        const int grp = it / QUADS, q = it % QUADS;
+        const long long row = row0 + grp * 8 + r;
+        const int k = q * 16 + c * 4;
+        const bool ok = row < rows && k < K;
+        const float* src = ok ? g + row * K + k : g;
+        const uint32_t dst = smem_u32(reinterpret_cast<char*>(sdst) + grp * SBO + (q * 4 + c) * 128 + r * 16);
+        const int nbytes = ok ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int KP, bool AFFINE>
+__device__ __forceinline__ void tile_transform(float* sdst, long long row0, long long rows, int K, const float* s_scale,
+                                               const float* s_shift, bool relu, int pw, int lane) {
+    constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll 4
+    for (int it = pw; it < TOTAL; it += 4) {
+        const int grp = it / QUADS, q = it % QUADS;
+        const int k = q * 16 + c * 4;
+        float4* p4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(sdst) + grp * SBO + (q * 4 + c) * 128 + r * 16);
+        float4 x = *p4;
+        if (AFFINE) {
+            const long long row = row0 + grp * 8 + r;
+            if (row < rows && k < K) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + k), sh = *reinterpret_cast<const float4*>(s_shift + k);
+                x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+                if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+        }
+        x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
+        *p4 = x;
+    }
+}
+
 constexpr int GEMM_WARPS = 8;   // warps 0-3: epilogue (they own TMEM lanes 0-127); warps 4-7: operand staging + MMA issue
 constexpr int STG_W = 33;       // per-warp 32 x 32 transpose tile, padded
 
@@ -127,22 +173,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // Warp-specialised, double-buffered: while the epilogue warps drain TMEM buffer b (tile i) to HBM, the producer
-// warps stage tile i+1 into the other shared-memory buffer and its MMAs fill the other TMEM buffer.
+// warps have tile i+1 in flight into the other shared-memory buffer and its MMAs fill the other TMEM buffer.
 //   full[b]       (count 1)  tcgen05.commit of tile i's MMAs: TMEM[b] is ready AND smem A[b] may be overwritten
 //   tmem_empty[b] (count 4)  the four epilogue warps have pulled TMEM[b] into registers
+template <int KP>
 __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K,
-                                                                         int KP, const float* __restrict__ W,
+                                                                         const float* __restrict__ W,
                                                                          const float* __restrict__ bias,
                                                                          const float* __restrict__ in_scale,
                                                                          const float* __restrict__ in_shift, int in_relu,
                                                                          float* __restrict__ Z, double* __restrict__ stats,
                                                                          long long num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const size_t blk = (size_t)TILE_M * KP * 4;
+    constexpr size_t BLK = (size_t)TILE_M * KP * 4;
     float* sW = reinterpret_cast<float*>(smem);
-    float* sA0 = reinterpret_cast<float*>(smem + blk);
-    float* sA1 = reinterpret_cast<float*>(smem + 2 * blk);
-    float* sStg = reinterpret_cast<float*>(smem + 3 * blk);
+    float* sA0 = reinterpret_cast<float*>(smem + BLK);
+    float* sA1 = reinterpret_cast<float*>(smem + 2 * BLK);
+    float* sStg = reinterpret_cast<float*>(smem + 3 * BLK);
     float* s_bias = sStg + 4 * 32 * STG_W;
     float* s_scale = s_bias + TILE_N;
     float* s_shift = s_scale + 128;
@@ -153,7 +200,10 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     const bool affine = in_scale != nullptr;
 
     if (tid < TILE_N) s_bias[tid] = bias ? bias[tid] : 0.f;
-    if (affine && tid < K) { s_scale[tid] = in_scale[tid]; s_shift[tid] = in_shift[tid]; }
+    if (tid < 128) {
+        s_scale[tid] = (affine && tid < K) ? in_scale[tid] : 1.f;
+        s_shift[tid] = (affine && tid < K) ? in_shift[tid] : 0.f;
+    }
     if (tid == 0) {
         mbar_init(smem_u32(s_bar + 0), 1);
         mbar_init(smem_u32(s_bar + 1), 1);
@@ -172,29 +222,37 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
-    const uint32_t sbo = (uint32_t)(KP / 4) * 128u;
+    constexpr uint32_t SBO = (uint32_t)(KP / 4) * 128u;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2);
 
     if (warp >= 4) {
         // ================= producers =================
         const int pw = warp - 4;
-        long long i = 0;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+        const long long stride = gridDim.x;
+        long long tile = blockIdx.x;
+        if (tile < num_tiles) tile_issue<KP>(sA0, X, tile * TILE_M, rows, K, pw, lane);
+        for (long long i = 0; tile < num_tiles; tile += stride, i++) {
             const int buf = (int)(i & 1);
-            const uint32_t prev_par = (uint32_t)(((i >> 1) - 1) & 1);
-            if (i >= 2) mbar_wait(bar_full + buf * 8, prev_par);  // MMAs of tile i-2 have consumed A[buf]
             float* sA = buf ? sA1 : sA0;
-            const long long row0 = tile * TILE_M;
-            if (affine) stage_block<true, 4>(sA, X, row0, rows, K, KP, K, s_scale, s_shift, in_relu != 0, pw, lane);
-            else stage_block<false, 4>(sA, X, row0, rows, K, KP, K, nullptr, nullptr, false, pw, lane);
+            const bool has_next = tile + stride < num_tiles;
+            if (has_next) {  // keep the next tile in flight while this one is transformed and multiplied
+                if (i >= 1) mbar_wait(bar_full + (buf ^ 1) * 8, (uint32_t)(((i - 1) >> 1) & 1));  // MMA(i-1) done with A[buf^1]
+                tile_issue<KP>(buf ? sA0 : sA1, X, (tile + stride) * TILE_M, rows, K, pw, lane);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            if (affine) tile_transform<KP, true>(sA, tile * TILE_M, rows, K, s_scale, s_shift, in_relu != 0, pw, lane);
+            else tile_transform<KP, false>(sA, tile * TILE_M, rows, K, nullptr, nullptr, false, pw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
             asm volatile("bar.sync 1, 128;" ::: "memory");                // the four producer warps
             if (tid == 128) {
-                if (i >= 2) mbar_wait(bar_empty + buf * 8, prev_par);     // epilogue of tile i-2 has drained TMEM[buf]
+                if (i >= 2) mbar_wait(bar_empty + buf * 8, (uint32_t)(((i >> 1) - 1) & 1));  // epilogue(i-2) drained TMEM[buf]
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+#pragma unroll
                 for (int k = 0; k < KP / 8; k++) {  // one MMA consumes 8 TF32 = two 16-byte chunks = 256 bytes of K
-                    umma_tf32(tmem_base + buf * TILE_N, make_desc(aA + k * 256, 128, sbo), make_desc(aW + k * 256, 128, sbo),
+                    umma_tf32(tmem_base + buf * TILE_N, make_desc(aA + k * 256, 128, SBO), make_desc(aW + k * 256, 128, SBO),
                               k > 0 ? 1u : 0u);
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_full + buf * 8)
@@ -205,6 +263,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
         // ================= epilogue =================
         float* stg = sStg + warp * 32 * STG_W;
         double csum[4] = {0, 0, 0, 0}, csq[4] = {0, 0, 0, 0};  // lane owns column cc*32 + lane
+        const float b0 = s_bias[lane], b1 = s_bias[32 + lane], b2 = s_bias[64 + lane], b3 = s_bias[96 + lane];
         long long i = 0;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
             const int buf = (int)(i & 1);
@@ -222,18 +281,35 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
                     if (lane == 0) mbar_arrive(bar_empty + buf * 8);
                 }
 #pragma unroll
-                for (int j = 0; j < 32; j++) stg[lane * STG_W + j] = __uint_as_float(r[j]) + s_bias[cc * 32 + j];
+                for (int j = 0; j < 32; j++) stg[lane * STG_W + j] = __uint_as_float(r[j]);
                 __syncwarp();
-#pragma unroll 4
-                for (int rr = 0; rr < 32; rr++) {
-                    const long long row = row0 + rr;
-                    if (row < rows) {
-                        const float v = stg[rr * STG_W + lane];
-                        Z[row * TILE_N + cc * 32 + lane] = v;
-                        csum[cc] += (double)v;
-                        csq[cc] += (double)v * (double)v;
+                // 32 rows x (this lane's column): 128-byte coalesced stores; column statistics as FP32 partials of
+                // the 32 rows (4 independent chains), folded into the FP64 running sums once per chunk
+                const float bb = cc == 0 ? b0 : cc == 1 ? b1 : cc == 2 ? b2 : b3;
+                float* zp = Z + row0 * TILE_N + cc * 32 + lane;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                if (row0 + 32 <= rows) {
+#pragma unroll
+                    for (int rr = 0; rr < 32; rr += 4) {
+                        const float v0 = stg[rr * STG_W + lane] + bb, v1 = stg[(rr + 1) * STG_W + lane] + bb;
+                        const float v2 = stg[(rr + 2) * STG_W + lane] + bb, v3 = stg[(rr + 3) * STG_W + lane] + bb;
+                        zp[(rr + 0) * TILE_N] = v0; zp[(rr + 1) * TILE_N] = v1;
+                        zp[(rr + 2) * TILE_N] = v2; zp[(rr + 3) * TILE_N] = v3;
+                        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+                        q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3);
+                    }
+                } else {
+                    for (int rr = 0; rr < 32; rr++) {
+                        if (row0 + rr < rows) {
+                            const float v = stg[rr * STG_W + lane] + bb;
+                            zp[rr * TILE_N] = v;
+                            s0 += v;
+                            q0 = fmaf(v, v, q0);
+                        }
                     }
                 }
+                csum[cc] += (double)((s0 + s1) + (s2 + s3));
+                csq[cc] += (double)((q0 + q1) + (q2 + q3));
                 __syncwarp();
             }
         }
@@ -266,28 +342,37 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double inv_
 
 }  // namespace
 
-extern "C" {
-
-int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
-                           const float* in_shift, int in_relu, float* Z, double* stats, void* stream) {
-    if (!X || !W || !Z || rows < 1 || K < 4 || K > 128 || (K % 4) != 0) return MTFJSP_E_ARG;
-    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
-    const int KP = (K + 15) / 16 * 16;
+template <int KP>
+static int launch_linear(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
+                         const float* in_shift, int in_relu, float* Z, double* stats, cudaStream_t stream) {
     const size_t smem = (size_t)3 * TILE_M * KP * 4 + (size_t)4 * 32 * STG_W * 4 + (TILE_N + 256) * 4 + 64;
-    static thread_local size_t configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(linear_tf32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return MTFJSP_E_CUDA;
-        configured = smem;
+        configured = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (rows + TILE_M - 1) / TILE_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    linear_tf32_kernel<<<grid, GEMM_WARPS * 32, smem, (cudaStream_t)stream>>>(X, rows, K, KP, W, bias, in_scale, in_shift, in_relu, Z,
-                                                                  stats, tiles);
+    linear_tf32_kernel<KP><<<grid, GEMM_WARPS * 32, smem, stream>>>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats,
+                                                                   tiles);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+extern "C" {
+
+int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
+                           const float* in_shift, int in_relu, float* Z, double* stats, void* stream) {
+    if (!X || !W || !Z || rows < 1 || K < 4 || K > 128 || (K % 4) != 0) return MTFJSP_E_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K <= 16) return launch_linear<16>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
+    if (K <= 32) return launch_linear<32>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
+    if (K <= 64) return launch_linear<64>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
+    return launch_linear<128>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
 }
 
 int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,

