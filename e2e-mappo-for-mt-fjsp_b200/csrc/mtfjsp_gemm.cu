@@ -119,6 +119,8 @@ __device__ __forceinline__ void stage_block(float* sdst, const float* __restrict
     }
 }
 
+constexpr int NPROD = 8;  // producer warps
+
 // Producer-side staging of one A tile, split in two: (1) every 16-byte piece goes global -> shared with cp.async
 // (a whole 128 x K tile is in flight at once, no register staging); (2) once landed, the issuing thread rounds its
 // own pieces to TF32 in place and applies the folded BatchNorm (+ReLU) of the producing layer.
@@ -127,8 +129,9 @@ __device__ __forceinline__ void tile_issue(float* sdst, const float* __restrict_
                                            int pw, int lane) {
     constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
     const int r = lane >> 2, c = lane & 3;
+    static_assert(NPROD % QUADS == 0, "a warp keeps one K chunk: its folded BatchNorm constants live in registers");
 #pragma unroll 8
-    for (int it = pw; it < TOTAL; it += 4) {
+    for (int it = pw; it < TOTAL; it += NPROD) {
         const int grp = it / QUADS, q = it % QUADS;
         const long long row = row0 + grp * 8 + r;
         const int k = q * 16 + c * 4;
@@ -146,16 +149,18 @@ __device__ __forceinline__ void tile_transform(float* sdst, long long row0, long
                                                const float* s_shift, bool relu, int pw, int lane) {
     constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
     const int r = lane >> 2, c = lane & 3;
-#pragma unroll 4
-    for (int it = pw; it < TOTAL; it += 4) {
-        const int grp = it / QUADS, q = it % QUADS;
-        const int k = q * 16 + c * 4;
+    const int q = pw % QUADS, k = q * 16 + c * 4;  // fixed per lane (NPROD % QUADS == 0)
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (AFFINE) { sc = *reinterpret_cast<const float4*>(s_scale + k); sh = *reinterpret_cast<const float4*>(s_shift + k); }
+    const bool kok = k < K;
+#pragma unroll 8
+    for (int it = pw; it < TOTAL; it += NPROD) {
+        const int grp = it / QUADS;
         float4* p4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(sdst) + grp * SBO + (q * 4 + c) * 128 + r * 16);
         float4 x = *p4;
         if (AFFINE) {
             const long long row = row0 + grp * 8 + r;
-            if (row < rows && k < K) {
-                const float4 sc = *reinterpret_cast<const float4*>(s_scale + k), sh = *reinterpret_cast<const float4*>(s_shift + k);
+            if (row < rows && kok) {
                 x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
                 if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             }
@@ -165,7 +170,8 @@ __device__ __forceinline__ void tile_transform(float* sdst, long long row0, long
     }
 }
 
-constexpr int GEMM_WARPS = 8;   // warps 0-3: epilogue (they own TMEM lanes 0-127); warps 4-7: operand staging + MMA issue
+constexpr int NEPI = 8;          // epilogue warps: warp w drains TMEM lanes 32*(w%4).., columns 64*(w/4)..
+constexpr int GEMM_WARPS = NEPI + NPROD;  // warps 0-7 epilogue, 8-15 operand staging (+ one MMA-issuing thread)
 constexpr int STG_W = 33;       // per-warp 32 x 32 transpose tile, padded
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -175,7 +181,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Warp-specialised, double-buffered: while the epilogue warps drain TMEM buffer b (tile i) to HBM, the producer
 // warps have tile i+1 in flight into the other shared-memory buffer and its MMAs fill the other TMEM buffer.
 //   full[b]       (count 1)  tcgen05.commit of tile i's MMAs: TMEM[b] is ready AND smem A[b] may be overwritten
-//   tmem_empty[b] (count 4)  the four epilogue warps have pulled TMEM[b] into registers
+//   tmem_empty[b] (count 8)  the eight epilogue warps have pulled TMEM[b] into registers
 template <int KP>
 __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K,
                                                                          const float* __restrict__ W,
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     float* sA0 = reinterpret_cast<float*>(smem + BLK);
     float* sA1 = reinterpret_cast<float*>(smem + 2 * BLK);
     float* sStg = reinterpret_cast<float*>(smem + 3 * BLK);
-    float* s_bias = sStg + 4 * 32 * STG_W;
+    float* s_bias = sStg + NEPI * 32 * STG_W;
     float* s_scale = s_bias + TILE_N;
     float* s_shift = s_scale + 128;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2]
@@ -207,8 +213,8 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     if (tid == 0) {
         mbar_init(smem_u32(s_bar + 0), 1);
         mbar_init(smem_u32(s_bar + 1), 1);
-        mbar_init(smem_u32(s_bar + 2), 4);
-        mbar_init(smem_u32(s_bar + 3), 4);
+        mbar_init(smem_u32(s_bar + 2), NEPI);
+        mbar_init(smem_u32(s_bar + 3), NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM: 2 x 128 columns x 128 lanes of FP32 accumulators
@@ -225,9 +231,9 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     constexpr uint32_t SBO = (uint32_t)(KP / 4) * 128u;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2);
 
-    if (warp >= 4) {
+    if (warp >= NEPI) {
         // ================= producers =================
-        const int pw = warp - 4;
+        const int pw = warp - NEPI;
         const long long stride = gridDim.x;
         long long tile = blockIdx.x;
         if (tile < num_tiles) tile_issue<KP>(sA0, X, tile * TILE_M, rows, K, pw, lane);
@@ -245,8 +251,8 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
             if (affine) tile_transform<KP, true>(sA, tile * TILE_M, rows, K, s_scale, s_shift, in_relu != 0, pw, lane);
             else tile_transform<KP, false>(sA, tile * TILE_M, rows, K, nullptr, nullptr, false, pw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
-            asm volatile("bar.sync 1, 128;" ::: "memory");                // the four producer warps
-            if (tid == 128) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");  // the producer warps
+            if (tid == NEPI * 32) {
                 if (i >= 2) mbar_wait(bar_empty + buf * 8, (uint32_t)(((i >> 1) - 1) & 1));  // epilogue(i-2) drained TMEM[buf]
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
@@ -262,21 +268,23 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     } else {
         // ================= epilogue =================
         float* stg = sStg + warp * 32 * STG_W;
-        double csum[4] = {0, 0, 0, 0}, csq[4] = {0, 0, 0, 0};  // lane owns column cc*32 + lane
-        const float b0 = s_bias[lane], b1 = s_bias[32 + lane], b2 = s_bias[64 + lane], b3 = s_bias[96 + lane];
+        const int quad = warp & 3, half = warp >> 2;  // TMEM lanes 32*quad.., columns 64*half..
+        double csum[2] = {0, 0}, csq[2] = {0, 0};     // lane owns column 64*half + 32*c2 + lane
+        const float b0 = s_bias[half * 64 + lane], b1 = s_bias[half * 64 + 32 + lane];
         long long i = 0;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
             const int buf = (int)(i & 1);
             mbar_wait(bar_full + buf * 8, (uint32_t)((i >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long row0 = tile * TILE_M + warp * 32;
+            const long long row0 = tile * TILE_M + quad * 32;
 #pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
+            for (int c2 = 0; c2 < 2; c2++) {
+                const int cc = half * 2 + c2;
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TILE_N + cc * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TILE_N + cc * 32);
                 TMEM_LD32(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == 3) {  // this warp no longer needs TMEM[buf]
+                if (c2 == 1) {  // this warp no longer needs TMEM[buf]
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (lane == 0) mbar_arrive(bar_empty + buf * 8);
                 }
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
                 __syncwarp();
                 // 32 rows x (this lane's column): 128-byte coalesced stores; column statistics as FP32 partials of
                 // the 32 rows (4 independent chains), folded into the FP64 running sums once per chunk
-                const float bb = cc == 0 ? b0 : cc == 1 ? b1 : cc == 2 ? b2 : b3;
+                const float bb = c2 == 0 ? b0 : b1;
                 float* zp = Z + row0 * TILE_N + cc * 32 + lane;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
                 if (row0 + 32 <= rows) {
@@ -308,16 +316,16 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
                         }
                     }
                 }
-                csum[cc] += (double)((s0 + s1) + (s2 + s3));
-                csq[cc] += (double)((q0 + q1) + (q2 + q3));
+                csum[c2] += (double)((s0 + s1) + (s2 + s3));
+                csq[c2] += (double)((q0 + q1) + (q2 + q3));
                 __syncwarp();
             }
         }
         if (stats) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                atomicAdd(stats + j * 32 + lane, csum[j]);
-                atomicAdd(stats + TILE_N + j * 32 + lane, csq[j]);
+            for (int j = 0; j < 2; j++) {
+                atomicAdd(stats + half * 64 + j * 32 + lane, csum[j]);
+                atomicAdd(stats + TILE_N + half * 64 + j * 32 + lane, csq[j]);
             }
         }
     }
@@ -345,7 +353,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double inv_
 template <int KP>
 static int launch_linear(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
                          const float* in_shift, int in_relu, float* Z, double* stats, cudaStream_t stream) {
-    const size_t smem = (size_t)3 * TILE_M * KP * 4 + (size_t)4 * 32 * STG_W * 4 + (TILE_N + 256) * 4 + 64;
+    const size_t smem = (size_t)3 * TILE_M * KP * 4 + (size_t)NEPI * 32 * STG_W * 4 + (TILE_N + 256) * 4 + 64;
     static thread_local bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(linear_tf32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
