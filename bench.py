@@ -260,6 +260,31 @@ def run_ours(args, wl):
     e2e_val = B * world * Ke / e2e_s
     assert float(info6[:, 1].sum()) in (0.0, float(B))
     clocks = sampler.stop() if sampler else None
+
+    # ---- BASELINE.json configs[4] (forward half): the same env slice driven by the MAPPO actors on the device ----
+    policy = None
+    if not args.no_policy and (J, M) == (6, 6):
+        enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+        rom = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
+        job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(128), 11), J, M, precision="tf32")
+        mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M)
+        ro = rom.Rollout(env, job, mch, greedy=False, use_cuda_graph=True, seed=1)
+        ro.begin_episode(w)
+        for _ in range(4):
+            ro.step()  # eager first step, warm-up, capture
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nstep = N - 4
+        p0.record()
+        for _ in range(nstep):
+            ro.step()
+        p1.record()
+        barrier()
+        pms = sh.max_over_ranks(p0.elapsed_time(p1), dev)
+        assert int(env.done.sum().item()) == B and int(env.invalid.sum().item()) == 0
+        policy = {"value": B * world * nstep / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms / nstep, "steps": nstep,
+                  "what": "job actor (GIN encoder, tcgen05 TF32 layers) + machine actor (GAT) + sampling + env step/obs, "
+                          "CUDA-graph replay, random-init weights", "hidden": 128}
     stats = sh.reduce_episode_stats(env.costs(), device=dev)  # the rollout side's only other exchange (6 doubles)
 
     cpu = None
@@ -287,6 +312,8 @@ def run_ours(args, wl):
             "clocks": clocks,
             "episode_stats": {k: float(v) for k, v in stats.items()},
         }
+        if policy:
+            line["policy_rollout"] = policy
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -303,6 +330,7 @@ def main():
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-policy", action="store_true", help="skip the actor-driven rollout measurement")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
