@@ -267,7 +267,7 @@ def run_ours(args, wl):
         enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
         rom = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
         job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(128), 11), J, M, precision="tf32")
-        mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M)
+        mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M, precision="tf32")
         ro = rom.Rollout(env, job, mch, greedy=False, use_cuda_graph=True, seed=1)
         ro.begin_episode(w)
         for _ in range(4):

@@ -14,24 +14,36 @@ SRC_DIR = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmtfjsp_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "mtfjsp.h")
 SOURCES = ["mtfjsp_env.cu", "mtfjsp_encoder.cu", "mtfjsp_gemm.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+# the env kernels restate the reference's FP64 arithmetic operation by operation: no FMA contraction there
+EXTRA_FLAGS = {"mtfjsp_env.cu": ["-fmad=false"]}
 
 
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     mt = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(SRC_DIR, s) for s in os.listdir(SRC_DIR)] + [HEADER]
+    deps = [os.path.join(SRC_DIR, s) for s in os.listdir(SRC_DIR)] + [HEADER, os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > mt for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree so it travels to the GPU box."""
+    """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree so it travels to the GPU box.
+    One object per source (compiled in parallel), then one shared library."""
     if force or _stale():
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
-              [os.path.join(SRC_DIR, s) for s in SOURCES]
-        subprocess.check_call(cmd)
+        obj_dir = os.path.join(_HERE, "build")
+        os.makedirs(obj_dir, exist_ok=True)
+        procs, objs = [], []
+        for src in SOURCES:
+            obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+            objs.append(obj)
+            cmd = ["nvcc"] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + \
+                  ["-c", "-o", obj, os.path.join(SRC_DIR, src)]
+            procs.append((cmd, subprocess.Popen(cmd)))
+        for cmd, pr in procs:
+            if pr.wait() != 0:
+                raise subprocess.CalledProcessError(pr.returncode, cmd)
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 

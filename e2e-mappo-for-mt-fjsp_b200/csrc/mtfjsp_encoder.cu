@@ -49,10 +49,17 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float4* __restrict
             x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
             if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
         }
-        a0 += ww[k] * (double)x.x; a1 += ww[k] * (double)x.y; a2 += ww[k] * (double)x.z; a3 += ww[k] * (double)x.w;
+        a0 = fma(ww[k], (double)x.x, a0); a1 = fma(ww[k], (double)x.y, a1);
+        a2 = fma(ww[k], (double)x.z, a2); a3 = fma(ww[k], (double)x.w, a3);
     }
-    const double deg = (double)n;
-    out[idx] = make_float4((float)(a0 / deg), (float)(a1 / deg), (float)(a2 / deg), (float)(a3 / deg));
+    // weights are small integers and h is FP32, so every product is exact in FP64 and the fused form rounds the
+    // same way as multiply-then-add.  Division by 1 and 2 is exact without a divide sequence.
+    if (n == 3) {
+        a0 = a0 / 3.0; a1 = a1 / 3.0; a2 = a2 / 3.0; a3 = a3 / 3.0;
+    } else if (n == 2) {
+        a0 *= 0.5; a1 *= 0.5; a2 *= 0.5; a3 *= 0.5;
+    }
+    out[idx] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
 }
 
 // per-env mean over the N node rows (graph_pool average): one block per env, thread per channel

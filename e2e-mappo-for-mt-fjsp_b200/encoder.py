@@ -264,16 +264,24 @@ class JobActor:
 class MachineActor:
     """Forward of Machine_Actor_JointAction_selfGAT_selfCritic (model/actor_critic.py:359-498)."""
 
-    def __init__(self, state_dict, n_machine, hidden=128, device=None):
+    def __init__(self, state_dict, n_machine, hidden=128, device=None, precision="fp32"):
         self.M, self.H = n_machine, hidden
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.w = _Params(machine_actor_keys(hidden), state_dict, self.device)
+        if precision not in ("fp32", "tf32") or (precision == "tf32" and hidden != 128):
+            raise ValueError("precision must be 'fp32' or 'tf32' (tf32 needs hidden = 128)")
+        self.precision = precision
+        self._Wt = self.w["gat_layer.W"].t().contiguous()  # [out, in] = the layout the tensor-core layer takes
 
     def _gat(self, h1, h2):
         """GATLayer.forward (gat.py:82-159) on the fixed 2-node graph: node 1 attends to {1, 2}, node 2 to itself."""
         W, a = self.w["gat_layer.W"], self.w["gat_layer.a"]
         H = self.H
-        t1, t2 = h1 @ W, h2 @ W
+        if self.precision == "tf32":  # both node sets in one [2*rows,128] x [128,128] tensor-core launch
+            t = linear_tf32(torch.cat((h1, h2), dim=0), self._Wt, None)
+            t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
+        else:
+            t1, t2 = h1 @ W, h2 @ W
         a_src, a_dst = a[0, :H, 0], a[0, H:, 0]
         e11 = F.leaky_relu(t1 @ a_src + t1 @ a_dst, 0.2)
         e12 = F.leaky_relu(t1 @ a_src + t2 @ a_dst, 0.2)
