@@ -259,8 +259,6 @@ def run_ours(args, wl):
     e2e_s = sh.max_over_ranks(e2e_s, dev)
     e2e_val = B * world * Ke / e2e_s
     assert float(info6[:, 1].sum()) in (0.0, float(B))
-    clocks = sampler.stop() if sampler else None
-
     # ---- BASELINE.json configs[4] (forward half): the same env slice driven by the MAPPO actors on the device ----
     policy = None
     if not args.no_policy and (J, M) == (6, 6):
@@ -287,6 +285,35 @@ def run_ours(args, wl):
                           "CUDA-graph replay, random-init weights", "hidden": 128}
     stats = sh.reduce_episode_stats(env.costs(), device=dev)  # the rollout side's only other exchange (6 doubles)
 
+    clocks = sampler.stop() if sampler else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_env_kernel_traffic.json")
+    if (J, M, B) == (6, 6, 65536) and os.path.exists(tpath):  # ncu --set full capture of this kernel on this workload
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+
+    # ---- the strict drop-in call: Parallel_env.DGFJSPEnv_paral_step with the reference's argument / return types
+    # (python list of action pairs in, numpy float64 dense adjacency [B,N,N] + features + python info list out) ----
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_dropin:
+        pem = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.parallel_env")
+        Bd = min(B, 8192)
+        pe = pem.Parallel_env({"n_job": J, "n_machine": M, "n_edge": E, "env_batch": Bd, "GAMMA": 0.99,
+                               "reward_scaling": {"scaling_divisor": 1}, "weight_mk": 0.4, "weight_ec": 0.4, "weight_tt": 0.2})
+        pe.get_batch({k2: torch.as_tensor(d[k1][:Bd]) for k1, k2 in (("t", "t"), ("p", "p"), ("transT", "transT"), ("edge", "edge"))})
+        pe.init_RewardScaling_sameBATCH(shape=4)
+        pe.init_DGFJSPEnv_state0(weights=w[:Bd].cpu().numpy())
+        acts = [list(zip(h_op[s2][:Bd].tolist(), h_mc[s2][:Bd].tolist())) for s2 in range(6)]
+        pe.DGFJSPEnv_paral_step(acts[0])
+        t0 = time.perf_counter()
+        for s2 in range(1, 6):
+            pe.DGFJSPEnv_paral_step(acts[s2])
+        dt = time.perf_counter() - t0
+        dropin = {"value": Bd * 5 / dt, "unit": UNIT, "envs": Bd, "d2h_bytes_per_step": Bd * (N * N * 8 + N * 96 + M * 64 + 80),
+                  "api": "Parallel_env.DGFJSPEnv_paral_step (reference types: python action list in, numpy f64 dense "
+                         "adjacency + features + python info list out)"}
+        del pe
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r1, sample = cpu_port_rate(wl, 1, 8.0)
@@ -306,7 +333,7 @@ def run_ours(args, wl):
                     "steps": Ke},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "env_kernel<STEP|OBS,float>", "kernel_us": k_us,
+                         "traffic": traffic, "kernel": "env_kernel_s<STEP|OBS,float> (fused step + reward + observation + job mask)", "kernel_us": k_us,
                          "bytes_per_env_step": bytes_step, "peak_source": peak_src,
                          "steps_per_s_kernel_only": B / (k_us * 1e-6)},
             "clocks": clocks,
@@ -314,6 +341,8 @@ def run_ours(args, wl):
         }
         if policy:
             line["policy_rollout"] = policy
+        if dropin:
+            line["e2e"]["dropin_parallel_env"] = dropin
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -331,6 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy", action="store_true", help="skip the actor-driven rollout measurement")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the Parallel_env (reference-typed) call measurement")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -136,6 +136,7 @@ class Parallel_env(object):
         self._dirty = True
         self._scaler_reset_pending = False
         self._loaded = False
+        self._pin = None
 
     # ---- reference surface ------------------------------------------------------------------------------------
     def get_batch(self, dataset_dict):
@@ -192,7 +193,10 @@ class Parallel_env(object):
         inv = self._env.invalid.cpu().numpy()
         if inv.any():  # the reference prints and corrupts its state; here the step is refused for those envs
             print("============= 'DGFJSPEnv_paral_step': invalid (task, machine) for envs", np.nonzero(inv)[0].tolist())
-        self.oenv_info = [[r5[b, 0], bool(done[b]), s4[b, 0], s4[b, 1], s4[b, 2], s4[b, 3]] for b in range(self.batch_size)]
+        rows = np.concatenate([r5[:, :1], done[:, None].astype(np.float64), s4], axis=1).tolist()
+        for row, dn in zip(rows, done.tolist()):
+            row[1] = bool(dn)
+        self.oenv_info = rows
         adj, mfea, tfea = self._emit_obs()
         return adj, self.oenv_info, mfea, tfea
 
@@ -207,7 +211,12 @@ class Parallel_env(object):
         mfea = self._env.mach_fea
         if self.return_torch:
             return adj, mfea.clone(), tfea.clone()
-        return adj.cpu().numpy(), mfea.cpu().numpy(), tfea.cpu().numpy()
+        if self._pin is None:  # pinned staging, reused every step: the copies run at PCIe speed
+            self._pin = tuple(torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (adj, mfea, tfea))
+        for dst, src in zip(self._pin, (adj, mfea, tfea)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return tuple(x.numpy().copy() for x in self._pin)  # fresh arrays, as the reference returns deep copies
 
     def job_mask_and_candidates(self, mask_mode=MASK_ESA):
         """Kernel-computed equivalent of esa_update_chosenTaskID_CandidateTaskIDx_JobMask's return value."""
