@@ -79,9 +79,69 @@ __global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict
     }
 }
 
+// 4-stream generalised advantage estimation (algorithm/ppo_algorithm.py:438-536): per env and reward stream a
+// backward scan over the buffered steps, delta = r + gamma*v_next - v, gae = delta + gamma*lambda*gae*(1-done).
+// Layout [T,B,4] (stream innermost), one thread per (env, stream): every step's load/store is coalesced.
+// Also accumulates sum / sum of squares per stream (FP64) for the block-wide advantage normalisation.
+__global__ void gae4_kernel(const float* __restrict__ r, const float* __restrict__ v, const float* __restrict__ vn,
+                            const float* __restrict__ done, float* __restrict__ adv, double* __restrict__ stats, int T,
+                            long long B, float gamma, float lam) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0, q = 0.0;
+    const int k = (int)(threadIdx.x & 3);  // blockDim.x is a multiple of 4, so idx % 4 == threadIdx.x % 4
+    if (idx < B * 4) {
+        const long long b = idx >> 2;
+        float gae = 0.f;
+        for (int t = T - 1; t >= 0; t--) {
+            const long long o = (long long)t * B * 4 + idx;
+            const float delta = r[o] + gamma * vn[o] - v[o];
+            gae = delta + gamma * lam * gae * (1.0f - done[(long long)t * B + b]);
+            adv[o] = gae;
+            s += (double)gae;
+            q += (double)gae * (double)gae;
+        }
+    }
+    // lanes with equal k hold the same stream: reduce over the warp with stride-4 shuffles, one atomic per warp and stream
+    for (int o = 16; o >= 4; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        q += __shfl_down_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) < 4 && stats) {
+        atomicAdd(stats + k, s);
+        atomicAdd(stats + 4 + k, q);
+    }
+}
+
+// adv <- (adv - mean) / (std + 1e-5) per stream, std unbiased (torch.std), ppo_algorithm.py:485, 532
+__global__ void adv_normalize_kernel(float* __restrict__ adv, const double* __restrict__ stats, double count, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx & 3);
+    const double mean = stats[k] / count;
+    double var = (stats[4 + k] - count * mean * mean) / (count - 1.0);
+    if (var < 0) var = 0;
+    adv[idx] = (float)(((double)adv[idx] - mean) / (sqrt(var) + 1e-5));
+}
+
 }  // namespace
 
 extern "C" {
+
+int mtfjsp_gae4(const float* r, const float* v, const float* v_next, const float* done, float* adv, double* stats, int T,
+                int64_t B, float gamma, float lam, void* stream) {
+    if (!r || !v || !v_next || !done || !adv || T < 1 || B < 1) return MTFJSP_E_ARG;
+    const long long n = (long long)B * 4;
+    gae4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r, v, v_next, done, adv, stats, T, B, gamma, lam);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_adv_normalize(float* adv, const double* stats, double count, int T, int64_t B, void* stream) {
+    if (!adv || !stats || count < 2 || T < 1 || B < 1) return MTFJSP_E_ARG;
+    const long long total = (long long)T * B * 4;
+    adv_normalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(adv, stats, count, total);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
 
 int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_src, float* out, int64_t B, int N,
                          int C, const float* in_scale, const float* in_shift, int in_relu, void* stream) {

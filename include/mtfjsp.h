@@ -157,6 +157,14 @@ int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, 
 int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,
                            float* scale, float* shift, int C, void* stream);
 
+/* replaces: the per-reward GAE of algorithm/ppo_algorithm.py:438-536 (python loop over buffered steps per stream).
+ * r, v, v_next, adv: [T,B,4] f32 (streams mk, pt, tt, idle); done [T,B] f32; stats[8] f64 accumulates per-stream
+ * sum and sum of squares of the advantages (allreduce it across ranks, then normalise). */
+int mtfjsp_gae4(const float* r, const float* v, const float* v_next, const float* done, float* adv, double* stats, int T,
+                int64_t B, float gamma, float lam, void* stream);
+/* adv <- (adv - mean) / (std + 1e-5) per stream over `count` values (unbiased std), ppo_algorithm.py:485, 532. */
+int mtfjsp_adv_normalize(float* adv, const double* stats, double count, int T, int64_t B, void* stream);
+
 /* Number of kernel launches issued through this handle so far (bench.py reports it). */
 int64_t mtfjsp_launch_count(const mtfjsp_env* h);
 /* Algorithmic bytes per env-step of the fused step+obs kernel for this handle's sizes. */
