@@ -1501,7 +1501,8 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     const Layout& L = h->L;
     if (L.sd_stride != S::SD || L.si_stride != S::SI || L.xs_stride != S::XS || L.o_sc != S::O_SC || L.o_misc != S::O_MISC)
         return fail(MTFJSP_E_STATE, "specialised kernel layout mismatch");
-    const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES;
+    static const size_t extra = getenv("MTFJSP_EXTRA_SMEM") ? (size_t)atoi(getenv("MTFJSP_EXTRA_SMEM")) : 0;  // occupancy experiments
+    const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES + extra;
     static thread_local int configured_dev = -1;
     if (configured_dev != h->device) {
         CK(cudaFuncSetAttribute(env_kernel_s<S, MODE, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
