@@ -246,8 +246,7 @@ static int env_step(const oracle_t *o, int b, env_t *e, int a, int m, double r5[
                     if (gap < d) continue;
                     double x = arrival(o, b, e, a);
                     double y = e->ft[prev] + tr(o, b, e, prev, a);
-                    st = x > y ? x : y; /* python max(x, y): returns x unless y > x */
-                    if (y > x) st = y; else st = x;
+                    st = (y > x) ? y : x; /* python max(x, y): returns x unless y > x */
                     where = k + 1;
                     if (next == prev + 1 && (next % M) != 0) e->removed_head = next; /* SS:1660 */
                     break;
