@@ -83,7 +83,7 @@ __device__ __forceinline__ void stage_block(float* sdst, const float* __restrict
                                             int K, int KP, int ld, const float* s_scale, const float* s_shift,
                                             bool relu, int warp, int lane) {
     const int sbo = (KP / 4) * 128;
-    const int r = lane >> 2, c = lane & 3;
+    const int r = lane & 7, c = lane >> 3;  // a quarter-warp covers 128 contiguous bytes of shared memory
     const int quads = KP / 16;
     const int total = 16 * quads;
     constexpr int U = 8;  // loads in flight per thread
@@ -128,7 +128,7 @@ template <int KP>
 __device__ __forceinline__ void tile_issue(float* sdst, const float* __restrict__ g, long long row0, long long rows, int K,
                                            int pw, int lane) {
     constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
-    const int r = lane >> 2, c = lane & 3;
+    const int r = lane & 7, c = lane >> 3;  // a quarter-warp covers 128 contiguous bytes of shared memory
     static_assert(NPROD % QUADS == 0, "a warp keeps one K chunk: its folded BatchNorm constants live in registers");
 #pragma unroll 8
     for (int it = pw; it < TOTAL; it += NPROD) {
@@ -148,25 +148,35 @@ template <int KP, bool AFFINE>
 __device__ __forceinline__ void tile_transform(float* sdst, long long row0, long long rows, int K, const float* s_scale,
                                                const float* s_shift, bool relu, int pw, int lane) {
     constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
-    const int r = lane >> 2, c = lane & 3;
+    const int r = lane & 7, c = lane >> 3;  // a quarter-warp covers 128 contiguous bytes of shared memory
     const int q = pw % QUADS, k = q * 16 + c * 4;  // fixed per lane (NPROD % QUADS == 0)
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (AFFINE) { sc = *reinterpret_cast<const float4*>(s_scale + k); sh = *reinterpret_cast<const float4*>(s_shift + k); }
     const bool kok = k < K;
-#pragma unroll 8
-    for (int it = pw; it < TOTAL; it += NPROD) {
-        const int grp = it / QUADS;
-        float4* p4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(sdst) + grp * SBO + (q * 4 + c) * 128 + r * 16);
-        float4 x = *p4;
-        if (AFFINE) {
-            const long long row = row0 + grp * 8 + r;
-            if (row < rows && kok) {
-                x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
-                if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            }
+    constexpr int PER = TOTAL / NPROD > 0 ? TOTAL / NPROD : 1;  // pieces per lane (TOTAL is a multiple of 16)
+    constexpr int U = PER < 8 ? PER : 8;
+    char* const colbase = reinterpret_cast<char*>(sdst) + (q * 4 + c) * 128 + r * 16;
+    for (int j0 = 0; j0 < PER; j0 += U) {
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {  // all loads first: the in-place stores below would otherwise serialise them
+            const int grp = (pw + (j0 + u) * NPROD) / QUADS;
+            x[u] = *reinterpret_cast<const float4*>(colbase + grp * SBO);
         }
-        x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
-        *p4 = x;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int grp = (pw + (j0 + u) * NPROD) / QUADS;
+            float4 v = x[u];
+            if (AFFINE) {
+                const long long row = row0 + grp * 8 + r;
+                if (row < rows && kok) {
+                    v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+            }
+            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+            *reinterpret_cast<float4*>(colbase + grp * SBO) = v;
+        }
     }
 }
 
