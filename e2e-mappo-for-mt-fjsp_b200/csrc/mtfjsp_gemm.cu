@@ -182,7 +182,7 @@ __device__ __forceinline__ void tile_transform(float* sdst, long long row0, long
 
 constexpr int NEPI = 8;          // epilogue warps: warp w drains TMEM lanes 32*(w%4).., columns 64*(w/4)..
 constexpr int GEMM_WARPS = NEPI + NPROD;  // warps 0-7 epilogue, 8-15 operand staging (+ one MMA-issuing thread)
-constexpr int STG_W = 33;       // per-warp 32 x 32 transpose tile, padded
+constexpr int STG_W = 32;       // per-warp 32 x 32 transpose tile, XOR-swizzled in 16-byte pieces
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -277,10 +277,16 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
         }
     } else {
         // ================= epilogue =================
+        // Each warp drains a 32-row x 32-column chunk: TMEM gives lane = row with the 32 columns in registers; a
+        // swizzled 4 KB shared-memory tile (16-byte piece j of row r at position j ^ (r & 7), conflict-free both
+        // ways) turns that into lane = (row % 4, 4 columns) so that rows leave as full 128-byte lines (STG.128) and
+        // the BatchNorm column statistics stay lane-local.
         float* stg = sStg + warp * 32 * STG_W;
         const int quad = warp & 3, half = warp >> 2;  // TMEM lanes 32*quad.., columns 64*half..
-        double csum[2] = {0, 0}, csq[2] = {0, 0};     // lane owns column 64*half + 32*c2 + lane
-        const float b0 = s_bias[half * 64 + lane], b1 = s_bias[half * 64 + 32 + lane];
+        const int sub = lane >> 3, c4 = lane & 7;     // lane owns columns 4*c4..4*c4+3 of rows == sub (mod 4)
+        double csum[2][4] = {}, csq[2][4] = {};
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c4 * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + half * 64 + 32 + c4 * 4);
         long long i = 0;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
             const int buf = (int)(i & 1);
@@ -299,44 +305,43 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
                     if (lane == 0) mbar_arrive(bar_empty + buf * 8);
                 }
 #pragma unroll
-                for (int j = 0; j < 32; j++) stg[lane * STG_W + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_W + ((j ^ (lane & 7)) << 2)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
-                // 32 rows x (this lane's column): 128-byte coalesced stores; column statistics as FP32 partials of
-                // the 32 rows (4 independent chains), folded into the FP64 running sums once per chunk
-                const float bb = c2 == 0 ? b0 : b1;
-                float* zp = Z + row0 * TILE_N + cc * 32 + lane;
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-                if (row0 + 32 <= rows) {
+                const float4 bb = c2 == 0 ? b0 : b1;
+                float* zp = Z + (row0 + sub) * TILE_N + cc * 32 + c4 * 4;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool full = row0 + 32 <= rows;
 #pragma unroll
-                    for (int rr = 0; rr < 32; rr += 4) {
-                        const float v0 = stg[rr * STG_W + lane] + bb, v1 = stg[(rr + 1) * STG_W + lane] + bb;
-                        const float v2 = stg[(rr + 2) * STG_W + lane] + bb, v3 = stg[(rr + 3) * STG_W + lane] + bb;
-                        zp[(rr + 0) * TILE_N] = v0; zp[(rr + 1) * TILE_N] = v1;
-                        zp[(rr + 2) * TILE_N] = v2; zp[(rr + 3) * TILE_N] = v3;
-                        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
-                        q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3);
-                    }
-                } else {
-                    for (int rr = 0; rr < 32; rr++) {
-                        if (row0 + rr < rows) {
-                            const float v = stg[rr * STG_W + lane] + bb;
-                            zp[rr * TILE_N] = v;
-                            s0 += v;
-                            q0 = fmaf(v, v, q0);
-                        }
+                for (int it = 0; it < 8; it++) {
+                    const int rr = it * 4 + sub;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_W + ((c4 ^ (rr & 7)) << 2));
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    if (full || row0 + rr < rows) {
+                        *reinterpret_cast<float4*>(zp + (size_t)it * 4 * TILE_N) = v;
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
                     }
                 }
-                csum[c2] += (double)((s0 + s1) + (s2 + s3));
-                csq[c2] += (double)((q0 + q1) + (q2 + q3));
+                csum[c2][0] += (double)s.x; csum[c2][1] += (double)s.y; csum[c2][2] += (double)s.z; csum[c2][3] += (double)s.w;
+                csq[c2][0] += (double)q.x; csq[c2][1] += (double)q.y; csq[c2][2] += (double)q.z; csq[c2][3] += (double)q.w;
                 __syncwarp();
             }
         }
-        if (stats) {
+        if (stats) {  // fold the four row classes, then one atomic per column and warp
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                atomicAdd(stats + half * 64 + j * 32 + lane, csum[j]);
-                atomicAdd(stats + TILE_N + half * 64 + j * 32 + lane, csq[j]);
-            }
+            for (int c2 = 0; c2 < 2; c2++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double a = csum[c2][j], b = csq[c2][j];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
+                    if (sub == 0) {
+                        atomicAdd(stats + half * 64 + c2 * 32 + c4 * 4 + j, a);
+                        atomicAdd(stats + TILE_N + half * 64 + c2 * 32 + c4 * 4 + j, b);
+                    }
+                }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
