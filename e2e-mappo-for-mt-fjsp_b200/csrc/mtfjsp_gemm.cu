@@ -121,62 +121,60 @@ __device__ __forceinline__ void stage_block(float* sdst, const float* __restrict
 
 constexpr int NPROD = 8;  // producer warps
 
-// Producer-side staging of one A tile, split in two: (1) every 16-byte piece goes global -> shared with cp.async
-// (a whole 128 x K tile is in flight at once, no register staging); (2) once landed, the issuing thread rounds its
-// own pieces to TF32 in place and applies the folded BatchNorm (+ReLU) of the producing layer.
-template <int KP>
+// Producer-side staging of one A stage (128 rows x KS columns starting at column kbase), split in two: (1) every
+// 16-byte piece goes global -> shared with cp.async (no register staging; several stages are in flight at once);
+// (2) once landed, the issuing thread rounds its own pieces to TF32 in place and applies the folded BatchNorm
+// (+ReLU) of the producing layer.
+template <int KS>
 __device__ __forceinline__ void tile_issue(float* sdst, const float* __restrict__ g, long long row0, long long rows, int K,
-                                           int pw, int lane) {
-    constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
+                                           int kbase, int pw, int lane) {
+    constexpr int SBO = (KS / 4) * 128, QUADS = KS / 16, TOTAL = 16 * QUADS;
     const int r = lane & 7, c = lane >> 3;  // a quarter-warp covers 128 contiguous bytes of shared memory
     static_assert(NPROD % QUADS == 0, "a warp keeps one K chunk: its folded BatchNorm constants live in registers");
-#pragma unroll 8
+#pragma unroll
     for (int it = pw; it < TOTAL; it += NPROD) {
         const int grp = it / QUADS, q = it % QUADS;
         const long long row = row0 + grp * 8 + r;
-        const int k = q * 16 + c * 4;
+        const int k = kbase + q * 16 + c * 4;
         const bool ok = row < rows && k < K;
         const float* src = ok ? g + row * K + k : g;
         const uint32_t dst = smem_u32(reinterpret_cast<char*>(sdst) + grp * SBO + (q * 4 + c) * 128 + r * 16);
         const int nbytes = ok ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int KP, bool AFFINE>
-__device__ __forceinline__ void tile_transform(float* sdst, long long row0, long long rows, int K, const float* s_scale,
-                                               const float* s_shift, bool relu, int pw, int lane) {
-    constexpr int SBO = (KP / 4) * 128, QUADS = KP / 16, TOTAL = 16 * QUADS;
-    const int r = lane & 7, c = lane >> 3;  // a quarter-warp covers 128 contiguous bytes of shared memory
-    const int q = pw % QUADS, k = q * 16 + c * 4;  // fixed per lane (NPROD % QUADS == 0)
+template <int KS, bool AFFINE>
+__device__ __forceinline__ void tile_transform(float* sdst, long long row0, long long rows, int K, int kbase,
+                                               const float* s_scale, const float* s_shift, bool relu, int pw, int lane) {
+    constexpr int SBO = (KS / 4) * 128, QUADS = KS / 16, TOTAL = 16 * QUADS;
+    const int r = lane & 7, c = lane >> 3;
+    const int q = pw % QUADS, k = kbase + q * 16 + c * 4;  // fixed per lane (NPROD % QUADS == 0)
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (AFFINE) { sc = *reinterpret_cast<const float4*>(s_scale + k); sh = *reinterpret_cast<const float4*>(s_shift + k); }
     const bool kok = k < K;
-    constexpr int PER = TOTAL / NPROD > 0 ? TOTAL / NPROD : 1;  // pieces per lane (TOTAL is a multiple of 16)
-    constexpr int U = PER < 8 ? PER : 8;
+    constexpr int PER = TOTAL / NPROD;  // pieces per lane
+    static_assert(PER >= 1 && PER <= 8, "stage size");
     char* const colbase = reinterpret_cast<char*>(sdst) + (q * 4 + c) * 128 + r * 16;
-    for (int j0 = 0; j0 < PER; j0 += U) {
-        float4 x[U];
+    float4 x[PER];
 #pragma unroll
-        for (int u = 0; u < U; u++) {  // all loads first: the in-place stores below would otherwise serialise them
-            const int grp = (pw + (j0 + u) * NPROD) / QUADS;
-            x[u] = *reinterpret_cast<const float4*>(colbase + grp * SBO);
-        }
+    for (int u = 0; u < PER; u++) {  // all loads first: the in-place stores below would otherwise serialise them
+        const int grp = (pw + u * NPROD) / QUADS;
+        x[u] = *reinterpret_cast<const float4*>(colbase + grp * SBO);
+    }
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int grp = (pw + (j0 + u) * NPROD) / QUADS;
-            float4 v = x[u];
-            if (AFFINE) {
-                const long long row = row0 + grp * 8 + r;
-                if (row < rows && kok) {
-                    v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
-                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                }
+    for (int u = 0; u < PER; u++) {
+        const int grp = (pw + u * NPROD) / QUADS;
+        float4 v = x[u];
+        if (AFFINE) {
+            const long long row = row0 + grp * 8 + r;
+            if (row < rows && kok) {
+                v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             }
-            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-            *reinterpret_cast<float4*>(colbase + grp * SBO) = v;
         }
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+        *reinterpret_cast<float4*>(colbase + grp * SBO) = v;
     }
 }
 
@@ -188,10 +186,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Warp-specialised, double-buffered: while the epilogue warps drain TMEM buffer b (tile i) to HBM, the producer
-// warps have tile i+1 in flight into the other shared-memory buffer and its MMAs fill the other TMEM buffer.
-//   full[b]       (count 1)  tcgen05.commit of tile i's MMAs: TMEM[b] is ready AND smem A[b] may be overwritten
+// Warp-specialised.  The A operand streams through a ring of NSTAGE shared-memory stages of 128 rows x KS columns
+// (KS = min(K, 64): a K=128 tile is two stages), NSTAGE-1 of them in flight from HBM while one is transformed and
+// multiplied; the accumulator is double-buffered in TMEM so the epilogue warps drain tile i while tile i+1 is formed.
+//   sfree[s]      (count 1)  tcgen05.commit after the MMAs that read stage slot s: the slot may be refilled
+//   full[b]       (count 1)  tcgen05.commit after the last MMA of a tile: TMEM[b] is ready
 //   tmem_empty[b] (count 8)  the eight epilogue warps have pulled TMEM[b] into registers
+constexpr int NSTAGE = 4;
+
 template <int KP>
 __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const float* __restrict__ X, long long rows, int K,
                                                                          const float* __restrict__ W,
@@ -201,16 +203,16 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
                                                                          float* __restrict__ Z, double* __restrict__ stats,
                                                                          long long num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr size_t BLK = (size_t)TILE_M * KP * 4;
+    constexpr int KS = KP > 64 ? 64 : KP, SPT = KP / KS;  // stage width, stages per tile
+    constexpr size_t WBYTES = (size_t)TILE_N * KP * 4, SBYTES = (size_t)TILE_M * KS * 4;
     float* sW = reinterpret_cast<float*>(smem);
-    float* sA0 = reinterpret_cast<float*>(smem + BLK);
-    float* sA1 = reinterpret_cast<float*>(smem + 2 * BLK);
-    float* sStg = reinterpret_cast<float*>(smem + 3 * BLK);
+    unsigned char* sRing = smem + WBYTES;
+    float* sStg = reinterpret_cast<float*>(sRing + NSTAGE * SBYTES);
     float* s_bias = sStg + NEPI * 32 * STG_W;
     float* s_scale = s_bias + TILE_N;
     float* s_shift = s_scale + 128;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2], sfree[NSTAGE]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 + NSTAGE);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool affine = in_scale != nullptr;
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
         mbar_init(smem_u32(s_bar + 1), 1);
         mbar_init(smem_u32(s_bar + 2), NEPI);
         mbar_init(smem_u32(s_bar + 3), NEPI);
+        for (int st = 0; st < NSTAGE; st++) mbar_init(smem_u32(s_bar + 4 + st), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM: 2 x 128 columns x 128 lanes of FP32 accumulators
@@ -238,43 +241,53 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
-    constexpr uint32_t SBO = (uint32_t)(KP / 4) * 128u;
-    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2);
+    constexpr uint32_t SBO_W = (uint32_t)(KP / 4) * 128u, SBO_A = (uint32_t)(KS / 4) * 128u;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2), bar_free = smem_u32(s_bar + 4);
 
     if (warp >= NEPI) {
         // ================= producers =================
         const int pw = warp - NEPI;
-        const long long stride = gridDim.x;
-        long long tile = blockIdx.x;
-        if (tile < num_tiles) tile_issue<KP>(sA0, X, tile * TILE_M, rows, K, pw, lane);
-        for (long long i = 0; tile < num_tiles; tile += stride, i++) {
-            const int buf = (int)(i & 1);
-            float* sA = buf ? sA1 : sA0;
-            const bool has_next = tile + stride < num_tiles;
-            if (has_next) {  // keep the next tile in flight while this one is transformed and multiplied
-                if (i >= 1) mbar_wait(bar_full + (buf ^ 1) * 8, (uint32_t)(((i - 1) >> 1) & 1));  // MMA(i-1) done with A[buf^1]
-                tile_issue<KP>(buf ? sA0 : sA1, X, (tile + stride) * TILE_M, rows, K, pw, lane);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const long long my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const long long nst = my_tiles * SPT;  // stages this CTA streams, in order
+        auto issue = [&](long long g) {        // every thread commits one group per stage, empty past the end
+            if (g < nst) {
+                const long long tile = blockIdx.x + (g / SPT) * (long long)gridDim.x;
+                tile_issue<KS>(reinterpret_cast<float*>(sRing + (g % NSTAGE) * SBYTES), X, tile * TILE_M, rows, K,
+                               (int)(g % SPT) * KS, pw, lane);
             }
-            if (affine) tile_transform<KP, true>(sA, tile * TILE_M, rows, K, s_scale, s_shift, in_relu != 0, pw, lane);
-            else tile_transform<KP, false>(sA, tile * TILE_M, rows, K, nullptr, nullptr, false, pw, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int g = 0; g < NSTAGE - 1; g++) issue(g);
+        for (long long g = 0; g < nst; g++) {
+            const long long i = g / SPT, tile = blockIdx.x + i * (long long)gridDim.x;
+            const int h = (int)(g % SPT), slot = (int)(g % NSTAGE), buf = (int)(i & 1);
+            float* sA = reinterpret_cast<float*>(sRing + slot * SBYTES);
+            asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");  // stage g has landed (this thread's pieces)
+            if (affine) tile_transform<KS, true>(sA, tile * TILE_M, rows, K, h * KS, s_scale, s_shift, in_relu != 0, pw, lane);
+            else tile_transform<KS, false>(sA, tile * TILE_M, rows, K, h * KS, nullptr, nullptr, false, pw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+            // refill the slot stage g-1 used: its MMAs ran while this stage was being transformed
+            if (g >= 1 && g + NSTAGE - 1 < nst)
+                mbar_wait(bar_free + (uint32_t)((g - 1) % NSTAGE) * 8, (uint32_t)(((g - 1) / NSTAGE) & 1));
+            issue(g + NSTAGE - 1);
             asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");  // the producer warps
             if (tid == NEPI * 32) {
-                if (i >= 2) mbar_wait(bar_empty + buf * 8, (uint32_t)(((i >> 1) - 1) & 1));  // epilogue(i-2) drained TMEM[buf]
+                if (h == 0 && i >= 2) mbar_wait(bar_empty + buf * 8, (uint32_t)(((i >> 1) - 1) & 1));  // TMEM[buf] drained
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+                const uint32_t aA = smem_u32(sA), aW = smem_u32(sW) + (uint32_t)h * (KS / 8) * 256u;
 #pragma unroll
-                for (int k = 0; k < KP / 8; k++) {  // one MMA consumes 8 TF32 = two 16-byte chunks = 256 bytes of K
-                    umma_tf32(tmem_base + buf * TILE_N, make_desc(aA + k * 256, 128, SBO), make_desc(aW + k * 256, 128, SBO),
-                              k > 0 ? 1u : 0u);
+                for (int k = 0; k < KS / 8; k++) {  // one MMA consumes 8 TF32 = two 16-byte chunks = 256 bytes of K
+                    umma_tf32(tmem_base + buf * TILE_N, make_desc(aA + k * 256, 128, SBO_A), make_desc(aW + k * 256, 128, SBO_W),
+                              (h > 0 || k > 0) ? 1u : 0u);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_full + buf * 8)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_free + slot * 8)
                              : "memory");
+                if (h == SPT - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_full + buf * 8)
+                                 : "memory");
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         // ================= epilogue =================
         // Each warp drains a 32-row x 32-column chunk: TMEM gives lane = row with the 32 columns in registers; a
@@ -368,7 +381,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double inv_
 template <int KP>
 static int launch_linear(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
                          const float* in_shift, int in_relu, float* Z, double* stats, cudaStream_t stream) {
-    const size_t smem = (size_t)3 * TILE_M * KP * 4 + (size_t)NEPI * 32 * STG_W * 4 + (TILE_N + 256) * 4 + 64;
+    const size_t smem = (size_t)TILE_N * KP * 4 + (size_t)NSTAGE * TILE_M * (KP > 64 ? 64 : KP) * 4 +
+                        (size_t)NEPI * 32 * STG_W * 4 + (TILE_N + 256) * 4 + (4 + NSTAGE) * 8 + 16;
     static thread_local bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(linear_tf32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
