@@ -10,9 +10,10 @@ Forward-only mirrors of the reference networks that consume the environment's na
 
 What runs where (round 1): the neighbour aggregation (reference: dense adj -> COO -> FP64 cuSPARSE SpMM -> second
 SpMM for the degree) is the hand-written `mtfjsp_enc_aggregate` kernel over ELL; graph pooling is
-`mtfjsp_enc_graph_mean`; the 2x2 GAT attention is closed-form elementwise math; the dense per-node projections are
-plain library GEMMs (`torch.nn.functional.linear` -> cuBLAS) and BatchNorm uses batch statistics exactly as the
-reference does (its modules are never put in eval mode).
+`mtfjsp_enc_graph_mean`; the 2x2 GAT attention is closed-form elementwise math; the dense per-node projections run
+on the tcgen05 kernel `mtfjsp_enc_linear_tf32` with `precision="tf32"` (BatchNorm statistics in its epilogue, the
+folded BatchNorm + ReLU of the previous layer in its prologue) or on library FP32 GEMMs with `precision="fp32"`;
+BatchNorm uses batch statistics exactly as the reference does (its modules are never put in eval mode).
 """
 from __future__ import annotations
 
@@ -39,7 +40,7 @@ def _optr(t):
 
 
 def aggregate(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False):
-    """out[b,v] = (x[b,v] + w_job*x[b,v-1] + w_mach*x[b,src]) / in_degree (FP64 accumulate); h [B,N,C] f32;
+    """out[b,v] = (x[b,v] + w_job*x[b,v-1] + w_mach*x[b,src]) / in_degree (FP32 FMAs); h [B,N,C] f32;
     x = relu?(h*in_scale+in_shift) when an input affine is given (the producing layer's BatchNorm, folded in)."""
     B, N, Cc = h.shape
     h = h.contiguous()

@@ -74,6 +74,7 @@ def test_actor_forward_matches_reference_modules(H, precision):
 
 @pytest.mark.gpu
 def test_aggregate_kernel_matches_dense_fp64_reference():
+    """gcn_mlp.py:125-149 forms the neighbourhood mean in FP64; the kernel is FP32 (see mtfjsp_encoder.cu header)."""
     torch = pytest.importorskip("torch")
     enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
@@ -91,7 +92,9 @@ def test_aggregate_kernel_matches_dense_fp64_reference():
         h = torch.randn(B, J * M, C, device=env.device)
         ref = torch.bmm(A, h.double()) / (A != 0).sum(-1, keepdim=True).double()   # gcn_mlp.py:125-149
         out = enc.aggregate(h, env.adj_w, env.adj_src)
-        np.testing.assert_allclose(out.cpu().numpy(), ref.float().cpu().numpy(), rtol=1e-6, atol=1e-6)
+        # FP32 fused multiply-adds: within 3 FP32 ulp of the magnitude sum |A| |h| / deg of the reference FP64 value
+        bound = 3 * 2.0 ** -24 * (torch.bmm(A.abs(), h.double().abs()) / (A != 0).sum(-1, keepdim=True).double()) + 1e-30
+        assert bool(((out.double() - ref).abs() <= bound).all()), float(((out.double() - ref).abs() / bound).max())
         pm = enc.graph_mean(h)
         np.testing.assert_allclose(pm.cpu().numpy(), h.mean(1).cpu().numpy(), rtol=1e-5, atol=1e-6)
 
