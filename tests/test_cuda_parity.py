@@ -214,6 +214,46 @@ def test_step_before_reset_is_a_state_error():
         env.step(env.op, env.mach)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_step_equals_device_step(pinned, kernel_path):
+    """mtfjsp_step_host with pinned and with pageable host buffers must equal the device-pointer call bit for bit,
+    including the all-invalid step after the episode has ended."""
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    B, J, M, E = 4096 + 77, 6, 6, 2
+    N = J * M
+    d = ins.synthetic_instances(0, B, J, M, E, 77)
+    w = ins.random_weights(0, B, 77)
+    envs = []
+    for _ in range(2):
+        env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)
+        env.load(d["t"], d["p"], d["transT"], d["edge"])
+        env.scaler_init()
+        env.reset(w)
+        envs.append(env)
+    dev_env, host_env = envs
+    pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
+    info6 = pin(torch.full((B, 6), -7.0, dtype=torch.float64))
+    h_jm = pin(torch.full((B, J), 9, dtype=torch.uint8))
+    h_cd = pin(torch.full((B, J), -1, dtype=torch.int32))
+    for s in range(N + 1):  # one step past the end: every action is invalid and must be reported as such
+        op, mach = dev_env.policy_random(seed=5)
+        if s == N:
+            op, mach = torch.zeros_like(op), torch.zeros_like(mach)
+        h_op, h_mc = pin(op.cpu()), pin(mach.cpu())
+        dev_env.step_obs(op, mach)
+        host_env.step_host(h_op, h_mc, info6, h_jm, h_cd)
+        eq(info6[:, 0].numpy(), dev_env.reward5[:, 0].cpu().numpy())
+        eq(info6[:, 1].numpy(), dev_env.done.cpu().numpy().astype(np.float64))
+        eq(info6[:, 2:].numpy(), dev_env.scaled4.cpu().numpy())
+        eq(h_jm.numpy(), dev_env.job_mask.cpu().numpy())
+        eq(h_cd.numpy(), dev_env.candidate.cpu().numpy())
+        for name in ("task_fea", "mach_fea", "adj_w", "adj_src"):
+            assert torch.equal(getattr(host_env, name), getattr(dev_env, name)), (name, s)
+        assert int(dev_env.invalid.sum()) == (B if s == N else 0)
+    assert bool(dev_env.done.all()) and float(info6[:, 1].sum()) == B
+    eq(host_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
+
+
 @pytest.mark.parametrize("cfg", [(65536, 6, 6, 2), (16384, 10, 10, 3), (4096, 30, 20, 5)])
 def test_full_size_rollout_invariants(cfg):
     """BASELINE.json sizes: schedule invariants + telescoping rewards + a replay-checked random subset."""
