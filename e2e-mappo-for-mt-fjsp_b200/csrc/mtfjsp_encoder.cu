@@ -62,6 +62,53 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float4* __restrict
     out[idx] = a;
 }
 
+// machine-successor index: adj_dst[b,u] = v with adj_src[b,v] == u, else -1 (a machine route gives every op at most
+// one successor, so the gather below has at most one machine term as well)
+__global__ void ell_invert_kernel(const int16_t* __restrict__ adj_src, int16_t* __restrict__ adj_dst, unsigned rows, int N) {
+    const unsigned row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int src = adj_src[row];
+    if (src >= 0) adj_dst[row - row % (unsigned)N + (unsigned)src] = (int16_t)(row % (unsigned)N);
+}
+
+// transpose of aggregate_kernel, again a gather: dL/dx[u] = g[u]/deg[u] + w_job[u+1]*g[u+1]/deg[u+1]
+//                                                           + w_mach[d]*g[d]/deg[d],  d = adj_dst[u]
+__global__ void __launch_bounds__(256) aggregate_bwd_kernel(const float4* __restrict__ g, const float2* __restrict__ adj_w,
+                                                            const int16_t* __restrict__ adj_src,
+                                                            const int16_t* __restrict__ adj_dst, float4* __restrict__ out,
+                                                            unsigned total, int N, int C4, int c4_shift) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const unsigned row = c4_shift >= 0 ? idx >> c4_shift : idx / (unsigned)C4;
+    const unsigned c = idx - row * (unsigned)C4;
+    const unsigned v = row % (unsigned)N;
+    auto inv_deg = [&](unsigned r, float2 w) {
+        const int n = 1 + (w.x != 0.f ? 1 : 0) + (__ldg(adj_src + r) >= 0 ? 1 : 0);
+        return n == 3 ? (1.0f / 3.0f) : n == 2 ? 0.5f : 1.0f;
+    };
+    const float2 w0 = __ldg(adj_w + row);
+    const float s0 = inv_deg(row, w0);
+    const float4 g0 = __ldg(g + idx);
+    float4 a = make_float4(g0.x * s0, g0.y * s0, g0.z * s0, g0.w * s0);
+    if (v + 1 < (unsigned)N) {
+        const float2 w1 = __ldg(adj_w + row + 1);
+        if (w1.x != 0.f) {
+            const float s1 = w1.x * inv_deg(row + 1, w1);
+            const float4 g1 = __ldg(g + idx + (unsigned)C4);
+            a.x = fmaf(s1, g1.x, a.x); a.y = fmaf(s1, g1.y, a.y); a.z = fmaf(s1, g1.z, a.z); a.w = fmaf(s1, g1.w, a.w);
+        }
+    }
+    const int d = __ldg(adj_dst + row);
+    if (d >= 0) {
+        const unsigned r2 = row - v + (unsigned)d;
+        const float2 w2 = __ldg(adj_w + r2);
+        const float s2 = w2.y * inv_deg(r2, w2);
+        const float4 g2 = __ldg(g + ((size_t)r2 * C4 + c));
+        a.x = fmaf(s2, g2.x, a.x); a.y = fmaf(s2, g2.y, a.y); a.z = fmaf(s2, g2.z, a.z); a.w = fmaf(s2, g2.w, a.w);
+    }
+    out[idx] = a;
+}
+
 // per-env mean over the N node rows (graph_pool average): one block per env, thread per channel
 __global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict__ out, int N, int C,
                                   const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu) {
@@ -163,6 +210,35 @@ int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_
             reinterpret_cast<const float4*>(h) + r0 * C4, reinterpret_cast<const float2*>(adj_w) + r0, adj_src + r0,
             reinterpret_cast<float4*>(out) + r0 * C4, total, N, C4, c4_shift, reinterpret_cast<const float4*>(in_scale),
             reinterpret_cast<const float4*>(in_shift), in_relu);
+    }
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_ell_invert(const int16_t* adj_src, int16_t* adj_dst, int64_t B, int N, void* stream) {
+    if (!adj_src || !adj_dst || B < 1 || N < 1 || (long long)B * N > 0x7fffff00LL) return MTFJSP_E_ARG;
+    const unsigned rows = (unsigned)(B * N);
+    if (cudaMemsetAsync(adj_dst, 0xff, (size_t)rows * 2, (cudaStream_t)stream) != cudaSuccess) return MTFJSP_E_CUDA;
+    ell_invert_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(adj_src, adj_dst, rows, N);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_aggregate_bwd(const float* g, const float* adj_w, const int16_t* adj_src, const int16_t* adj_dst, float* out,
+                             int64_t B, int N, int C, void* stream) {
+    if (!g || !adj_w || !adj_src || !adj_dst || !out || B < 1 || N < 1 || C < 4 || (C % 4) != 0) return MTFJSP_E_ARG;
+    const int C4 = C / 4;
+    int c4_shift = -1;
+    for (int k = 0; k < 16; k++)
+        if ((1 << k) == C4) c4_shift = k;
+    const long long per_env = (long long)N * C4;
+    const long long chunk = (long long)0x7fffff00 / per_env;
+    if (chunk < 1) return MTFJSP_E_ARG;
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = B - b0 < chunk ? B - b0 : chunk;
+        const unsigned total = (unsigned)(nb * per_env);
+        const long long r0 = b0 * N;
+        aggregate_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(g) + r0 * C4, reinterpret_cast<const float2*>(adj_w) + r0, adj_src + r0,
+            adj_dst + r0, reinterpret_cast<float4*>(out) + r0 * C4, total, N, C4, c4_shift);
     }
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }

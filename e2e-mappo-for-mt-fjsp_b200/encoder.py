@@ -39,9 +39,7 @@ def _optr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def aggregate(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False):
-    """out[b,v] = (x[b,v] + w_job*x[b,v-1] + w_mach*x[b,src]) / in_degree (FP32 FMAs); h [B,N,C] f32;
-    x = relu?(h*in_scale+in_shift) when an input affine is given (the producing layer's BatchNorm, folded in)."""
+def _aggregate_raw(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False):
     B, N, Cc = h.shape
     h = h.contiguous()
     out = torch.empty_like(h)
@@ -50,13 +48,70 @@ def aggregate(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False):
     return out
 
 
-def graph_mean(h, in_scale=None, in_shift=None, relu=False):
+def ell_invert(adj_src):
+    """adj_dst[b,u] = v with adj_src[b,v] == u (machine successor), -1 if none; needed by the aggregation backward."""
+    B, N = adj_src.shape
+    adj_dst = torch.empty_like(adj_src)
+    check(_lib.lib().mtfjsp_enc_ell_invert(_ptr(adj_src.contiguous()), _ptr(adj_dst), B, N, _stream()), "mtfjsp_enc_ell_invert")
+    return adj_dst
+
+
+class _AggregateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, adj_w, adj_src, adj_dst):
+        ctx.save_for_backward(adj_w, adj_src, adj_dst)
+        return _aggregate_raw(h, adj_w, adj_src)
+
+    @staticmethod
+    def backward(ctx, g):
+        adj_w, adj_src, adj_dst = ctx.saved_tensors
+        B, N, Cc = g.shape
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        check(_lib.lib().mtfjsp_enc_aggregate_bwd(_ptr(g), _ptr(adj_w), _ptr(adj_src), _ptr(adj_dst), _ptr(out), B, N, Cc,
+                                                  _stream()), "mtfjsp_enc_aggregate_bwd")
+        return out, None, None, None
+
+
+def aggregate(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False, adj_dst=None):
+    """out[b,v] = (x[b,v] + w_job*x[b,v-1] + w_mach*x[b,src]) / in_degree (FP32 FMAs); h [B,N,C] f32;
+    x = relu?(h*in_scale+in_shift) when an input affine is given (the producing layer's BatchNorm, folded in).
+    Differentiable in h (PPO update): the backward is the transposed gather, `mtfjsp_enc_aggregate_bwd`."""
+    adj_w, adj_src = adj_w.contiguous(), adj_src.contiguous()
+    if torch.is_grad_enabled() and h.requires_grad:
+        if in_scale is not None:
+            raise ValueError("the folded input affine is an inference-path option")
+        return _AggregateFn.apply(h, adj_w, adj_src, ell_invert(adj_src) if adj_dst is None else adj_dst)
+    return _aggregate_raw(h, adj_w, adj_src, in_scale, in_shift, relu)
+
+
+class _GraphMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h):
+        ctx.N = h.shape[1]
+        return _graph_mean_raw(h)
+
+    @staticmethod
+    def backward(ctx, g):
+        inv = torch.tensor(1.0 / ctx.N, dtype=torch.float32).item()
+        return (g * inv).unsqueeze(1).expand(-1, ctx.N, -1)
+
+
+def _graph_mean_raw(h, in_scale=None, in_shift=None, relu=False):
     B, N, Cc = h.shape
     h = h.contiguous()
     out = torch.empty((B, Cc), dtype=h.dtype, device=h.device)
     check(_lib.lib().mtfjsp_enc_graph_mean(_ptr(h), _ptr(out), B, N, Cc, _optr(in_scale), _optr(in_shift), int(relu),
                                            _stream()), "mtfjsp_enc_graph_mean")
     return out
+
+
+def graph_mean(h, in_scale=None, in_shift=None, relu=False):
+    if torch.is_grad_enabled() and h.requires_grad:
+        if in_scale is not None:
+            raise ValueError("the folded input affine is an inference-path option")
+        return _GraphMeanFn.apply(h)
+    return _graph_mean_raw(h, in_scale, in_shift, relu)
 
 
 def linear_tf32(x, weight, bias, in_scale=None, in_shift=None, relu=False, stats=None):
@@ -147,13 +202,19 @@ def seeded_state_dict(keys: dict, seed: int):
     return sd
 
 
-def _bn_train(x, w, b, eps=1e-5):
-    """BatchNorm1d with batch statistics (the reference never leaves train mode)."""
-    return F.batch_norm(x, None, None, w, b, True, 0.0, eps)
+def _bn_train(x, w, b, eps=1e-5, groups=1):
+    """BatchNorm1d with batch statistics (the reference never leaves train mode).  groups > 1: the rows are `groups`
+    consecutive blocks, each normalised with its own statistics -- one block per buffered step, so a batched PPO
+    re-forward sees exactly the statistics of the reference's one-step-at-a-time loop (ppo_algorithm.py:739-775)."""
+    if groups == 1:
+        return F.batch_norm(x, None, None, w, b, True, 0.0, eps)
+    xs = x.reshape(groups, -1, x.shape[-1])
+    var, mean = torch.var_mean(xs, dim=1, unbiased=False, keepdim=True)
+    return ((xs - mean) * torch.rsqrt(var + eps) * w + b).reshape(x.shape)
 
 
 class _Params:
-    def __init__(self, keys, state_dict, device):
+    def __init__(self, keys, state_dict, device, trainable=False):
         missing = [k for k in keys if k not in state_dict]
         extra = [k for k in state_dict if k not in keys]
         if missing or extra:
@@ -163,50 +224,62 @@ class _Params:
             t = torch.as_tensor(state_dict[k])
             if tuple(t.shape) != tuple(shape):
                 raise ValueError("%s: shape %s, expected %s" % (k, tuple(t.shape), tuple(shape)))
-            self.p[k] = t.to(device=device, dtype=torch.float32 if t.is_floating_point() else t.dtype).contiguous()
+            self.p[k] = t.to(device=device, dtype=torch.float32 if t.is_floating_point() else t.dtype).contiguous().clone()
+            if trainable and self.is_parameter(k):
+                self.p[k].requires_grad_(True)
+
+    @staticmethod
+    def is_parameter(k):
+        return not k.endswith(("running_mean", "running_var", "num_batches_tracked"))
 
     def __getitem__(self, k):
         return self.p[k]
 
+    def parameters(self):
+        """Learnable tensors in state_dict order (what `module.parameters()` yields in the reference)."""
+        return [t for k, t in self.p.items() if self.is_parameter(k)]
 
-class JobActor:
-    """Forward of Operation_Actor_JointAction_selfCritic (model/actor_critic.py:104-296) on native observations."""
+    def state_dict(self):
+        return {k: t.detach().clone() for k, t in self.p.items()}
 
-    def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None, precision="fp32"):
-        """precision "fp32": library FP32 GEMMs, bit-for-bit the reference's arithmetic types;
-        "tf32": the fused tcgen05 layer kernel (hidden must be 128) -- BatchNorm folded into prologue/epilogue."""
-        self.J, self.M, self.N, self.H = n_job, n_machine, n_job * n_machine, hidden
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.w = _Params(job_actor_keys(hidden, in_dim), state_dict, self.device)
-        if precision not in ("fp32", "tf32"):
-            raise ValueError("precision must be 'fp32' or 'tf32'")
-        if precision == "tf32" and hidden != 128:
-            raise ValueError("the tcgen05 layer kernel is built for hidden = 128")
-        self.precision = precision
 
-    def _mlp(self, l, x):  # gcn_mlp.py:238-249
+def _mlp3_tanh(w, prefix, x):
+    """MLPActor / MLPCritic with three linears and tanh between them (model/gcn_mlp.py:258-320)."""
+    h = torch.tanh(F.linear(x, w[prefix + "linears.0.weight"], w[prefix + "linears.0.bias"]))
+    h = torch.tanh(F.linear(h, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"]))
+    return F.linear(h, w[prefix + "linears.2.weight"], w[prefix + "linears.2.bias"])
+
+
+class _GraphEncoder:
+    """GraphCNN (model/gcn_mlp.py:109-197) over the env's ELL adjacency; shared by the job actor and the global critic."""
+
+    def _mlp(self, l, x, groups=1):  # gcn_mlp.py:238-249
         w = self.w
         p = "encoder.feature_extract.mlps.%d." % l
         h = x
         for i in (0, 1):
             h = F.linear(h, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i])
-            h = F.relu(_bn_train(h, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i]))
+            h = F.relu(_bn_train(h, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i], groups=groups))
         return F.linear(h, w[p + "linears.2.weight"], w[p + "linears.2.bias"])
 
-    def encode(self, task_fea, adj_w, adj_src):
+    def encode(self, task_fea, adj_w, adj_src, groups=1, adj_dst=None):
         """GraphCNN.forward (gcn_mlp.py:160-197): two rounds of aggregate -> MLP -> BN -> ReLU, then mean pooling.
-        task_fea [B,N,12] f32, adj_w [B,N,2] f32, adj_src [B,N] i16 -> (pooled [B,H], nodes [B,N,H])."""
+        task_fea [B,N,12] f32, adj_w [B,N,2] f32, adj_src [B,N] i16 -> (pooled [B,H], nodes [B,N,H]).
+        groups: B is `groups` consecutive env batches with separate BatchNorm statistics (see _bn_train)."""
         B = task_fea.shape[0]
         w = self.w
         h = task_fea.to(torch.float32)
         if self.precision == "tf32":
+            if groups != 1:
+                raise ValueError("the tf32 path is the rollout path: one BatchNorm group")
             return self._encode_tf32(h, adj_w, adj_src)
         for l in (0, 1):
-            pooled = aggregate(h, adj_w, adj_src)                                   # gcn_mlp.py:125-149
-            z = self._mlp(l, pooled.reshape(B * self.N, -1))
+            pooled = aggregate(h, adj_w, adj_src, adj_dst=adj_dst)                  # gcn_mlp.py:125-149
+            z = self._mlp(l, pooled.reshape(B * self.N, -1), groups)
             z = F.relu(_bn_train(z, w["encoder.feature_extract.batch_norms.%d.weight" % l],
-                                 w["encoder.feature_extract.batch_norms.%d.bias" % l]))   # gcn_mlp.py:154-157
+                                 w["encoder.feature_extract.batch_norms.%d.bias" % l], groups=groups))   # gcn_mlp.py:154-157
             h = z.reshape(B, self.N, self.H)
+        self._pending = None
         return graph_mean(h), h                                                    # gcn_mlp.py:192
 
     def _encode_tf32(self, h, adj_w, adj_src):
@@ -233,53 +306,80 @@ class JobActor:
         self._pending = (sc, sh)  # outer BatchNorm + ReLU of the last layer, applied by the consumers below
         return graph_mean(h, sc, sh, relu=True), h
 
-    def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None):
-        """-> task_index [B], action_index [B] (job), log_a [B], prob [B,J], h_g_o_pooled [B,H], job_v [B,2]."""
-        w = self.w
-        B = task_fea.shape[0]
-        pooled, nodes = self.encode(task_fea, adj_w, adj_src)
-        cand = candidate.long()
-        cf = torch.gather(nodes, 1, cand.unsqueeze(-1).expand(-1, self.J, self.H))     # actor_critic.py:197-207
-        if self.precision == "tf32":
+    def candidate_features(self, nodes, candidate):
+        cf = torch.gather(nodes, 1, candidate.long().unsqueeze(-1).expand(-1, self.J, self.H))   # actor_critic.py:197-207
+        if self._pending is not None:
             sc, sh = self._pending
             cf = torch.relu(cf * sc + sh)
+        return cf
+
+    def parameters(self):
+        return self.w.parameters()
+
+    def state_dict(self):
+        return self.w.state_dict()
+
+
+def _check_precision(precision, hidden):
+    if precision not in ("fp32", "tf32"):
+        raise ValueError("precision must be 'fp32' or 'tf32'")
+    if precision == "tf32" and hidden != 128:
+        raise ValueError("the tcgen05 layer kernel is built for hidden = 128")
+
+
+class JobActor(_GraphEncoder):
+    """Forward of Operation_Actor_JointAction_selfCritic (model/actor_critic.py:104-296) on native observations."""
+
+    def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None, precision="fp32", trainable=False):
+        """precision "fp32": library FP32 GEMMs, bit-for-bit the reference's arithmetic types;
+        "tf32": the fused tcgen05 layer kernel (hidden must be 128) -- BatchNorm folded into prologue/epilogue."""
+        self.J, self.M, self.N, self.H = n_job, n_machine, n_job * n_machine, hidden
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.w = _Params(job_actor_keys(hidden, in_dim), state_dict, self.device, trainable)
+        _check_precision(precision, hidden)
+        self.precision = precision
+        self._pending = None
+
+    def evaluate(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, groups=1, adj_dst=None):
+        """Action distribution and local values without sampling: prob [B,J], h_g_o_pooled [B,H], job_v [B,2].
+        h_g_m_pooled [B,H] or None (the learned `_input` vector stands in, actor_critic.py:232-240)."""
+        w = self.w
+        pooled, nodes = self.encode(task_fea, adj_w, adj_src, groups, adj_dst)
+        cf = self.candidate_features(nodes, candidate)
         gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
         x = torch.cat((cf, pooled.unsqueeze(-2).expand_as(cf), gm), dim=-1)              # actor_critic.py:244-247
-        s = torch.tanh(F.linear(x, w["o_policy.linears.0.weight"], w["o_policy.linears.0.bias"]))
-        s = torch.tanh(F.linear(s, w["o_policy.linears.1.weight"], w["o_policy.linears.1.bias"]))
-        s = F.linear(s, w["o_policy.linears.2.weight"], w["o_policy.linears.2.bias"]).squeeze(-1)
+        s = _mlp3_tanh(w, "o_policy.", x).squeeze(-1)
         s = s.masked_fill(mask_operation.bool(), float("-inf"))                          # actor_critic.py:266-268
         prob = F.softmax(s, dim=-1)
+        job_v = _mlp3_tanh(w, "job_critic.", pooled)
+        return prob, pooled, job_v
+
+    def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None):
+        """-> task_index [B], action_index [B] (job), log_a [B], prob [B,J], h_g_o_pooled [B,H], job_v [B,2]."""
+        prob, pooled, job_v = self.evaluate(task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation)
         if greedy:                                                                       # agent_func.py greedy / sample
             a = prob.argmax(dim=-1)
         else:
             a = torch.multinomial(prob, 1, generator=generator).squeeze(-1)
         log_a = torch.log(prob.gather(1, a.unsqueeze(-1)).squeeze(-1))
-        task_index = cand.gather(1, a.unsqueeze(-1)).squeeze(-1)
-        v = torch.tanh(F.linear(pooled, w["job_critic.linears.0.weight"], w["job_critic.linears.0.bias"]))
-        v = torch.tanh(F.linear(v, w["job_critic.linears.1.weight"], w["job_critic.linears.1.bias"]))
-        job_v = F.linear(v, w["job_critic.linears.2.weight"], w["job_critic.linears.2.bias"])
+        task_index = candidate.long().gather(1, a.unsqueeze(-1)).squeeze(-1)
         return task_index, a, log_a, prob, pooled, job_v
 
 
-class MachineActor:
-    """Forward of Machine_Actor_JointAction_selfGAT_selfCritic (model/actor_critic.py:359-498)."""
-
-    def __init__(self, state_dict, n_machine, hidden=128, device=None, precision="fp32"):
-        self.M, self.H = n_machine, hidden
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.w = _Params(machine_actor_keys(hidden), state_dict, self.device)
-        if precision not in ("fp32", "tf32") or (precision == "tf32" and hidden != 128):
-            raise ValueError("precision must be 'fp32' or 'tf32' (tf32 needs hidden = 128)")
-        self.precision = precision
-        self._Wt = self.w["gat_layer.W"].t().contiguous()  # [out, in] = the layout the tensor-core layer takes
+class _MachineTrunk:
+    """Machine-node embedding shared by the machine actor and the global critic (actor_critic.py:381-440, 666-700):
+    two input projections, the GAT layer (model/gat.py:68-159) applied three times on the fixed 2-node graph
+    [[1,1],[0,1]] in closed form, BatchNorm, mean over machines."""
 
     def _gat(self, h1, h2):
-        """GATLayer.forward (gat.py:82-159) on the fixed 2-node graph: node 1 attends to {1, 2}, node 2 to itself."""
+        """GATLayer.forward (gat.py:82-159): node 1 attends to {1, 2}, node 2 to itself."""
         W, a = self.w["gat_layer.W"], self.w["gat_layer.a"]
         H = self.H
         if self.precision == "tf32":  # both node sets in one [2*rows,128] x [128,128] tensor-core launch
-            t = linear_tf32(torch.cat((h1, h2), dim=0), self._Wt, None)
+            Wt = getattr(self, "_Wt", None)  # [out, in] = the layout the tensor-core layer takes (inference weights)
+            if Wt is None:
+                Wt = self._Wt = W.t().contiguous()
+            t = linear_tf32(torch.cat((h1, h2), dim=0), Wt, None)
             t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
         else:
             t1, t2 = h1 @ W, h2 @ W
@@ -289,9 +389,8 @@ class MachineActor:
         att = torch.softmax(torch.stack((e11, e12), dim=-1), dim=-1)
         return att[..., 0:1] * t1 + att[..., 1:2] * t2, t2
 
-    def forward(self, machine_fea_1, machine_fea_2, h_pooled_o, machine_mask):
-        """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] f32, h_pooled_o [B,H], machine_mask [B,M] (1 = infeasible)
-        -> mch_prob [B,M], h_pooled [B,H], machine_v [B,2]."""
+    def trunk(self, machine_fea_1, machine_fea_2, groups=1):
+        """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] -> (nodes [B,M,H], pooled [B,H])."""
         w = self.w
         B = machine_fea_1.shape[0]
         h1 = F.linear(machine_fea_1.to(torch.float32), w["m_fea_1_fcl.weight"]).reshape(B * self.M, self.H)
@@ -300,15 +399,77 @@ class MachineActor:
         h1, h2 = self._gat(F.elu(h1), F.elu(h2))
         h1, h2 = self._gat(F.elu(h1), F.elu(h2))
         hm = torch.stack((h1, h2), dim=1).mean(dim=-2)                                   # actor_critic.py:420
-        nodes = _bn_train(hm, w["bn.weight"], w["bn.bias"]).reshape(B, self.M, self.H)   # actor_critic.py:434
-        pooled = nodes.mean(dim=1)
+        nodes = _bn_train(hm, w["bn.weight"], w["bn.bias"], groups=groups).reshape(B, self.M, self.H)   # actor_critic.py:434
+        return nodes, nodes.mean(dim=1)
+
+    def parameters(self):
+        return self.w.parameters()
+
+    def state_dict(self):
+        return self.w.state_dict()
+
+
+class MachineActor(_MachineTrunk):
+    """Forward of Machine_Actor_JointAction_selfGAT_selfCritic (model/actor_critic.py:359-498)."""
+
+    def __init__(self, state_dict, n_machine, hidden=128, device=None, precision="fp32", trainable=False):
+        self.M, self.H = n_machine, hidden
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.w = _Params(machine_actor_keys(hidden), state_dict, self.device, trainable)
+        _check_precision(precision, hidden)
+        self.precision = precision
+
+    def heads(self, nodes, pooled, h_pooled_o, machine_mask):
+        w = self.w
+        B = nodes.shape[0]
         x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
-        s = torch.tanh(F.linear(x, w["m_policy.linears.0.weight"], w["m_policy.linears.0.bias"]))
-        s = torch.tanh(F.linear(s, w["m_policy.linears.1.weight"], w["m_policy.linears.1.bias"]))
-        s = F.linear(s, w["m_policy.linears.2.weight"], w["m_policy.linears.2.bias"]).squeeze(-1) * 10
+        s = _mlp3_tanh(w, "m_policy.", x).squeeze(-1) * 10
         s = s.masked_fill(machine_mask.reshape(B, self.M).bool(), float("-inf"))
-        prob = F.softmax(s, dim=-1)
-        v = torch.tanh(F.linear(pooled, w["machine_critic.linears.0.weight"], w["machine_critic.linears.0.bias"]))
-        v = torch.tanh(F.linear(v, w["machine_critic.linears.1.weight"], w["machine_critic.linears.1.bias"]))
-        machine_v = F.linear(v, w["machine_critic.linears.2.weight"], w["machine_critic.linears.2.bias"])
+        return F.softmax(s, dim=-1), _mlp3_tanh(w, "machine_critic.", pooled)
+
+    def forward(self, machine_fea_1, machine_fea_2, h_pooled_o, machine_mask, groups=1):
+        """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] f32, h_pooled_o [B,H], machine_mask [B,M] (1 = infeasible)
+        -> mch_prob [B,M], h_pooled [B,H], machine_v [B,2]."""
+        nodes, pooled = self.trunk(machine_fea_1, machine_fea_2, groups)
+        prob, machine_v = self.heads(nodes, pooled, h_pooled_o, machine_mask)
         return prob, pooled, machine_v
+
+
+def global_critic_keys(hidden=128, in_dim=12):
+    """state_dict layout of Global_Critic_JointAction_GAT (model/actor_critic.py:506-585); no checkpoint of it is
+    shipped, the layout is pinned against the reference module by tests/golden/gen_ppo_golden.py."""
+    H = hidden
+    k = {n: s for n, s in job_actor_keys(hidden, in_dim).items() if n.startswith("encoder.")}
+    for n, s in (("weight", (H,)), ("bias", (H,)), ("running_mean", (H,)), ("running_var", (H,)), ("num_batches_tracked", ())):
+        k["bn." + n] = s
+    k["m_fea_1_fcl.weight"] = (H, 6); k["m_fea_2_fcl.weight"] = (H, 8)
+    k["gat_layer.W"] = (H, H); k["gat_layer.a"] = (1, 2 * H, 1)
+    k["fcl_pooling.weight"] = (H, H)
+    k["critic.linears.0.weight"] = (H, 2 * H); k["critic.linears.0.bias"] = (H,)
+    k["critic.linears.1.weight"] = (H, H); k["critic.linears.1.bias"] = (H,)
+    k["critic.linears.2.weight"] = (4, H); k["critic.linears.2.bias"] = (4,)
+    return k
+
+
+class GlobalCritic(_GraphEncoder, _MachineTrunk):
+    """Forward of Global_Critic_JointAction_GAT (model/actor_critic.py:587-751): graph encoder over the op nodes,
+    machine trunk over the two machine feature sets, 4 values (mk, pt, tt, idle) from the two pooled embeddings."""
+
+    def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None, trainable=False):
+        self.J, self.M, self.N, self.H = n_job, n_machine, n_job * n_machine, hidden
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.w = _Params(global_critic_keys(hidden, in_dim), state_dict, self.device, trainable)
+        self.precision = "fp32"
+        self._pending = None
+
+    def parameters(self):
+        return self.w.parameters()
+
+    def state_dict(self):
+        return self.w.state_dict()
+
+    def forward(self, task_fea, adj_w, adj_src, machine_fea_1, machine_fea_2, groups=1, adj_dst=None):
+        """-> v [B,4].  (The candidate features the reference gathers at :650-655 are not used by its value head.)"""
+        pooled_o, _ = self.encode(task_fea, adj_w, adj_src, groups, adj_dst)
+        _, pooled_m = self.trunk(machine_fea_1, machine_fea_2, groups)
+        return _mlp3_tanh(self.w, "critic.", torch.cat((pooled_m, pooled_o), dim=-1))    # actor_critic.py:737-750

@@ -1,0 +1,268 @@
+"""Batched MAPPO update on the device.
+
+Reference: PPOAlgorithm.global_update_JointActions_GAT_selfCritic (algorithm/ppo_algorithm.py:539-1124) and the
+rollout bookkeeping that feeds it (Run.py:290-545, trainer/replaybuffer.py:18-204).
+
+What changes against the reference, and what does not:
+
+* The reference re-runs the three networks ONE BUFFERED STEP AT A TIME inside every minibatch (python loops at
+  ppo_algorithm.py:632-659 and :739-775: mini_bs forward passes of B envs each).  Here a minibatch is ONE forward
+  over [mini_bs * B] graphs.  The two things that made the loop look sequential are handled explicitly:
+    - BatchNorm batch statistics are per buffered step -> `groups = mini_bs` in encoder._bn_train;
+    - the job actor of item i receives the machine embedding of item i-1 of the (shuffled) minibatch, item 0 the
+      learned `_input` vector (:746 `h_mch_pooled`).  That embedding depends only on item i-1's machine features, so
+      all machine trunks are evaluated first and handed on shifted by one.
+  Losses, clipping, optimiser steps and their order are the reference's, line for line (cited below).
+* Observations are the env's native ones: F32 features and the ELL adjacency (10 bytes per node) instead of two
+  dense [steps, B, N, N] float64 adjacencies; the aggregation forward / backward are the hand-written kernels of
+  csrc/mtfjsp_encoder.cu, GAE is csrc `gae4_kernel`; the dense layers run on library FP32 GEMMs under autograd.
+* Data-parallel training: every rank updates on its own env slice, gradients are averaged with one
+  NCCL allreduce per backward pass, advantage statistics are summed across ranks (buffer.gae4).  BatchNorm statistics
+  stay local to the rank (the reference's statistics are per B-env batch as well).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch.distributions import Categorical
+
+from . import encoder as _enc
+from .buffer import gae4
+
+
+@dataclass
+class PPOConfig:
+    """Defaults of the reference's parameters.py:77-97."""
+    lr: float = 1e-3
+    lr_eps: float = 1e-5
+    use_lr_decay: bool = False
+    decay_step_size: int = 20
+    decay_ratio: float = 0.96
+    gamma: float = 0.99
+    lam: float = 0.98
+    epsilon: float = 0.2
+    entropy_beta: float = 0.01
+    k_epochs: int = 5
+    use_grad_clip: bool = True
+    clip_grad: float = 0.5
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_grads(params):
+    """One flat NCCL/gloo allreduce over every gradient that exists, then the mean."""
+    ws = _world()
+    if ws == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(ws)
+    o = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[o:o + n].view_as(g))
+        o += n
+    return flat.numel() * flat.element_size()
+
+
+class MAPPOUpdate:
+    def __init__(self, job_actor, machine_actor, global_critic, cfg: PPOConfig | None = None):
+        self.job, self.mch, self.critic = job_actor, machine_actor, global_critic
+        self.cfg = cfg or PPOConfig()
+        c = self.cfg
+        mk = lambda net: torch.optim.Adam(net.parameters(), lr=c.lr, eps=c.lr_eps)          # ppo_algorithm.py:57-79
+        self.opt_job, self.opt_mch, self.opt_critic = mk(self.job), mk(self.mch), mk(self.critic)
+        sch = lambda o: torch.optim.lr_scheduler.StepLR(o, step_size=c.decay_step_size, gamma=c.decay_ratio)
+        self.sched = [sch(self.opt_job), sch(self.opt_mch), sch(self.opt_critic)]
+        self.allreduce_bytes = 0
+
+    # ---- values and advantages (ppo_algorithm.py:585-703), no gradients ---------------------------------------------
+    def _critic_all(self, task_fea, adj_w, adj_src, mf1, mf2, max_rows=1 << 22):
+        """Global critic over all T buffered steps, T BatchNorm groups, chunked by whole steps."""
+        T, B, N = task_fea.shape[:3]
+        per = max(1, max_rows // (B * N))
+        out = []
+        for t0 in range(0, T, per):
+            t1 = min(T, t0 + per)
+            g = t1 - t0
+            v = self.critic.forward(task_fea[t0:t1].reshape(g * B, N, -1), adj_w[t0:t1].reshape(g * B, N, 2),
+                                    adj_src[t0:t1].reshape(g * B, N), mf1[t0:t1].reshape(g * B, -1, 6),
+                                    mf2[t0:t1].reshape(g * B, -1, 8), groups=g)
+            out.append(v.reshape(g, B, 4))
+        return torch.cat(out, dim=0)
+
+    def advantages(self, bt):
+        c = self.cfg
+        with torch.no_grad():
+            multi_v = self._critic_all(bt["task_fea"], bt["adj_w"], bt["adj_src"], bt["mach_fea1"], bt["mach_fea2"])
+            mf1_n = torch.cat((bt["mach_fea1"][1:], bt["mach_fea1"][-1:]), dim=0)                     # :598-603
+            multi_v_n = self._critic_all(bt["task_fea_n"], bt["adj_w_n"], bt["adj_src_n"], mf1_n, bt["mach_fea2_n"])
+            jv, mv, jvn, mvn = bt["job_v"], bt["mch_v"], bt["job_v_n"], bt["mch_v_n"]
+            # streams in the reference's order mk, pt, tt, it: local values = job[0], mch[0], mch[1], job[1] (:449-451)
+            v_loc = torch.stack((jv[..., 0], mv[..., 0], mv[..., 1], jv[..., 1]), dim=-1)
+            v_loc_n = torch.stack((jvn[..., 0], mvn[..., 0], mvn[..., 1], jvn[..., 1]), dim=-1)
+            adv_loc = gae4(bt["r4"], v_loc, v_loc_n, bt["done"], c.gamma, c.lam)                      # :438-489
+            adv_glob = gae4(bt["r4"], multi_v, multi_v_n, bt["done"], c.gamma, c.lam)                 # :491-536
+            return dict(adv_loc=adv_loc, adv_glob=adv_glob, tgt_loc=adv_loc + v_loc, tgt_glob=adv_glob + multi_v,
+                        multi_v=multi_v, multi_v_n=multi_v_n)
+
+    # ---- one minibatch (ppo_algorithm.py:716-1073) -------------------------------------------------------------------
+    def _minibatch(self, bt, adv, idx):
+        c = self.cfg
+        S = idx.numel()
+        T, B, N = bt["task_fea"].shape[:3]
+        J, M, H = self.job.J, self.job.M, self.job.H
+        take = lambda name: bt[name].index_select(0, idx)
+        tf = take("task_fea").reshape(S * B, N, -1)
+        aw, asrc = take("adj_w").reshape(S * B, N, 2), take("adj_src").reshape(S * B, N)
+        mf1, mf2 = take("mach_fea1").reshape(S * B, M, 6), take("mach_fea2").reshape(S * B, M, 8)
+        adst = _enc.ell_invert(asrc)
+
+        # machine trunks first: item i's job head consumes item i-1's machine embedding (:739-768)
+        nodes_m, pooled_m = self.mch.trunk(mf1, mf2, groups=S)
+        inp = self.job.w["_input"][None, None, :].expand(1, B, H)
+        gm = torch.cat((inp, pooled_m.reshape(S, B, H)[:-1]), dim=0).reshape(S * B, H)
+        prob_j, pooled_o, job_v = self.job.evaluate(tf, aw, asrc, take("candidate").reshape(S * B, J), gm,
+                                                    take("job_mask").reshape(S * B, J), groups=S, adj_dst=adst)
+        prob_m, mch_v = self.mch.heads(nodes_m, pooled_m, pooled_o, take("mach_mask").reshape(S * B, M))
+        prob_j, prob_m = prob_j.reshape(S, B, J), prob_m.reshape(S, B, M)
+        job_v, mch_v = job_v.reshape(S, B, 2), mch_v.reshape(S, B, 2)
+
+        dist_j, dist_m = Categorical(probs=prob_j), Categorical(probs=prob_m)                        # :779-783
+        ratio_j = torch.exp(dist_j.log_prob(take("a_job").long()) - take("log_a"))                    # :795
+        ratio_m = torch.exp(dist_m.log_prob(take("a_mach").long()) - take("m_log_a"))                 # :796
+        ag, al = adv["adv_glob"].index_select(0, idx), adv["adv_loc"].index_select(0, idx)
+        rw = take("rw")
+        w_mk, w_ec, w_tt = rw[..., 0], rw[..., 1], rw[..., 2]
+
+        def clipped(ratio, a):                                                                      # :800-814
+            return torch.min(ratio * a, torch.clamp(ratio, 1 - c.epsilon, 1 + c.epsilon) * a)
+
+        def weighted_global(ratio):                                                                 # :820-822, :861-863
+            return (w_mk * clipped(ratio, ag[..., 0]) + w_ec * (clipped(ratio, ag[..., 1]) + clipped(ratio, ag[..., 3]))
+                    + w_tt * clipped(ratio, ag[..., 2]))
+
+        glob_j, glob_m = weighted_global(ratio_j), weighted_global(ratio_m)
+        loc_j = w_mk * clipped(ratio_j, al[..., 0]) + w_ec * clipped(ratio_j, al[..., 3])              # :826-835
+        loc_m = w_ec * clipped(ratio_m, al[..., 1]) + w_tt * clipped(ratio_m, al[..., 2])              # :867-876
+        tl = adv["tgt_loc"].index_select(0, idx)
+        mse = F.mse_loss
+        crit_j = mse(w_mk * job_v[..., 0], w_mk * tl[..., 0]) + mse(w_ec * job_v[..., 1], w_ec * tl[..., 3])    # :896-907
+        crit_m = mse(w_ec * mch_v[..., 0], w_ec * tl[..., 1]) + mse(w_tt * mch_v[..., 1], w_tt * tl[..., 2])
+        loss_j = -2 * glob_j + (-1) * loc_j + 0.5 * crit_j - c.entropy_beta * dist_j.entropy()         # :913
+        loss_m = -2 * glob_m + (-1) * loc_m + 0.5 * crit_m - c.entropy_beta * dist_m.entropy()         # :914
+        # The reference calls clip_grad_norm_ right after zero_grad and BEFORE backward (:918-930): no gradient
+        # exists at that point, so the actors are not clipped.  Reproduced by not clipping them.
+        self.opt_job.zero_grad(set_to_none=True)
+        self.opt_mch.zero_grad(set_to_none=True)
+        loss = loss_j.mean() + loss_m.mean()                                                         # :932
+        loss.backward()
+        self.allreduce_bytes += allreduce_mean_grads(self.job.parameters() + self.mch.parameters())
+        self.opt_job.step()
+        self.opt_mch.step()
+
+        # global critic on the same minibatch (:943-1000): backward, THEN clip, then step
+        v_s = self.critic.forward(tf, aw, asrc, mf1, mf2, groups=S, adj_dst=adst).reshape(S, B, 4)
+        tg = adv["tgt_glob"].index_select(0, idx)
+        crit = (mse(w_mk * tg[..., 0], w_mk * v_s[..., 0]) + mse(w_ec * tg[..., 1], w_ec * v_s[..., 1])
+                + mse(w_ec * tg[..., 3], w_ec * v_s[..., 3]) + mse(w_tt * tg[..., 2], w_tt * v_s[..., 2]))     # :965-976
+        self.opt_critic.zero_grad(set_to_none=True)
+        crit.backward()
+        self.allreduce_bytes += allreduce_mean_grads(self.critic.parameters())
+        if c.use_grad_clip:
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), c.clip_grad)                   # :993-996
+        self.opt_critic.step()
+        return loss_j.mean().detach(), loss_m.mean().detach(), crit.detach()
+
+    def update(self, bt, mini_bs, orders=None, generator=None):
+        """bt: dict of [T, B, ...] device tensors (see `collect`).  orders: optional list (one per epoch) of index
+        permutations of range(T), for replaying the reference's SubsetRandomSampler draws in tests.
+        -> (loss_mean [3], loss_std [3]) over the K epochs: job actor, machine actor, global critic (:1080-1124)."""
+        c = self.cfg
+        T = bt["task_fea"].shape[0]
+        dev = bt["task_fea"].device
+        adv = self.advantages(bt)
+        per_epoch = []
+        for k in range(c.k_epochs):
+            if orders is not None:
+                perm = torch.as_tensor(orders[k], device=dev, dtype=torch.long)
+            elif generator is None:
+                perm = torch.randperm(T, device=dev)
+            else:
+                perm = torch.randperm(T, generator=generator, device=generator.device).to(dev)
+            lj, lm, lc = [], [], []
+            for s0 in range(0, T, mini_bs):                                                          # BatchSampler(..., drop_last=False)
+                a, b, cc = self._minibatch(bt, adv, perm[s0:s0 + mini_bs])
+                lj.append(a); lm.append(b); lc.append(cc)
+            per_epoch.append(torch.stack((torch.stack(lj).mean(), torch.stack(lm).mean(), torch.stack(lc).mean())))
+        if c.use_lr_decay:
+            for s in self.sched:
+                s.step()
+        pe = torch.stack(per_epoch)
+        std = pe.std(dim=0) if c.k_epochs > 1 else torch.full((3,), float("nan"), device=dev)
+        return pe.mean(dim=0), std
+
+
+def collect(rollout, weights_per_episode):
+    """Runs len(weights_per_episode) episodes with `rollout` (Run.py:290-545) and returns the update batch: a dict of
+    [T, B, ...] device tensors, T = episodes * N.  `*_n` are the next-state fields (terminal observation included)."""
+    env = rollout.env
+    B, N, M, J = env.B, env.N, env.M, env.J
+    job, mch = rollout.job, rollout.mch
+    T = len(weights_per_episode) * N
+    dev = env.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    bt = dict(
+        task_fea=torch.empty((T, B, N, 12), **f32), adj_w=torch.empty((T, B, N, 2), **f32),
+        adj_src=torch.empty((T, B, N), dtype=torch.int16, device=dev),
+        candidate=torch.empty((T, B, J), dtype=torch.int32, device=dev), job_mask=torch.empty((T, B, J), dtype=torch.uint8, device=dev),
+        mach_fea1=torch.empty((T, B, M, 6), **f32), mach_fea2=torch.empty((T, B, M, 8), **f32),
+        mach_mask=torch.empty((T, B, M), dtype=torch.uint8, device=dev),
+        a_job=torch.empty((T, B), dtype=torch.int32, device=dev), a_mach=torch.empty((T, B), dtype=torch.int32, device=dev),
+        log_a=torch.empty((T, B), **f32), m_log_a=torch.empty((T, B), **f32),
+        job_v=torch.empty((T, B, 2), **f32), mch_v=torch.empty((T, B, 2), **f32),
+        job_v_n=torch.empty((T, B, 2), **f32), mch_v_n=torch.empty((T, B, 2), **f32),
+        r4=torch.empty((T, B, 4), **f32), done=torch.empty((T, B), **f32), rw=torch.empty((T, B, 3), **f32),
+        task_fea_n=torch.empty((T, B, N, 12), **f32), adj_w_n=torch.empty((T, B, N, 2), **f32),
+        adj_src_n=torch.empty((T, B, N), dtype=torch.int16, device=dev), mach_fea2_n=torch.empty((T, B, M, 8), **f32),
+    )
+    t = 0
+    for w in weights_per_episode:
+        rollout.begin_episode(w)
+        wt = torch.as_tensor(w, dtype=torch.float32, device=dev)
+        for s in range(N):
+            bt["task_fea"][t].copy_(env.task_fea); bt["adj_w"][t].copy_(env.adj_w); bt["adj_src"][t].copy_(env.adj_src)
+            bt["candidate"][t].copy_(env.candidate); bt["job_mask"][t].copy_(env.job_mask); bt["mach_fea2"][t].copy_(env.mach_fea)
+            rollout.step()
+            bt["mach_fea1"][t].copy_(env.mfea1_buf); bt["mach_mask"][t].copy_(env.mach_mask)
+            bt["a_job"][t].copy_(torch.div(env.op, M, rounding_mode="floor")); bt["a_mach"][t].copy_(env.mach)
+            bt["log_a"][t].copy_(rollout.log_a); bt["m_log_a"][t].copy_(rollout.m_log_a)
+            bt["job_v"][t].copy_(rollout.job_v); bt["mch_v"][t].copy_(rollout.mch_v)
+            if s > 0:                                                                                # Run.py:448-451
+                bt["job_v_n"][t - 1].copy_(rollout.job_v); bt["mch_v_n"][t - 1].copy_(rollout.mch_v)
+            s4 = env.scaled4                                                                         # env order mk, idle, pt, tt
+            bt["r4"][t, :, 0].copy_(s4[:, 0]); bt["r4"][t, :, 1].copy_(s4[:, 2])
+            bt["r4"][t, :, 2].copy_(s4[:, 3]); bt["r4"][t, :, 3].copy_(s4[:, 1])
+            bt["done"][t].copy_(env.done); bt["rw"][t].copy_(wt)
+            bt["task_fea_n"][t].copy_(env.task_fea); bt["adj_w_n"][t].copy_(env.adj_w); bt["adj_src_n"][t].copy_(env.adj_src)
+            bt["mach_fea2_n"][t].copy_(env.mach_fea)
+            t += 1
+        with torch.no_grad():                                                                        # Run.py:452-475
+            _, h_o, jv = job.evaluate(env.task_fea, env.adj_w, env.adj_src, env.candidate, rollout.h_mch, bt["job_mask"][t - 1])
+            _, _, mv = mch.forward(bt["mach_fea1"][t - 1], env.mach_fea, h_o, bt["mach_mask"][t - 1])
+        bt["job_v_n"][t - 1].copy_(jv); bt["mch_v_n"][t - 1].copy_(mv)
+    return bt
+
+
+def train_iteration(rollout, updater, weights_per_episode, mini_bs=None):
+    """One buffer of experience followed by one PPO update (the body of the reference's training loop, Run.py:530-560)."""
+    bt = collect(rollout, weights_per_episode)
+    return updater.update(bt, mini_bs or rollout.env.N)

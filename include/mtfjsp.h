@@ -138,10 +138,17 @@ int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_
 
 /* ---- encoder side --------------------------------------------------------------------------
  * replaces: actor_critic.py:139-140 (dense adj -> sparse COO), gcn_mlp.py:125 (FP64 SpMM A*h) and :133-149 (degree
- * SpMM): out[b,v,:] = (h[b,v,:] + adj_w[b,v,0]*h[b,v-1,:] + adj_w[b,v,1]*h[b,adj_src[b,v],:]) / in_degree, FP64
- * accumulate, FP32 in/out.  h, out: [B,N,C] f32 (C % 4 == 0); adj_w / adj_src as written by mtfjsp_obs. */
+ * SpMM): out[b,v,:] = (h[b,v,:] + adj_w[b,v,0]*h[b,v-1,:] + adj_w[b,v,1]*h[b,adj_src[b,v],:]) / in_degree, FP32
+ * fused multiply-adds.  h, out: [B,N,C] f32 (C % 4 == 0); adj_w / adj_src as written by mtfjsp_obs. */
 int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_src, float* out, int64_t B, int N,
                          int C, const float* in_scale, const float* in_shift, int in_relu, void* stream);
+/* Backward of mtfjsp_enc_aggregate for the PPO update (ppo_algorithm.py:739-775 re-runs the encoder with gradients;
+ * torch autograd does the transposed FP64 SpMM there).  mtfjsp_enc_ell_invert builds the machine-successor index
+ * adj_dst [B,N] i16 (-1 = none) from adj_src once per stored step; mtfjsp_enc_aggregate_bwd then computes
+ * out[b,u,:] = g[b,u,:]/deg[u] + w_job[u+1]*g[b,u+1,:]/deg[u+1] + w_mach[d]*g[b,d,:]/deg[d], d = adj_dst[b,u]. */
+int mtfjsp_enc_ell_invert(const int16_t* adj_src, int16_t* adj_dst, int64_t B, int N, void* stream);
+int mtfjsp_enc_aggregate_bwd(const float* g, const float* adj_w, const int16_t* adj_src, const int16_t* adj_dst, float* out,
+                             int64_t B, int N, int C, void* stream);
 /* replaces: gcn_mlp.py:192 graph mean pooling; h [B,N,C] f32 -> out [B,C] f32.
  * Both take an optional per-column affine (+ReLU) applied to h on the fly: the BatchNorm of the producing layer
  * (gcn_mlp.py:154-157) folded into its consumer.  in_scale / in_shift [C] f32 or both NULL. */

@@ -1,0 +1,170 @@
+"""Batched PPO update against the reference's own update.
+
+Golden: tests/golden/ppo_golden.npz, produced by tests/golden/gen_ppo_golden.py from the REAL
+PPOAlgorithm.global_update_JointActions_GAT_selfCritic on CPU (hidden 32, 2 episodes x 36 steps x 4 envs, K_epochs 2,
+minibatches of 36 steps in the recorded SubsetRandomSampler order).  The update here is one batched forward per
+minibatch instead of 36 sequential ones; it must land on the same parameters.
+
+Tolerance (floating point, FP32 like the reference): parameters after the 4 Adam steps rtol 2e-3 / atol 5e-4 = half of
+one Adam step (a step moves a weight by ~lr = 1e-3 whatever the gradient's size, so rounding in gradients near
+lr_eps = 1e-5 is amplified); at most max(2, 1 %) of a tensor's elements may exceed atol 2e-4; losses rtol 1e-3.
+
+The CPU variant swaps the three CUDA kernels the update calls (aggregate fwd/bwd, graph mean, GAE) for torch
+restatements defined in this file, so the host logic is covered without a GPU; the `gpu` variant runs the kernels."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+ppo = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.ppo")
+
+
+def dense_to_ell(adj, M):
+    """[.., N, N] dense adj[dst, src] (diagonal 1) -> adj_w [.., N, 2] f32, adj_src [.., N] i16 as the env emits them."""
+    adj = np.asarray(adj, dtype=np.float64)
+    N = adj.shape[-1]
+    flat = adj.reshape(-1, N, N)
+    w = np.zeros((flat.shape[0], N, 2), dtype=np.float32)
+    src = np.full((flat.shape[0], N), -1, dtype=np.int16)
+    for v in range(N):
+        row = flat[:, v, :].copy()
+        row[:, v] = 0
+        if v % M != 0:
+            w[:, v, 0] = row[:, v - 1]
+            row[:, v - 1] = 0
+        assert ((row != 0).sum(axis=1) <= 1).all()
+        has = (row != 0).any(axis=1)
+        col = row.argmax(axis=1)
+        w[has, v, 1] = row[has, col[has]]
+        src[has, v] = col[has]
+    return w.reshape(adj.shape[:-2] + (N, 2)), src.reshape(adj.shape[:-2] + (N,))
+
+
+def build_batch(dev):
+    g = np.load(os.path.join(GOLD, "replay_j6m6_ls_esa.npz"))
+    p = np.load(os.path.join(GOLD, "ppo_golden.npz"))
+    J, M = int(g["J"]), int(g["M"])
+    N, B, EP = J * M, g["t"].shape[0], g["actions"].shape[0]
+    T = EP * N
+    pre = lambda post, first: np.concatenate([np.concatenate((first[e][None], post[e, :-1]), axis=0) for e in range(EP)], axis=0)
+    post = lambda x: x.reshape((T,) + x.shape[2:])
+    tfea_post = g["tfea"].reshape(EP, N, B, N, 12)
+    tfea0 = g["tfea0"].reshape(EP, B, N, 12)
+    cand0 = np.tile(np.arange(J) * M, (EP, B, 1)).astype(np.int16)
+    mask0 = np.zeros((EP, B, J), dtype=bool)
+    adj_pre, adj_post = pre(g["adj"], g["adj0"]), post(g["adj"])
+    aw, asrc = dense_to_ell(adj_pre, M)
+    awn, asrcn = dense_to_ell(adj_post, M)
+    info = post(g["info"])
+    f = lambda x: torch.tensor(np.ascontiguousarray(x), dtype=torch.float32, device=dev)
+    bt = dict(
+        task_fea=f(pre(tfea_post, tfea0)), adj_w=f(aw), adj_src=torch.tensor(asrc, device=dev),
+        candidate=torch.tensor(pre(g["cand"], cand0).astype(np.int32), device=dev),
+        job_mask=torch.tensor(pre(g["mask"], mask0).astype(np.uint8), device=dev),
+        mach_fea1=f(post(g["mfea1"])), mach_fea2=f(pre(g["mfea2"], g["mfea20"])),
+        mach_mask=torch.tensor(p["mach_mask"].astype(np.uint8), device=dev),
+        a_job=torch.tensor((post(g["actions"])[..., 0] // M).astype(np.int32), device=dev),
+        a_mach=torch.tensor(post(g["actions"])[..., 1].astype(np.int32), device=dev),
+        log_a=f(p["log_a"]), m_log_a=f(p["m_log_a"]), job_v=f(p["job_v"]), mch_v=f(p["mch_v"]),
+        job_v_n=f(p["job_v_n"]), mch_v_n=f(p["mch_v_n"]),
+        r4=f(np.stack((info[..., 2], info[..., 4], info[..., 5], info[..., 3]), axis=-1)),   # mk, pt, tt, it
+        done=f(info[..., 1]), rw=f(np.repeat(g["weights"][:, None], N, axis=1).reshape(T, B, 3)),
+        task_fea_n=f(post(tfea_post)), adj_w_n=f(awn), adj_src_n=torch.tensor(asrcn, device=dev), mach_fea2_n=f(post(g["mfea2"])),
+    )
+    return bt, p, (J, M)
+
+
+# ---- torch restatements of the kernels (CPU variant only) -----------------------------------------------------------
+def _t_aggregate(h, adj_w, adj_src, in_scale=None, in_shift=None, relu=False, adj_dst=None):
+    B, N, C = h.shape
+    prev = torch.cat((torch.zeros_like(h[:, :1]), h[:, :-1]), dim=1)
+    has_m = (adj_src >= 0)
+    gsrc = torch.gather(h, 1, adj_src.clamp(min=0).long().unsqueeze(-1).expand(-1, -1, C))
+    deg = 1.0 + (adj_w[..., 0] != 0).float() + has_m.float()
+    return (h + adj_w[..., 0:1] * prev + (adj_w[..., 1:2] * has_m.unsqueeze(-1)) * gsrc) / deg.unsqueeze(-1)
+
+
+def _t_gae4(r, v, v_next, done, gamma=0.99, lam=0.98, normalize=True):
+    T = r.shape[0]
+    adv = torch.zeros_like(r)
+    gae = torch.zeros_like(r[0])
+    delta = r + gamma * v_next - v
+    for t in range(T - 1, -1, -1):
+        gae = delta[t] + gamma * lam * gae * (1.0 - done[t]).unsqueeze(-1)
+        adv[t] = gae
+    if normalize:
+        flat = adv.reshape(-1, 4)
+        adv = (adv - flat.mean(0)) / (flat.std(0) + 1e-5)
+    return adv
+
+
+def _run_update(dev, monkeypatch=None):
+    if monkeypatch is not None:
+        monkeypatch.setattr(enc, "aggregate", _t_aggregate)
+        monkeypatch.setattr(enc, "graph_mean", lambda h, *a, **k: h.mean(dim=1))
+        monkeypatch.setattr(enc, "ell_invert", lambda s: None)
+        monkeypatch.setattr(ppo, "gae4", _t_gae4)
+    bt, p, (J, M) = build_batch(dev)
+    H = int(p["H"])
+    job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 11), J, M, hidden=H, device=dev, trainable=True)
+    mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 12), M, hidden=H, device=dev, trainable=True)
+    crit = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 13), J, M, hidden=H, device=dev, trainable=True)
+    up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=int(p["K_epochs"])))
+    mean, std = up.update(bt, int(p["mini_bs"]), orders=p["orders"])
+    np.testing.assert_allclose(mean.cpu().numpy(), p["loss_mean"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(std.cpu().numpy(), p["loss_std"], rtol=2e-2, atol=1e-4)
+    worst = 0.0
+    for tag, net in (("job", job), ("mch", mch), ("crit", crit)):
+        sd = net.state_dict()
+        for k in sd:
+            if enc._Params.is_parameter(k):
+                ref = p["%s/%s" % (tag, k)]
+                got = sd[k].cpu().numpy()
+                worst = max(worst, float(np.abs(got - ref).max()))
+                np.testing.assert_allclose(got, ref, rtol=2e-3, atol=5e-4, err_msg="%s/%s" % (tag, k))
+                loose = np.abs(got - ref) > 2e-4 + 2e-3 * np.abs(ref)
+                assert loose.sum() <= max(2, 0.01 * loose.size), ("%s/%s" % (tag, k), int(loose.sum()), loose.size)
+    return worst
+
+
+def test_update_matches_reference_with_torch_kernels(monkeypatch):
+    _run_update(torch.device("cpu"), monkeypatch)
+
+
+def test_parameters_actually_move():
+    """Guards the comparison above against a vacuous pass: the golden parameters differ from the seeded ones."""
+    p = np.load(os.path.join(GOLD, "ppo_golden.npz"))
+    H = int(p["H"])
+    sd = enc.seeded_state_dict(enc.job_actor_keys(H), 11)
+    k = "encoder.feature_extract.mlps.0.linears.0.weight"
+    assert np.abs(p["job/" + k] - sd[k].numpy()).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_update_matches_reference_on_device():
+    _run_update(torch.device("cuda", 0))
+
+
+@pytest.mark.gpu
+def test_aggregate_backward_matches_autograd_of_dense_product():
+    dev = torch.device("cuda", 0)
+    bt, p, (J, M) = build_batch(dev)
+    N = J * M
+    aw, asrc = bt["adj_w_n"][40:60].reshape(-1, N, 2).contiguous(), bt["adj_src_n"][40:60].reshape(-1, N).contiguous()
+    for C in (12, 32, 128):
+        h = torch.randn(aw.shape[0], N, C, device=dev, requires_grad=True)
+        g = torch.randn_like(h)
+        out = enc.aggregate(h, aw, asrc)
+        out.backward(g)
+        h2 = h.detach().clone().requires_grad_(True)
+        ref = _t_aggregate(h2.double(), aw.double(), asrc)
+        ref.backward(g.double())
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().float().cpu().numpy(), rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(h.grad.cpu().numpy(), h2.grad.cpu().numpy(), rtol=1e-5, atol=1e-4)
+        pm = enc.graph_mean(h)
+        pm.backward(torch.ones_like(pm))
