@@ -126,6 +126,127 @@ __global__ void graph_mean_kernel(const float* __restrict__ h, float* __restrict
     }
 }
 
+// ---- grouped BatchNorm1d (+ReLU) with batch statistics, forward and backward ------------------------------------
+// x [G, R, C] f32: G row groups (one per buffered step of a PPO minibatch), each normalised with its own statistics
+// (the reference re-forwards one step at a time, so every step has its own BatchNorm batch: gcn_mlp.py:154, 248,
+// actor_critic.py:434 inside the loops of ppo_algorithm.py:739-775).  HBM-bound: forward = one statistics pass
+// (read x) + one apply pass (read x, write y); backward = one sums pass (read x, gy) + one apply pass (read x, gy,
+// write dx).  Nothing but x is kept for the backward: y's sign (ReLU mask) is recomputed from x.
+constexpr int BN_ROWS = 512;  // rows of one group per block
+
+// column sums of (a, b) over this block's rows -> FP64 atomics into acc[g][0][C], acc[g][1][C]
+// MODE 0: a = x, b = x*x (statistics);  MODE 1: a = g', b = g' * xhat (backward sums), g' = gy * [y > 0]
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float4* __restrict__ x, const float4* __restrict__ gy,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        double* __restrict__ acc, long long R, int C4, int relu) {
+    extern __shared__ double s_red[];  // [2][ty][C]
+    const int g = blockIdx.y;
+    const int cq = threadIdx.x % C4, ty = threadIdx.x / C4, ny = blockDim.x / C4;
+    const long long r0 = (long long)blockIdx.x * BN_ROWS;
+    const long long r1 = r0 + BN_ROWS < R ? r0 + BN_ROWS : R;
+    const int C = C4 * 4;
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    float4 mu = sa, rs = sa, ww = sa, bb = sa;
+    if (MODE == 1) {
+        mu = reinterpret_cast<const float4*>(mean + (size_t)g * C)[cq];
+        rs = reinterpret_cast<const float4*>(rstd + (size_t)g * C)[cq];
+        ww = reinterpret_cast<const float4*>(w)[cq];
+        bb = reinterpret_cast<const float4*>(b)[cq];
+    }
+    if (ty < ny) {
+        for (long long r = r0 + ty; r < r1; r += ny) {
+            const size_t i = ((size_t)g * R + r) * C4 + cq;
+            const float4 v = __ldg(x + i);
+            if (MODE == 0) {
+                sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
+                sb.x = fmaf(v.x, v.x, sb.x); sb.y = fmaf(v.y, v.y, sb.y); sb.z = fmaf(v.z, v.z, sb.z); sb.w = fmaf(v.w, v.w, sb.w);
+            } else {
+                float4 d = __ldg(gy + i);
+                const float4 xh = make_float4((v.x - mu.x) * rs.x, (v.y - mu.y) * rs.y, (v.z - mu.z) * rs.z, (v.w - mu.w) * rs.w);
+                if (relu) {
+                    if (!(fmaf(xh.x, ww.x, bb.x) > 0.f)) d.x = 0.f;
+                    if (!(fmaf(xh.y, ww.y, bb.y) > 0.f)) d.y = 0.f;
+                    if (!(fmaf(xh.z, ww.z, bb.z) > 0.f)) d.z = 0.f;
+                    if (!(fmaf(xh.w, ww.w, bb.w) > 0.f)) d.w = 0.f;
+                }
+                sa.x += d.x; sa.y += d.y; sa.z += d.z; sa.w += d.w;
+                sb.x = fmaf(d.x, xh.x, sb.x); sb.y = fmaf(d.y, xh.y, sb.y); sb.z = fmaf(d.z, xh.z, sb.z); sb.w = fmaf(d.w, xh.w, sb.w);
+            }
+        }
+        double* pa = s_red + (size_t)ty * C + cq * 4;
+        double* pb = s_red + (size_t)(ny + ty) * C + cq * 4;
+        pa[0] = sa.x; pa[1] = sa.y; pa[2] = sa.z; pa[3] = sa.w;
+        pb[0] = sb.x; pb[1] = sb.y; pb[2] = sb.z; pb[3] = sb.w;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, col = c - which * C;
+        double t = 0.0;
+        for (int y = 0; y < ny; y++) t += s_red[(size_t)(which * ny + y) * C + col];
+        atomicAdd(acc + ((size_t)g * 2 + which) * C + col, t);
+    }
+}
+
+__global__ void bn_stats_finalize_kernel(const double* __restrict__ acc, double inv_rows, float eps, float* mean, float* rstd,
+                                         int G, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * C) return;
+    const int g = i / C, c = i - g * C;
+    const double m = acc[((size_t)g * 2) * C + c] * inv_rows;
+    double var = acc[((size_t)g * 2 + 1) * C + c] * inv_rows - m * m;  // biased, as torch normalises in training mode
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// MODE 0: y = relu?(xhat*w + b);  MODE 1: dx = (g' - (sg + xhat*sgx)/R) * rstd * w
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ gy,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const double* __restrict__ sums, float4* __restrict__ out, long long R,
+                                                       int C4, int relu, float inv_rows) {
+    const int g = blockIdx.y;
+    const int cq = threadIdx.x % C4, ty = threadIdx.x / C4, ny = blockDim.x / C4;
+    if (ty >= ny) return;
+    const int C = C4 * 4;
+    const long long r0 = (long long)blockIdx.x * BN_ROWS;
+    const long long r1 = r0 + BN_ROWS < R ? r0 + BN_ROWS : R;
+    const float4 mu = reinterpret_cast<const float4*>(mean + (size_t)g * C)[cq];
+    const float4 rs = reinterpret_cast<const float4*>(rstd + (size_t)g * C)[cq];
+    const float4 ww = reinterpret_cast<const float4*>(w)[cq];
+    const float4 bb = reinterpret_cast<const float4*>(b)[cq];
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sx = sg;
+    if (MODE == 1) {
+        const double* p0 = sums + ((size_t)g * 2) * C + cq * 4;
+        const double* p1 = sums + ((size_t)g * 2 + 1) * C + cq * 4;
+        sg = make_float4((float)(p0[0] * inv_rows), (float)(p0[1] * inv_rows), (float)(p0[2] * inv_rows), (float)(p0[3] * inv_rows));
+        sx = make_float4((float)(p1[0] * inv_rows), (float)(p1[1] * inv_rows), (float)(p1[2] * inv_rows), (float)(p1[3] * inv_rows));
+    }
+    for (long long r = r0 + ty; r < r1; r += ny) {
+        const size_t i = ((size_t)g * R + r) * C4 + cq;
+        const float4 v = __ldg(x + i);
+        const float4 xh = make_float4((v.x - mu.x) * rs.x, (v.y - mu.y) * rs.y, (v.z - mu.z) * rs.z, (v.w - mu.w) * rs.w);
+        float4 y = make_float4(fmaf(xh.x, ww.x, bb.x), fmaf(xh.y, ww.y, bb.y), fmaf(xh.z, ww.z, bb.z), fmaf(xh.w, ww.w, bb.w));
+        if (MODE == 0) {
+            if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+            out[i] = y;
+        } else {
+            float4 d = __ldg(gy + i);
+            if (relu) {
+                if (!(y.x > 0.f)) d.x = 0.f;
+                if (!(y.y > 0.f)) d.y = 0.f;
+                if (!(y.z > 0.f)) d.z = 0.f;
+                if (!(y.w > 0.f)) d.w = 0.f;
+            }
+            out[i] = make_float4((d.x - (sg.x + xh.x * sx.x)) * (rs.x * ww.x), (d.y - (sg.y + xh.y * sx.y)) * (rs.y * ww.y),
+                                 (d.z - (sg.z + xh.z * sx.z)) * (rs.z * ww.z), (d.w - (sg.w + xh.w * sx.w)) * (rs.w * ww.w));
+        }
+    }
+}
+
 // 4-stream generalised advantage estimation (algorithm/ppo_algorithm.py:438-536): per env and reward stream a
 // backward scan over the buffered steps, delta = r + gamma*v_next - v, gae = delta + gamma*lambda*gae*(1-done).
 // Layout [T,B,4] (stream innermost), one thread per (env, stream): every step's load/store is coalesced.
@@ -240,6 +361,41 @@ int mtfjsp_enc_aggregate_bwd(const float* g, const float* adj_w, const int16_t* 
             reinterpret_cast<const float4*>(g) + r0 * C4, reinterpret_cast<const float2*>(adj_w) + r0, adj_src + r0,
             adj_dst + r0, reinterpret_cast<float4*>(out) + r0 * C4, total, N, C4, c4_shift);
     }
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+static bool bn_args_ok(int64_t G, int64_t R, int C) { return G >= 1 && G <= 65535 && R >= 1 && C >= 4 && C <= 1024 && (C % 4) == 0; }
+
+int mtfjsp_enc_bn_fwd(const float* x, const float* w, const float* b, float eps, int64_t G, int64_t R, int C, int relu, float* y,
+                      float* mean, float* rstd, double* workspace, void* stream) {
+    if (!x || !w || !b || !y || !mean || !rstd || !workspace || !bn_args_ok(G, R, C)) return MTFJSP_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int C4 = C / 4, ny = 256 / C4 > 0 ? 256 / C4 : 1;
+    const int threads = C4 * ny > 256 ? C4 : 256;
+    const dim3 grid((unsigned)((R + BN_ROWS - 1) / BN_ROWS), (unsigned)G);
+    const size_t smem = (size_t)2 * (threads / C4) * C * sizeof(double);
+    if (cudaMemsetAsync(workspace, 0, (size_t)G * 2 * C * sizeof(double), s) != cudaSuccess) return MTFJSP_E_CUDA;
+    bn_reduce_kernel<0><<<grid, threads, smem, s>>>(reinterpret_cast<const float4*>(x), nullptr, w, b, nullptr, nullptr, workspace,
+                                                    R, C4, 0);
+    bn_stats_finalize_kernel<<<(unsigned)((G * C + 255) / 256), 256, 0, s>>>(workspace, 1.0 / (double)R, eps, mean, rstd, (int)G, C);
+    bn_apply_kernel<0><<<grid, threads, 0, s>>>(reinterpret_cast<const float4*>(x), nullptr, w, b, mean, rstd, nullptr,
+                                                reinterpret_cast<float4*>(y), R, C4, relu, 0.f);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_bn_bwd(const float* x, const float* gy, const float* w, const float* b, const float* mean, const float* rstd,
+                      int64_t G, int64_t R, int C, int relu, float* dx, double* sums, void* stream) {
+    if (!x || !gy || !w || !b || !mean || !rstd || !dx || !sums || !bn_args_ok(G, R, C)) return MTFJSP_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int C4 = C / 4, ny = 256 / C4 > 0 ? 256 / C4 : 1;
+    const int threads = C4 * ny > 256 ? C4 : 256;
+    const dim3 grid((unsigned)((R + BN_ROWS - 1) / BN_ROWS), (unsigned)G);
+    const size_t smem = (size_t)2 * (threads / C4) * C * sizeof(double);
+    if (cudaMemsetAsync(sums, 0, (size_t)G * 2 * C * sizeof(double), s) != cudaSuccess) return MTFJSP_E_CUDA;
+    bn_reduce_kernel<1><<<grid, threads, smem, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gy), w, b, mean,
+                                                    rstd, sums, R, C4, relu);
+    bn_apply_kernel<1><<<grid, threads, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gy), w, b, mean,
+                                                rstd, sums, reinterpret_cast<float4*>(dx), R, C4, relu, 1.0f / (float)R);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 

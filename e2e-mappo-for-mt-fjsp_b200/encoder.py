@@ -202,15 +202,64 @@ def seeded_state_dict(keys: dict, seed: int):
     return sd
 
 
-def _bn_train(x, w, b, eps=1e-5, groups=1):
-    """BatchNorm1d with batch statistics (the reference never leaves train mode).  groups > 1: the rows are `groups`
-    consecutive blocks, each normalised with its own statistics -- one block per buffered step, so a batched PPO
-    re-forward sees exactly the statistics of the reference's one-step-at-a-time loop (ppo_algorithm.py:739-775)."""
+def bn_forward(x, w, b, eps, groups, relu):
+    """Grouped BatchNorm1d with batch statistics (+ReLU) on the device: -> y, mean [G,C], rstd [G,C]."""
+    Cc = x.shape[-1]
+    x = x.contiguous()
+    R = x.numel() // (groups * Cc)
+    y = torch.empty_like(x)
+    mean = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty((groups, 2, Cc), dtype=torch.float64, device=x.device)
+    check(_lib.lib().mtfjsp_enc_bn_fwd(_ptr(x), _ptr(w.contiguous()), _ptr(b.contiguous()), float(eps), groups, R, Cc, int(relu),
+                                       _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ws), _stream()), "mtfjsp_enc_bn_fwd")
+    return y, mean, rstd
+
+
+def bn_backward(x, gy, w, b, mean, rstd, groups, relu):
+    """-> dx, dgamma [C], dbeta [C]."""
+    Cc = x.shape[-1]
+    R = x.numel() // (groups * Cc)
+    gy = gy.contiguous()
+    dx = torch.empty_like(x)
+    sums = torch.empty((groups, 2, Cc), dtype=torch.float64, device=x.device)
+    check(_lib.lib().mtfjsp_enc_bn_bwd(_ptr(x), _ptr(gy), _ptr(w.contiguous()), _ptr(b.contiguous()), _ptr(mean), _ptr(rstd),
+                                       groups, R, Cc, int(relu), _ptr(dx), _ptr(sums), _stream()), "mtfjsp_enc_bn_bwd")
+    tot = sums.sum(dim=0)
+    return dx, tot[1].float(), tot[0].float()
+
+
+class _GroupBNFn(torch.autograd.Function):
+    """BatchNorm1d with batch statistics per row group (+ optional ReLU) that keeps only its input for the backward:
+    the PPO re-forward holds ~20 of these per network, so the usual elementwise chain (centred, scaled, shifted,
+    rectified copies) would be most of the activation memory.  Kernels: csrc/mtfjsp_encoder.cu bn_*_kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, groups, relu):
+        x = x.contiguous()
+        y, mean, rstd = bn_forward(x, w, b, eps, groups, relu)
+        ctx.save_for_backward(x, w, b, mean, rstd)
+        ctx.groups, ctx.relu = groups, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, b, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = bn_backward(x, gy, w, b, mean, rstd, ctx.groups, ctx.relu)
+        return dx, dgamma, dbeta, None, None, None
+
+
+def _bn_train(x, w, b, eps=1e-5, groups=1, relu=False):
+    """BatchNorm1d with batch statistics (the reference never leaves train mode), optionally followed by ReLU.
+    groups > 1: the rows are `groups` consecutive blocks, each normalised with its own statistics -- one block per
+    buffered step, so a batched PPO re-forward sees exactly the statistics of the reference's one-step-at-a-time loop
+    (ppo_algorithm.py:739-775)."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return _GroupBNFn.apply(x, w, b, eps, groups, relu)
     if groups == 1:
-        return F.batch_norm(x, None, None, w, b, True, 0.0, eps)
-    xs = x.reshape(groups, -1, x.shape[-1])
-    var, mean = torch.var_mean(xs, dim=1, unbiased=False, keepdim=True)
-    return ((xs - mean) * torch.rsqrt(var + eps) * w + b).reshape(x.shape)
+        y = F.batch_norm(x, None, None, w, b, True, 0.0, eps)
+        return F.relu(y) if relu else y
+    return bn_forward(x, w, b, eps, groups, relu)[0]
 
 
 class _Params:
@@ -234,6 +283,12 @@ class _Params:
 
     def __getitem__(self, k):
         return self.p[k]
+
+    def detached(self):
+        """Same storage, no autograd: the view an inference twin reads while the optimiser updates in place."""
+        v = object.__new__(_Params)
+        v.p = {k: t.detach() for k, t in self.p.items()}
+        return v
 
     def parameters(self):
         """Learnable tensors in state_dict order (what `module.parameters()` yields in the reference)."""
@@ -259,7 +314,7 @@ class _GraphEncoder:
         h = x
         for i in (0, 1):
             h = F.linear(h, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i])
-            h = F.relu(_bn_train(h, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i], groups=groups))
+            h = _bn_train(h, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i], groups=groups, relu=True)
         return F.linear(h, w[p + "linears.2.weight"], w[p + "linears.2.bias"])
 
     def encode(self, task_fea, adj_w, adj_src, groups=1, adj_dst=None):
@@ -276,8 +331,8 @@ class _GraphEncoder:
         for l in (0, 1):
             pooled = aggregate(h, adj_w, adj_src, adj_dst=adj_dst)                  # gcn_mlp.py:125-149
             z = self._mlp(l, pooled.reshape(B * self.N, -1), groups)
-            z = F.relu(_bn_train(z, w["encoder.feature_extract.batch_norms.%d.weight" % l],
-                                 w["encoder.feature_extract.batch_norms.%d.bias" % l], groups=groups))   # gcn_mlp.py:154-157
+            z = _bn_train(z, w["encoder.feature_extract.batch_norms.%d.weight" % l],
+                          w["encoder.feature_extract.batch_norms.%d.bias" % l], groups=groups, relu=True)   # gcn_mlp.py:154-157
             h = z.reshape(B, self.N, self.H)
         self._pending = None
         return graph_mean(h), h                                                    # gcn_mlp.py:192
@@ -320,6 +375,26 @@ class _GraphEncoder:
         return self.w.state_dict()
 
 
+class _Twin:
+    def inference_twin(self, precision="tf32"):
+        """A second handle on the SAME weights for rollouts (no autograd, optionally the tcgen05 path) while this
+        object trains them; call `refresh()` on the twin after optimiser steps (re-derives cached layouts in place,
+        so captured CUDA graphs stay valid)."""
+        _check_precision(precision, self.H)
+        t = object.__new__(type(self))
+        t.__dict__.update(self.__dict__)
+        t.w = self.w.detached()
+        t.precision = precision
+        t._pending = None
+        t._Wt = None
+        return t
+
+    def refresh(self):
+        Wt = getattr(self, "_Wt", None)
+        if Wt is not None:
+            Wt.copy_(self.w["gat_layer.W"].t())
+
+
 def _check_precision(precision, hidden):
     if precision not in ("fp32", "tf32"):
         raise ValueError("precision must be 'fp32' or 'tf32'")
@@ -327,7 +402,7 @@ def _check_precision(precision, hidden):
         raise ValueError("the tcgen05 layer kernel is built for hidden = 128")
 
 
-class JobActor(_GraphEncoder):
+class JobActor(_GraphEncoder, _Twin):
     """Forward of Operation_Actor_JointAction_selfCritic (model/actor_critic.py:104-296) on native observations."""
 
     def __init__(self, state_dict, n_job, n_machine, hidden=128, in_dim=12, device=None, precision="fp32", trainable=False):
@@ -409,7 +484,7 @@ class _MachineTrunk:
         return self.w.state_dict()
 
 
-class MachineActor(_MachineTrunk):
+class MachineActor(_MachineTrunk, _Twin):
     """Forward of Machine_Actor_JointAction_selfGAT_selfCritic (model/actor_critic.py:359-498)."""
 
     def __init__(self, state_dict, n_machine, hidden=128, device=None, precision="fp32", trainable=False):

@@ -74,8 +74,10 @@ def allreduce_mean_grads(params):
 
 
 class MAPPOUpdate:
-    def __init__(self, job_actor, machine_actor, global_critic, cfg: PPOConfig | None = None):
+    def __init__(self, job_actor, machine_actor, global_critic, cfg: PPOConfig | None = None, max_rows=1 << 21):
+        """max_rows: node rows (steps x envs x N) per forward/backward chunk -- bounds activation memory, see _minibatch."""
         self.job, self.mch, self.critic = job_actor, machine_actor, global_critic
+        self.max_rows = max_rows
         self.cfg = cfg or PPOConfig()
         c = self.cfg
         mk = lambda net: torch.optim.Adam(net.parameters(), lr=c.lr, eps=c.lr_eps)          # ppo_algorithm.py:57-79
@@ -85,10 +87,10 @@ class MAPPOUpdate:
         self.allreduce_bytes = 0
 
     # ---- values and advantages (ppo_algorithm.py:585-703), no gradients ---------------------------------------------
-    def _critic_all(self, task_fea, adj_w, adj_src, mf1, mf2, max_rows=1 << 22):
+    def _critic_all(self, task_fea, adj_w, adj_src, mf1, mf2):
         """Global critic over all T buffered steps, T BatchNorm groups, chunked by whole steps."""
         T, B, N = task_fea.shape[:3]
-        per = max(1, max_rows // (B * N))
+        per = max(1, (2 * self.max_rows) // (B * N))
         out = []
         for t0 in range(0, T, per):
             t1 = min(T, t0 + per)
@@ -116,71 +118,103 @@ class MAPPOUpdate:
 
     # ---- one minibatch (ppo_algorithm.py:716-1073) -------------------------------------------------------------------
     def _minibatch(self, bt, adv, idx):
+        """One actor step and one critic step on the buffered steps `idx` (in this order).
+
+        Memory: the minibatch is walked in chunks of whole steps (`max_rows` node rows each) with gradient
+        accumulation.  Every loss term is a sum over (step, env) divided by S*B, and BatchNorm groups are single
+        steps, so the accumulated gradient is the gradient of the unchunked minibatch.  The machine embedding that
+        crosses from item i-1 to item i is re-evaluated for the one step a chunk overlaps its predecessor."""
         c = self.cfg
         S = idx.numel()
         T, B, N = bt["task_fea"].shape[:3]
         J, M, H = self.job.J, self.job.M, self.job.H
-        take = lambda name: bt[name].index_select(0, idx)
-        tf = take("task_fea").reshape(S * B, N, -1)
-        aw, asrc = take("adj_w").reshape(S * B, N, 2), take("adj_src").reshape(S * B, N)
-        mf1, mf2 = take("mach_fea1").reshape(S * B, M, 6), take("mach_fea2").reshape(S * B, M, 8)
-        adst = _enc.ell_invert(asrc)
-
-        # machine trunks first: item i's job head consumes item i-1's machine embedding (:739-768)
-        nodes_m, pooled_m = self.mch.trunk(mf1, mf2, groups=S)
-        inp = self.job.w["_input"][None, None, :].expand(1, B, H)
-        gm = torch.cat((inp, pooled_m.reshape(S, B, H)[:-1]), dim=0).reshape(S * B, H)
-        prob_j, pooled_o, job_v = self.job.evaluate(tf, aw, asrc, take("candidate").reshape(S * B, J), gm,
-                                                    take("job_mask").reshape(S * B, J), groups=S, adj_dst=adst)
-        prob_m, mch_v = self.mch.heads(nodes_m, pooled_m, pooled_o, take("mach_mask").reshape(S * B, M))
-        prob_j, prob_m = prob_j.reshape(S, B, J), prob_m.reshape(S, B, M)
-        job_v, mch_v = job_v.reshape(S, B, 2), mch_v.reshape(S, B, 2)
-
-        dist_j, dist_m = Categorical(probs=prob_j), Categorical(probs=prob_m)                        # :779-783
-        ratio_j = torch.exp(dist_j.log_prob(take("a_job").long()) - take("log_a"))                    # :795
-        ratio_m = torch.exp(dist_m.log_prob(take("a_mach").long()) - take("m_log_a"))                 # :796
-        ag, al = adv["adv_glob"].index_select(0, idx), adv["adv_loc"].index_select(0, idx)
-        rw = take("rw")
-        w_mk, w_ec, w_tt = rw[..., 0], rw[..., 1], rw[..., 2]
+        cs = max(1, min(S, self.max_rows // (B * N)))
+        take = lambda name, i=idx: bt[name].index_select(0, i)
+        mse_sum = lambda a, b: ((a - b) ** 2).sum()
+        inv = 1.0 / (S * B)
 
         def clipped(ratio, a):                                                                      # :800-814
             return torch.min(ratio * a, torch.clamp(ratio, 1 - c.epsilon, 1 + c.epsilon) * a)
 
-        def weighted_global(ratio):                                                                 # :820-822, :861-863
-            return (w_mk * clipped(ratio, ag[..., 0]) + w_ec * (clipped(ratio, ag[..., 1]) + clipped(ratio, ag[..., 3]))
-                    + w_tt * clipped(ratio, ag[..., 2]))
-
-        glob_j, glob_m = weighted_global(ratio_j), weighted_global(ratio_m)
-        loc_j = w_mk * clipped(ratio_j, al[..., 0]) + w_ec * clipped(ratio_j, al[..., 3])              # :826-835
-        loc_m = w_ec * clipped(ratio_m, al[..., 1]) + w_tt * clipped(ratio_m, al[..., 2])              # :867-876
-        tl = adv["tgt_loc"].index_select(0, idx)
-        mse = F.mse_loss
-        crit_j = mse(w_mk * job_v[..., 0], w_mk * tl[..., 0]) + mse(w_ec * job_v[..., 1], w_ec * tl[..., 3])    # :896-907
-        crit_m = mse(w_ec * mch_v[..., 0], w_ec * tl[..., 1]) + mse(w_tt * mch_v[..., 1], w_tt * tl[..., 2])
-        loss_j = -2 * glob_j + (-1) * loc_j + 0.5 * crit_j - c.entropy_beta * dist_j.entropy()         # :913
-        loss_m = -2 * glob_m + (-1) * loc_m + 0.5 * crit_m - c.entropy_beta * dist_m.entropy()         # :914
+        inp = self.job.w["_input"][None, None, :].expand(1, B, H)
         # The reference calls clip_grad_norm_ right after zero_grad and BEFORE backward (:918-930): no gradient
         # exists at that point, so the actors are not clipped.  Reproduced by not clipping them.
         self.opt_job.zero_grad(set_to_none=True)
         self.opt_mch.zero_grad(set_to_none=True)
-        loss = loss_j.mean() + loss_m.mean()                                                         # :932
-        loss.backward()
+        dev = bt["task_fea"].device
+        tot_j = torch.zeros((), device=dev)
+        tot_m = torch.zeros((), device=dev)
+        chunks = []
+        for s0 in range(0, S, cs):
+            s1 = min(S, s0 + cs)
+            g, ci = s1 - s0, idx[s0:s1]
+            # machine trunks first: item i's job head consumes item i-1's machine embedding (:739-768)
+            p0 = max(s0 - 1, 0)
+            ti = idx[p0:s1]
+            nodes_m, pooled_m = self.mch.trunk(take("mach_fea1", ti).reshape(-1, M, 6), take("mach_fea2", ti).reshape(-1, M, 8),
+                                               groups=s1 - p0)
+            pm = pooled_m.reshape(s1 - p0, B, H)
+            gm = (torch.cat((inp, pm[:-1]), dim=0) if s0 == 0 else pm[:-1]).reshape(g * B, H)
+            if s0 > 0:
+                nodes_m, pooled_m = nodes_m[B:], pooled_m[B:]
+            tf = take("task_fea", ci).reshape(g * B, N, -1)
+            aw, asrc = take("adj_w", ci).reshape(g * B, N, 2), take("adj_src", ci).reshape(g * B, N)
+            adst = _enc.ell_invert(asrc)
+            chunks.append((ci, tf, aw, asrc, adst))
+            prob_j, pooled_o, job_v = self.job.evaluate(tf, aw, asrc, take("candidate", ci).reshape(g * B, J), gm,
+                                                        take("job_mask", ci).reshape(g * B, J), groups=g, adj_dst=adst)
+            prob_m, mch_v = self.mch.heads(nodes_m, pooled_m, pooled_o, take("mach_mask", ci).reshape(g * B, M))
+            prob_j, prob_m = prob_j.reshape(g, B, J), prob_m.reshape(g, B, M)
+            job_v, mch_v = job_v.reshape(g, B, 2), mch_v.reshape(g, B, 2)
+            dist_j, dist_m = Categorical(probs=prob_j), Categorical(probs=prob_m)                    # :779-783
+            ratio_j = torch.exp(dist_j.log_prob(take("a_job", ci).long()) - take("log_a", ci))        # :795
+            ratio_m = torch.exp(dist_m.log_prob(take("a_mach", ci).long()) - take("m_log_a", ci))     # :796
+            ag, al = adv["adv_glob"].index_select(0, ci), adv["adv_loc"].index_select(0, ci)
+            rw = take("rw", ci)
+            w_mk, w_ec, w_tt = rw[..., 0], rw[..., 1], rw[..., 2]
+
+            def weighted_global(ratio):                                                             # :820-822, :861-863
+                return (w_mk * clipped(ratio, ag[..., 0]) + w_ec * (clipped(ratio, ag[..., 1]) + clipped(ratio, ag[..., 3]))
+                        + w_tt * clipped(ratio, ag[..., 2]))
+
+            glob_j, glob_m = weighted_global(ratio_j), weighted_global(ratio_m)
+            loc_j = w_mk * clipped(ratio_j, al[..., 0]) + w_ec * clipped(ratio_j, al[..., 3])          # :826-835
+            loc_m = w_ec * clipped(ratio_m, al[..., 1]) + w_tt * clipped(ratio_m, al[..., 2])          # :867-876
+            tl = adv["tgt_loc"].index_select(0, ci)
+            # MSELoss over the whole [S,B] minibatch (:896-907) = sum of squared errors / (S*B)
+            crit_j = mse_sum(w_mk * job_v[..., 0], w_mk * tl[..., 0]) + mse_sum(w_ec * job_v[..., 1], w_ec * tl[..., 3])
+            crit_m = mse_sum(w_ec * mch_v[..., 0], w_ec * tl[..., 1]) + mse_sum(w_tt * mch_v[..., 1], w_tt * tl[..., 2])
+            # job_actor_loss.mean() + machine_actor_loss.mean() (:913-932), this chunk's share
+            lj = ((-2 * glob_j - loc_j - c.entropy_beta * dist_j.entropy()).sum() + 0.5 * crit_j) * inv
+            lm = ((-2 * glob_m - loc_m - c.entropy_beta * dist_m.entropy()).sum() + 0.5 * crit_m) * inv
+            (lj + lm).backward()
+            tot_j += lj.detach()
+            tot_m += lm.detach()
+            del nodes_m, pooled_m, pm, gm, prob_j, prob_m, pooled_o, job_v, mch_v, dist_j, dist_m, ratio_j, ratio_m, glob_j, glob_m, loc_j, loc_m, crit_j, crit_m, lj, lm
         self.allreduce_bytes += allreduce_mean_grads(self.job.parameters() + self.mch.parameters())
         self.opt_job.step()
         self.opt_mch.step()
 
         # global critic on the same minibatch (:943-1000): backward, THEN clip, then step
-        v_s = self.critic.forward(tf, aw, asrc, mf1, mf2, groups=S, adj_dst=adst).reshape(S, B, 4)
-        tg = adv["tgt_glob"].index_select(0, idx)
-        crit = (mse(w_mk * tg[..., 0], w_mk * v_s[..., 0]) + mse(w_ec * tg[..., 1], w_ec * v_s[..., 1])
-                + mse(w_ec * tg[..., 3], w_ec * v_s[..., 3]) + mse(w_tt * tg[..., 2], w_tt * v_s[..., 2]))     # :965-976
         self.opt_critic.zero_grad(set_to_none=True)
-        crit.backward()
+        tot_c = torch.zeros((), device=tot_j.device)
+        for ci, tf, aw, asrc, adst in chunks:
+            g = ci.numel()
+            v_s = self.critic.forward(tf, aw, asrc, take("mach_fea1", ci).reshape(g * B, M, 6),
+                                      take("mach_fea2", ci).reshape(g * B, M, 8), groups=g, adj_dst=adst).reshape(g, B, 4)
+            tg = adv["tgt_glob"].index_select(0, ci)
+            rw = take("rw", ci)
+            w_mk, w_ec, w_tt = rw[..., 0], rw[..., 1], rw[..., 2]
+            crit = (mse_sum(w_mk * tg[..., 0], w_mk * v_s[..., 0]) + mse_sum(w_ec * tg[..., 1], w_ec * v_s[..., 1])
+                    + mse_sum(w_ec * tg[..., 3], w_ec * v_s[..., 3]) + mse_sum(w_tt * tg[..., 2], w_tt * v_s[..., 2])) * inv   # :965-976
+            crit.backward()
+            tot_c += crit.detach()
+            del v_s, crit
         self.allreduce_bytes += allreduce_mean_grads(self.critic.parameters())
         if c.use_grad_clip:
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), c.clip_grad)                   # :993-996
         self.opt_critic.step()
-        return loss_j.mean().detach(), loss_m.mean().detach(), crit.detach()
+        return tot_j, tot_m, tot_c
 
     def update(self, bt, mini_bs, orders=None, generator=None):
         """bt: dict of [T, B, ...] device tensors (see `collect`).  orders: optional list (one per epoch) of index

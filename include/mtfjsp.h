@@ -149,6 +149,16 @@ int mtfjsp_enc_aggregate(const float* h, const float* adj_w, const int16_t* adj_
 int mtfjsp_enc_ell_invert(const int16_t* adj_src, int16_t* adj_dst, int64_t B, int N, void* stream);
 int mtfjsp_enc_aggregate_bwd(const float* g, const float* adj_w, const int16_t* adj_src, const int16_t* adj_dst, float* out,
                              int64_t B, int N, int C, void* stream);
+/* Grouped BatchNorm1d with batch statistics (+ optional ReLU), forward and backward, for the batched PPO re-forward:
+ * x [G,R,C] f32, every one of the G row groups (= buffered steps) normalised with its own biased batch variance, as
+ * the reference's per-step BatchNorm1d calls do in training mode (gcn_mlp.py:154,248; actor_critic.py:434 inside
+ * ppo_algorithm.py:739-775).  C % 4 == 0.  fwd: y [G,R,C], mean / rstd [G,C] kept for the backward, workspace
+ * [G,2,C] f64.  bwd: dx [G,R,C]; sums [G,2,C] f64 = per group (sum of g', sum of g'*xhat), whose sums over G are the
+ * gradients of beta and gamma; g' = gy masked by y > 0 when relu. */
+int mtfjsp_enc_bn_fwd(const float* x, const float* w, const float* b, float eps, int64_t G, int64_t R, int C, int relu, float* y,
+                      float* mean, float* rstd, double* workspace, void* stream);
+int mtfjsp_enc_bn_bwd(const float* x, const float* gy, const float* w, const float* b, const float* mean, const float* rstd,
+                      int64_t G, int64_t R, int C, int relu, float* dx, double* sums, void* stream);
 /* replaces: gcn_mlp.py:192 graph mean pooling; h [B,N,C] f32 -> out [B,C] f32.
  * Both take an optional per-column affine (+ReLU) applied to h on the fly: the BatchNorm of the producing layer
  * (gcn_mlp.py:154-157) folded into its consumer.  in_scale / in_shift [C] f32 or both NULL. */

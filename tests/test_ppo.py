@@ -9,8 +9,8 @@ Tolerance (floating point, FP32 like the reference): parameters after the 4 Adam
 one Adam step (a step moves a weight by ~lr = 1e-3 whatever the gradient's size, so rounding in gradients near
 lr_eps = 1e-5 is amplified); at most max(2, 1 %) of a tensor's elements may exceed atol 2e-4; losses rtol 1e-3.
 
-The CPU variant swaps the three CUDA kernels the update calls (aggregate fwd/bwd, graph mean, GAE) for torch
-restatements defined in this file, so the host logic is covered without a GPU; the `gpu` variant runs the kernels."""
+The CPU variant swaps the CUDA kernels the update calls (aggregate fwd/bwd, graph mean, grouped BatchNorm fwd/bwd,
+GAE) for torch restatements defined in this file, so the host logic is covered without a GPU; the `gpu` variant runs the kernels."""
 import importlib
 import os
 
@@ -103,8 +103,30 @@ def _t_gae4(r, v, v_next, done, gamma=0.99, lam=0.98, normalize=True):
     return adv
 
 
-def _run_update(dev, monkeypatch=None):
+def _t_bn_forward(x, w, b, eps, groups, relu):
+    xs = x.reshape(groups, -1, x.shape[-1])
+    var, mean = torch.var_mean(xs, dim=1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + eps)
+    y = (xs - mean) * rstd * w + b
+    return (torch.relu(y) if relu else y).reshape(x.shape), mean.squeeze(1), rstd.squeeze(1)
+
+
+def _t_bn_backward(x, gy, w, b, mean, rstd, groups, relu):
+    xs = x.reshape(groups, -1, x.shape[-1])
+    R = xs.shape[1]
+    xhat = (xs - mean.unsqueeze(1)) * rstd.unsqueeze(1)
+    g = gy.reshape(xs.shape)
+    if relu:
+        g = g * (xhat * w + b > 0)
+    sg, sgx = g.sum(dim=1, keepdim=True), (g * xhat).sum(dim=1, keepdim=True)
+    dx = (g - (sg + xhat * sgx) / R) * (rstd.unsqueeze(1) * w)
+    return dx.reshape(x.shape), sgx.sum(dim=(0, 1)), sg.sum(dim=(0, 1))
+
+
+def _run_update(dev, monkeypatch=None, max_rows=1 << 21):
     if monkeypatch is not None:
+        monkeypatch.setattr(enc, "bn_forward", _t_bn_forward)
+        monkeypatch.setattr(enc, "bn_backward", _t_bn_backward)
         monkeypatch.setattr(enc, "aggregate", _t_aggregate)
         monkeypatch.setattr(enc, "graph_mean", lambda h, *a, **k: h.mean(dim=1))
         monkeypatch.setattr(enc, "ell_invert", lambda s: None)
@@ -114,7 +136,7 @@ def _run_update(dev, monkeypatch=None):
     job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 11), J, M, hidden=H, device=dev, trainable=True)
     mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 12), M, hidden=H, device=dev, trainable=True)
     crit = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 13), J, M, hidden=H, device=dev, trainable=True)
-    up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=int(p["K_epochs"])))
+    up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=int(p["K_epochs"])), max_rows=max_rows)
     mean, std = up.update(bt, int(p["mini_bs"]), orders=p["orders"])
     np.testing.assert_allclose(mean.cpu().numpy(), p["loss_mean"], rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(std.cpu().numpy(), p["loss_std"], rtol=2e-2, atol=1e-4)
@@ -132,8 +154,10 @@ def _run_update(dev, monkeypatch=None):
     return worst
 
 
-def test_update_matches_reference_with_torch_kernels(monkeypatch):
-    _run_update(torch.device("cpu"), monkeypatch)
+@pytest.mark.parametrize("max_rows", [1 << 21, 7 * 4 * 36])
+def test_update_matches_reference_with_torch_kernels(monkeypatch, max_rows):
+    """max_rows = 7 steps' worth of node rows walks each 36-step minibatch in 6 gradient-accumulation chunks."""
+    _run_update(torch.device("cpu"), monkeypatch, max_rows)
 
 
 def test_parameters_actually_move():
@@ -146,8 +170,9 @@ def test_parameters_actually_move():
 
 
 @pytest.mark.gpu
-def test_update_matches_reference_on_device():
-    _run_update(torch.device("cuda", 0))
+@pytest.mark.parametrize("max_rows", [1 << 21, 7 * 4 * 36])
+def test_update_matches_reference_on_device(max_rows):
+    _run_update(torch.device("cuda", 0), None, max_rows)
 
 
 @pytest.mark.gpu
@@ -168,3 +193,85 @@ def test_aggregate_backward_matches_autograd_of_dense_product():
         np.testing.assert_allclose(h.grad.cpu().numpy(), h2.grad.cpu().numpy(), rtol=1e-5, atol=1e-4)
         pm = enc.graph_mean(h)
         pm.backward(torch.ones_like(pm))
+
+
+@pytest.mark.gpu
+def test_collect_feeds_update_consistently():
+    """collect() -> update() plumbing on a live rollout: with every minibatch equal to one episode in temporal order
+    the batched re-forward sees exactly what the rollout saw (item 0 gets `_input`, item i the machine embedding of
+    step i-1), so before the first optimiser step both importance ratios are 1; afterwards parameters have moved and
+    losses are finite.  Also the next-state bookkeeping of Run.py:448-475."""
+    dev = torch.device("cuda", 0)
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
+    rom = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
+    B, J, M, E, H = 64, 6, 6, 2, 32
+    N = J * M
+    d = ins.synthetic_instances(0, B, J, M, E, 5)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 1), J, M, hidden=H, trainable=True)
+    mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 2), M, hidden=H, trainable=True)
+    crit = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 3), J, M, hidden=H, trainable=True)
+    ro = rom.Rollout(env, job, mch, greedy=False, seed=9)
+    ws = [ins.random_weights(0, B, 100 + e) for e in range(2)]
+    bt = ppo.collect(ro, ws)
+    T = 2 * N
+    assert bt["task_fea"].shape == (T, B, N, 12)
+    done = bt["done"].reshape(2, N, B)
+    assert bool((done[:, :-1] == 0).all()) and bool((done[:, -1] == 1).all())
+    for e in range(2):                                         # in-episode next values are the next step's values
+        sl = slice(e * N, e * N + N - 1)
+        assert torch.equal(bt["job_v_n"][sl], bt["job_v"][e * N + 1:e * N + N])
+        assert torch.equal(bt["mch_v_n"][sl], bt["mch_v"][e * N + 1:e * N + N])
+        assert torch.equal(bt["task_fea_n"][sl], bt["task_fea"][e * N + 1:e * N + N])
+    assert bool((bt["a_job"] >= 0).all()) and bool((bt["a_job"] < J).all())
+
+    up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=1))
+    seen = []
+    orig = torch.exp
+
+    def spy(x):
+        seen.append(x.detach().clone())
+        return orig(x)
+
+    before = {k: v.clone() for k, v in job.state_dict().items()}
+    ppo.torch.exp = spy
+    try:
+        mean, _ = up.update(bt, N, orders=[list(range(T))])
+    finally:
+        ppo.torch.exp = orig
+    # first minibatch = episode 0 in order: log-ratio of both actors is ~0 everywhere (FP32 re-evaluation noise)
+    assert float(seen[0].abs().max()) < 2e-4 and float(seen[1].abs().max()) < 2e-4, (float(seen[0].abs().max()), float(seen[1].abs().max()))
+    assert bool(torch.isfinite(mean).all())
+    after = job.state_dict()
+    moved = max(float((after[k] - before[k]).abs().max()) for k in before if enc._Params.is_parameter(k))
+    assert moved > 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 700, 128), (5, 1031, 128), (3, 64, 32), (36, 24, 32)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_grouped_batchnorm_kernels_match_torch_autograd(shape, relu):
+    dev = torch.device("cuda", 0)
+    G, R, C = shape
+    torch.manual_seed(G * 1000 + R)
+    x = (torch.randn(G * R, C, device=dev) * 2 + 0.5).requires_grad_(True)
+    w = (torch.rand(C, device=dev) + 0.5).requires_grad_(True)
+    b = (torch.randn(C, device=dev) * 0.3).requires_grad_(True)
+    gy = torch.randn(G * R, C, device=dev)
+    y = enc._bn_train(x, w, b, groups=G, relu=relu)
+    y.backward(gy)
+    x2, w2, b2 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    xs = x2.reshape(G, R, C)
+    var, mean = torch.var_mean(xs, dim=1, unbiased=False, keepdim=True)
+    ref = ((xs - mean) * torch.rsqrt(var + 1e-5) * w2 + b2).reshape(G * R, C)
+    if relu:
+        ref = torch.relu(ref)
+    ref.backward(gy.double())
+    close = lambda a, r, name: np.testing.assert_allclose(a.detach().cpu().numpy(), r.detach().float().cpu().numpy(), rtol=2e-4,
+                                                          atol=2e-4, err_msg=name)
+    close(y, ref, "y"); close(x.grad, x2.grad, "dx"); close(w.grad, w2.grad, "dgamma"); close(b.grad, b2.grad, "dbeta")
+    with torch.no_grad():
+        close(enc._bn_train(x, w, b, groups=G, relu=relu), ref, "y (no grad)")
