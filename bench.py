@@ -285,6 +285,49 @@ def run_ours(args, wl):
                           "CUDA-graph replay, random-init weights", "hidden": 128}
     stats = sh.reduce_episode_stats(env.costs(), device=dev)  # the rollout side's only other exchange (6 doubles)
 
+    # ---- BASELINE.json configs[4]: env slice + encoder + PPO update end to end, gradient allreduce share ----
+    train = None
+    if not args.no_train and (J, M) == (6, 6):
+        enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+        rom = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
+        ppo = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.ppo")
+        Bt = min(B, 8192)  # 65,536 envs over 8 GPUs
+        env_t = envm.BatchedMTFJSPEnv(Bt, J, M, E, left_shift=True, obs_dtype=torch.float32)
+        env_t.load(d["t"][:Bt], d["p"][:Bt], d["transT"][:Bt], d["edge"][:Bt])
+        env_t.scaler_init()
+        tj = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(128), 11), J, M, trainable=True)
+        tm = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M, trainable=True)
+        tc = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(128), 13), J, M, trainable=True)
+        tro = rom.Rollout(env_t, tj.inference_twin("tf32"), tm.inference_twin("tf32"), greedy=False, seed=2 + rank)
+        up = ppo.MAPPOUpdate(tj, tm, tc, ppo.PPOConfig(k_epochs=1))
+        wt = [w[:Bt]]
+        tms, cms, ams = [], [], []
+        for it in range(3):  # first iteration is warm-up (library initialisation)
+            barrier()
+            t0e, t1e, t2e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            t0e.record()
+            btc = ppo.collect(tro, wt)
+            t1e.record()
+            losses, _ = up.update(btc, N)
+            tro.job.refresh(); tro.mch.refresh()
+            t2e.record()
+            barrier()
+            a_ms = up.allreduce_ms()
+            if it > 0:
+                cms.append(sh.max_over_ranks(t0e.elapsed_time(t1e), dev)); tms.append(sh.max_over_ranks(t0e.elapsed_time(t2e), dev))
+                ams.append(a_ms)
+            del btc
+        tot = sum(tms) / len(tms)
+        train = {"value": Bt * world * N / (tot * 1e-3), "unit": UNIT, "envs_per_gpu": Bt, "buffer_steps": N, "k_epochs": 1,
+                 "mini_bs": N, "collect_ms": sum(cms) / len(cms), "update_ms": tot - sum(cms) / len(cms),
+                 "allreduce_ms": sum(ams) / len(ams), "allreduce_share": (sum(ams) / len(ams)) / tot,
+                 "allreduce_bytes_per_update": up.allreduce_bytes // 3, "losses": [float(x) for x in losses],
+                 "what": "one buffer (1 episode) collected with the tcgen05 rollout twins + one batched PPO update "
+                         "(FP32 library GEMMs under autograd; aggregation, grouped BatchNorm and GAE kernels hand-written; "
+                         "NCCL gradient allreduce when n_gpus > 1)"}
+        del env_t, up, tro
+        torch.cuda.empty_cache()
+
     clocks = sampler.stop() if sampler else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_env_kernel_traffic.json")
@@ -341,6 +384,8 @@ def run_ours(args, wl):
         }
         if policy:
             line["policy_rollout"] = policy
+        if train:
+            line["train_iteration"] = train
         if dropin:
             line["e2e"]["dropin_parallel_env"] = dropin
         if cpu:
@@ -361,6 +406,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy", action="store_true", help="skip the actor-driven rollout measurement")
     ap.add_argument("--no-dropin", action="store_true", help="skip the Parallel_env (reference-typed) call measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the rollout + PPO update measurement")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

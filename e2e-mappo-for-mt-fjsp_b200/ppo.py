@@ -48,14 +48,16 @@ class PPOConfig:
     k_epochs: int = 5
     use_grad_clip: bool = True
     clip_grad: float = 0.5
+    matmul_tf32: bool = False   # library GEMMs of the update on TF32 tensor cores (the reference computes in FP32)
 
 
 def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def allreduce_mean_grads(params):
-    """One flat NCCL/gloo allreduce over every gradient that exists, then the mean."""
+def allreduce_mean_grads(params, timer=None):
+    """One flat NCCL/gloo allreduce over every gradient that exists, then the mean.
+    timer: optional list that receives a (start, end) CUDA event pair around the collective."""
     ws = _world()
     if ws == 1:
         return 0
@@ -63,7 +65,14 @@ def allreduce_mean_grads(params):
     if not grads:
         return 0
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if timer is not None and flat.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        e1.record()
+        timer.append((e0, e1))
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.div_(ws)
     o = 0
     for g in grads:
@@ -85,6 +94,7 @@ class MAPPOUpdate:
         sch = lambda o: torch.optim.lr_scheduler.StepLR(o, step_size=c.decay_step_size, gamma=c.decay_ratio)
         self.sched = [sch(self.opt_job), sch(self.opt_mch), sch(self.opt_critic)]
         self.allreduce_bytes = 0
+        self.allreduce_events = []   # (start, end) CUDA events of every gradient allreduce, for the time-share report
 
     # ---- values and advantages (ppo_algorithm.py:585-703), no gradients ---------------------------------------------
     def _critic_all(self, task_fea, adj_w, adj_src, mf1, mf2):
@@ -191,7 +201,7 @@ class MAPPOUpdate:
             tot_j += lj.detach()
             tot_m += lm.detach()
             del nodes_m, pooled_m, pm, gm, prob_j, prob_m, pooled_o, job_v, mch_v, dist_j, dist_m, ratio_j, ratio_m, glob_j, glob_m, loc_j, loc_m, crit_j, crit_m, lj, lm
-        self.allreduce_bytes += allreduce_mean_grads(self.job.parameters() + self.mch.parameters())
+        self.allreduce_bytes += allreduce_mean_grads(self.job.parameters() + self.mch.parameters(), self.allreduce_events)
         self.opt_job.step()
         self.opt_mch.step()
 
@@ -210,7 +220,7 @@ class MAPPOUpdate:
             crit.backward()
             tot_c += crit.detach()
             del v_s, crit
-        self.allreduce_bytes += allreduce_mean_grads(self.critic.parameters())
+        self.allreduce_bytes += allreduce_mean_grads(self.critic.parameters(), self.allreduce_events)
         if c.use_grad_clip:
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), c.clip_grad)                   # :993-996
         self.opt_critic.step()
@@ -223,6 +233,15 @@ class MAPPOUpdate:
         c = self.cfg
         T = bt["task_fea"].shape[0]
         dev = bt["task_fea"].device
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(c.matmul_tf32)
+        try:
+            return self._update(bt, mini_bs, orders, generator, T, dev)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _update(self, bt, mini_bs, orders, generator, T, dev):
+        c = self.cfg
         adv = self.advantages(bt)
         per_epoch = []
         for k in range(c.k_epochs):
@@ -243,6 +262,14 @@ class MAPPOUpdate:
         pe = torch.stack(per_epoch)
         std = pe.std(dim=0) if c.k_epochs > 1 else torch.full((3,), float("nan"), device=dev)
         return pe.mean(dim=0), std
+
+
+    def allreduce_ms(self):
+        """Device time spent in gradient allreduces since the last call (synchronises)."""
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.allreduce_events)
+        self.allreduce_events.clear()
+        return ms
 
 
 def collect(rollout, weights_per_episode):

@@ -13,6 +13,7 @@ EP = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 KE = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 J, M, E, H = 6, 6, 2, 128
 MB = int(sys.argv[4]) if len(sys.argv) > 4 else J * M
+TF32 = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
 pkg = importlib.import_module("e2e-mappo-for-mt-fjsp_b200")
 envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
 enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
@@ -26,7 +27,7 @@ job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 1), J, M, hidden
 mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 2), M, hidden=H, trainable=True)
 crit = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 3), J, M, hidden=H, trainable=True)
 ro = rom.Rollout(env, job.inference_twin("tf32"), mch.inference_twin("tf32"), greedy=False, seed=3)
-up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=KE))
+up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=KE, matmul_tf32=TF32))
 ws = [pkg.instances.random_weights(0, B, 100 + e) for e in range(EP)]
 for it in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
