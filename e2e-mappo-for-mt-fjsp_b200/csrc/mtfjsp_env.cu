@@ -1524,8 +1524,9 @@ static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     if (!(MODE & MODE_RESET) && !h->force_generic) {
         const int J = h->L.J, M = h->L.M;
         if (J == 6 && M == 6) return launch_spec<Spec<6, 6, 8, 4>, MODE, OutT>(h, P, s);
-        if (J == 10 && M == 10) return launch_spec<Spec<10, 10, 16, 4>, MODE, OutT>(h, P, s);
-        if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 4>, MODE, OutT>(h, P, s);
+        // warps per block = what keeps the most envs resident: shared memory per env is the limiter (2.4 / 5.9 / 29 KB)
+        if (J == 10 && M == 10) return launch_spec<Spec<10, 10, 16, 1>, MODE, OutT>(h, P, s);
+        if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 2>, MODE, OutT>(h, P, s);
     }
     return launch_env<MODE, OutT>(h, P, s);
 }

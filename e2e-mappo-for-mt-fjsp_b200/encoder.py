@@ -386,13 +386,36 @@ class _Twin:
         t.w = self.w.detached()
         t.precision = precision
         t._pending = None
-        t._Wt = None
+        t._dcache = {}
         return t
 
+    def _derived(self, name, fn):
+        """Weight layouts derived for the tensor-core path (transposes, column blocks), built once per object."""
+        c = self.__dict__.setdefault("_dcache", {})
+        if name not in c:
+            c[name] = (fn().contiguous(), fn)
+        return c[name][0]
+
     def refresh(self):
-        Wt = getattr(self, "_Wt", None)
-        if Wt is not None:
-            Wt.copy_(self.w["gat_layer.W"].t())
+        for t, fn in self.__dict__.get("_dcache", {}).values():
+            t.copy_(fn())
+
+    def _head_tf32(self, prefix, per_row, env_terms, rows_per_env, in_scale=None, in_shift=None):
+        """First two layers of a 3-layer tanh MLP whose input is cat(per_row [B*r,H], env_term_0 [B,H], env_term_1 [B,H]):
+        the per-env blocks of the first weight matrix are applied once per env and added as a bias, the per-row block
+        and the second layer run on the tcgen05 kernel -- no [B*r, 3H] concatenation, a third of the GEMM work."""
+        w, H = self.w, self.H
+        W0 = w[prefix + "linears.0.weight"]
+        Wa = self._derived(prefix + "W0a", lambda: W0[:, :H])
+        z = linear_tf32(per_row, Wa, None, in_scale, in_shift, relu=in_scale is not None)
+        bias = w[prefix + "linears.0.bias"]
+        for k, e in enumerate(env_terms):
+            Wk = self._derived(prefix + "W0%d" % (k + 1), lambda k=k: W0[:, (k + 1) * H:(k + 2) * H])
+            bias = bias + F.linear(e, Wk)
+        B = per_row.shape[0] // rows_per_env
+        z = torch.tanh(z.view(B, rows_per_env, H) + (bias.unsqueeze(1) if bias.dim() == 2 else bias)).view(-1, H)
+        z = torch.tanh(linear_tf32(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"]))
+        return F.linear(z, w[prefix + "linears.2.weight"], w[prefix + "linears.2.bias"]).view(B, rows_per_env)
 
 
 def _check_precision(precision, hidden):
@@ -420,10 +443,16 @@ class JobActor(_GraphEncoder, _Twin):
         h_g_m_pooled [B,H] or None (the learned `_input` vector stands in, actor_critic.py:232-240)."""
         w = self.w
         pooled, nodes = self.encode(task_fea, adj_w, adj_src, groups, adj_dst)
-        cf = self.candidate_features(nodes, candidate)
-        gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
-        x = torch.cat((cf, pooled.unsqueeze(-2).expand_as(cf), gm), dim=-1)              # actor_critic.py:244-247
-        s = _mlp3_tanh(w, "o_policy.", x).squeeze(-1)
+        if self.precision == "tf32":
+            cf = torch.gather(nodes, 1, candidate.long().unsqueeze(-1).expand(-1, self.J, self.H)).reshape(-1, self.H)
+            sc, sh = self._pending
+            gmv = w["_input"].unsqueeze(0) if h_g_m_pooled is None else h_g_m_pooled
+            s = self._head_tf32("o_policy.", cf, (pooled, gmv), self.J, sc, sh)
+        else:
+            cf = self.candidate_features(nodes, candidate)
+            gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
+            x = torch.cat((cf, pooled.unsqueeze(-2).expand_as(cf), gm), dim=-1)          # actor_critic.py:244-247
+            s = _mlp3_tanh(w, "o_policy.", x).squeeze(-1)
         s = s.masked_fill(mask_operation.bool(), float("-inf"))                          # actor_critic.py:266-268
         prob = F.softmax(s, dim=-1)
         job_v = _mlp3_tanh(w, "job_critic.", pooled)
@@ -451,9 +480,7 @@ class _MachineTrunk:
         W, a = self.w["gat_layer.W"], self.w["gat_layer.a"]
         H = self.H
         if self.precision == "tf32":  # both node sets in one [2*rows,128] x [128,128] tensor-core launch
-            Wt = getattr(self, "_Wt", None)  # [out, in] = the layout the tensor-core layer takes (inference weights)
-            if Wt is None:
-                Wt = self._Wt = W.t().contiguous()
+            Wt = self._derived("gat_Wt", lambda: self.w["gat_layer.W"].t())  # [out, in]: the layout the tensor-core layer takes
             t = linear_tf32(torch.cat((h1, h2), dim=0), Wt, None)
             t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
         else:
@@ -497,8 +524,11 @@ class MachineActor(_MachineTrunk, _Twin):
     def heads(self, nodes, pooled, h_pooled_o, machine_mask):
         w = self.w
         B = nodes.shape[0]
-        x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
-        s = _mlp3_tanh(w, "m_policy.", x).squeeze(-1) * 10
+        if self.precision == "tf32":
+            s = self._head_tf32("m_policy.", nodes.reshape(-1, self.H), (pooled, h_pooled_o), self.M) * 10
+        else:
+            x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
+            s = _mlp3_tanh(w, "m_policy.", x).squeeze(-1) * 10
         s = s.masked_fill(machine_mask.reshape(B, self.M).bool(), float("-inf"))
         return F.softmax(s, dim=-1), _mlp3_tanh(w, "machine_critic.", pooled)
 
