@@ -71,6 +71,8 @@ SIGNATURES = {
     "mtfjsp_policy_random": ([_VP, _U64, _U64, _I, _VP, _VP, _VP], _I),
     "mtfjsp_random_step": ([_VP, _U64, _U64] + [_VP] * 14 + [_I, _I, _VP], _I),
     "mtfjsp_step_host": ([_VP] + [_VP] * 9 + [_I, _I, _VP], _I),
+    "mtfjsp_step_host_packed": ([_VP] + [_VP] * 6 + [_I, _I, _VP], _I),
+    "mtfjsp_host_record_bytes": ([_VP], _I),
     "mtfjsp_enc_aggregate": ([_VP, _VP, _VP, _VP, C.c_int64, _I, _I, _VP, _VP, _I, _VP], _I),
     "mtfjsp_enc_ell_invert": ([_VP, _VP, C.c_int64, _I, _VP], _I),
     "mtfjsp_enc_bn_fwd": ([_VP, _VP, _VP, C.c_float, C.c_int64, C.c_int64, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),

@@ -74,6 +74,11 @@ struct Params {
     double* scaled4;
     uint8_t* done;
     uint8_t* invalid;
+    double* info6;  // optional [B,6] = (r, done, mk_s, idle_s, pt_s, tt_s), trainer/parallel_env.py:260
+    const int2* act2;      // optional packed actions [B] (op, machine); used instead of op / mach when set
+    unsigned char* rec;    // optional packed step records, rec_stride bytes per env: f64 info6[6] | i16 cand[J] | u8 mask[J]
+    int rec_stride;
+    int b0, b1;     // env range [b0, b1) of this launch (host-step pipeline launches sub-ranges)
     // obs io
     void* tfea;
     void* mfea;
@@ -89,6 +94,13 @@ struct Params {
 };
 
 enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4 };
+
+// step info (r, done, mk_s, idle_s, pt_s, tt_s) goes to the contiguous [B,6] array and / or the packed host record
+#define INFO6_PUT(b_, k_, v_)                                                                               \
+    do {                                                                                                    \
+        if (P.info6) P.info6[(size_t)(b_) * 6 + (k_)] = (v_);                                               \
+        if (P.rec) reinterpret_cast<double*>(P.rec + (size_t)(b_) * P.rec_stride)[(k_)] = (v_);             \
+    } while (0)
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -175,8 +187,8 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Layout& L = P.L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * L.warps_per_block + warp;
-    if (b >= L.B) return;
+    const int b = P.b0 + blockIdx.x * L.warps_per_block + warp;
+    if (b >= P.b1) return;
     const int N = L.N, M = L.M, J = L.J;
     unsigned char* base = smem_raw + (size_t)warp * L.smem_per_warp;
     double* s_sd = reinterpret_cast<double*>(base + L.sm_sd);
@@ -243,8 +255,8 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
     double idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;  // step results kept in registers for the reward epilogue
 
     if (MODE & MODE_STEP) {
-        a = P.op[b];
-        m = P.mach[b];
+        if (P.act2) { const int2 am = P.act2[b]; a = am.x; m = am.y; }
+        else { a = P.op[b]; m = P.mach[b]; }
         const int nsched0 = s_misc[2];
         double d = 0.0, pa = 0.0;
         valid = (a >= 0) && (a < N) && (m >= 0) && (m < M) && (nsched0 < N);
@@ -466,6 +478,7 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 s_sc[lane] = R; s_sc[4 + lane] = mean; s_sc[8 + lane] = S;
                 if (lane == 0) s_sc[12] = nn;
                 if (P.scaled4) P.scaled4[(size_t)b * 4 + lane] = scaled;
+                INFO6_PUT(b, 2 + lane, scaled);
             }
             __syncwarp();
             // selective write-back of the doubles that changed: scalars, macc[m], scaler
@@ -480,13 +493,16 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 }
                 if (P.done) P.done[b] = done ? 1 : 0;
                 if (P.invalid) P.invalid[b] = 0;
+                INFO6_PUT(b, 0, total / P.divisor); INFO6_PUT(b, 1, done ? 1.0 : 0.0);
             }
         } else {
             if (lane < 5 && P.reward5) P.reward5[(size_t)b * 5 + lane] = 0.0;
             if (lane < 4 && P.scaled4) P.scaled4[(size_t)b * 4 + lane] = 0.0;
+            if (lane < 6 && lane != 1) INFO6_PUT(b, lane, 0.0);
             if (lane == 0) {
                 if (P.done) P.done[b] = (s_misc[2] == N) ? 1 : 0;
                 if (P.invalid) P.invalid[b] = 1;
+                INFO6_PUT(b, 1, (s_misc[2] == N) ? 1.0 : 0.0);
             }
         }
         __syncwarp();
@@ -517,6 +533,11 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
             if (MODE & MODE_OBS) {
                 if (P.jmask) P.jmask[(size_t)b * J + j] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
                 if (P.cand) P.cand[(size_t)b * J + j] = c;
+                if (P.rec) {
+                    unsigned char* r = P.rec + (size_t)b * P.rec_stride;
+                    reinterpret_cast<int16_t*>(r + 48)[j] = (int16_t)c;
+                    r[48 + 2 * J + j] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+                }
             }
         }
     }
@@ -656,8 +677,8 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (G - 1), ge = lane / G;
-    const int B = P.L.B;
-    const int wb0 = (blockIdx.x * S::WARPS + warp) * EPW;
+    const int B = P.b1;
+    const int wb0 = P.b0 + (blockIdx.x * S::WARPS + warp) * EPW;
     if (wb0 >= B) return;
     const int b = wb0 + ge;
     const bool active = b < B;
@@ -678,8 +699,8 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
     // the action is the head of a dependent chain (op -> t[op][m], mind row of its job): issue it first
     int a = 0, m = 0;
     if (MODE & MODE_STEP) {
-        a = __ldg(P.op + bc);
-        m = __ldg(P.mach + bc);
+        if (P.act2) { const int2 am = __ldg(P.act2 + bc); a = am.x; m = am.y; }
+        else { a = __ldg(P.op + bc); m = __ldg(P.mach + bc); }
     }
     // ---- stage the records: 16-byte async copies, G lanes per record ----
     {
@@ -941,6 +962,7 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
             if (gl < 4) {
                 s_sc[gl] = R; s_sc[4 + gl] = mean; s_sc[8 + gl] = Sn;
                 if (P.scaled4) P.scaled4[(size_t)b * 4 + gl] = scaled;
+                INFO6_PUT(b, 2 + gl, scaled);
             }
             if (gl == 0) {
                 s_sc[12] = nn;
@@ -954,13 +976,16 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
                 }
                 if (P.done) P.done[b] = done ? 1 : 0;
                 if (P.invalid) P.invalid[b] = 0;
+                INFO6_PUT(b, 0, total); INFO6_PUT(b, 1, done ? 1.0 : 0.0);
             }
         } else if (active) {
             if (gl < 5 && P.reward5) P.reward5[(size_t)b * 5 + gl] = 0.0;
             if (gl < 4 && P.scaled4) P.scaled4[(size_t)b * 4 + gl] = 0.0;
+            if (gl < 6 && gl != 1) INFO6_PUT(b, gl, 0.0);
             if (gl == 0) {
                 if (P.done) P.done[b] = (s_misc[2] == N) ? 1 : 0;
                 if (P.invalid) P.invalid[b] = 1;
+                INFO6_PUT(b, 1, (s_misc[2] == N) ? 1.0 : 0.0);
             }
         }
         __syncwarp();
@@ -993,6 +1018,11 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
             if (MODE & MODE_OBS) {
                 if (P.jmask) P.jmask[(size_t)b * J + gl] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
                 if (P.cand) P.cand[(size_t)b * J + gl] = c;
+                if (P.rec) {
+                    unsigned char* r = P.rec + (size_t)b * P.rec_stride;
+                    reinterpret_cast<int16_t*>(r + 48)[gl] = (int16_t)c;
+                    r[48 + 2 * J + gl] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+                }
             }
         }
     }
@@ -1402,16 +1432,6 @@ __global__ void export_scaler_kernel(Layout L, const double* __restrict__ sd, do
     n[b] = (int64_t)s[12];
 }
 
-// info6 = (r, done, mk_s, idle_s, pt_s, tt_s), trainer/parallel_env.py:260
-__global__ void info6_kernel(int B, const double* __restrict__ r5, const double* __restrict__ s4,
-                             const uint8_t* __restrict__ done, double* info6) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    info6[(size_t)b * 6 + 0] = r5[(size_t)b * 5];
-    info6[(size_t)b * 6 + 1] = (double)done[b];
-    for (int k = 0; k < 4; k++) info6[(size_t)b * 6 + 2 + k] = s4[(size_t)b * 4 + k];
-}
-
 thread_local char g_err[512] = "";
 
 int fail(int code, const char* msg, cudaError_t e = cudaSuccess) {
@@ -1452,11 +1472,32 @@ struct mtfjsp_env {
     // scratch for the host-step / random-step paths
     int32_t *a_op, *a_mach;
     double *r5, *s4, *info6;
+    int2* act2;          // packed host-step actions
+    unsigned char* rec;  // packed host-step records
+    int rec_stride;
     uint8_t *dn, *inv;
     float* tmp_adj_w;
     int16_t* tmp_adj_src;
     bool loaded, reset_done, force_generic;
+    int host_chunks;  // tuning knobs read from the environment at create time (tests compare the settings)
     int64_t launches;
+    struct HostPipe* pipe;  // host-step pipeline (streams, events, instantiated graphs), created on first use
+};
+
+// Host-step pipeline: the batch is cut into chunks; chunk c's (H2D actions -> fused kernel -> D2H step info) runs
+// on its own stream, so that chunk c's copy-out overlaps chunk c+1's kernel.  The whole fan-out is captured once per
+// set of buffer addresses into a CUDA graph and replayed with a single launch call per step (the eager form of the
+// same pipeline lost to its 9 API calls per chunk, profiles/README.md).
+struct HostPipe {
+    static constexpr int MAXC = 8;
+    cudaStream_t ms, cs[MAXC];
+    cudaEvent_t fork, join[MAXC];
+    struct Entry {
+        const void* key[11];
+        int mask_mode, dtype, chunks, kernels;
+        cudaGraphExec_t exec;
+    };
+    std::vector<Entry> cache;
 };
 
 #define CK(call, msg)                                            \
@@ -1474,6 +1515,7 @@ static Params make_params(mtfjsp_env* h) {
     P.cfgw[0] = h->cfgw[0]; P.cfgw[1] = h->cfgw[1]; P.cfgw[2] = h->cfgw[2];
     P.divisor = h->divisor; P.gamma = h->gamma;
     P.jm_fin = h->jm_fin; P.jm_esa = h->jm_esa; P.cand_int = h->cand;
+    P.b0 = 0; P.b1 = h->L.B;
     return P;
 }
 
@@ -1489,7 +1531,7 @@ static int launch_env(mtfjsp_env* h, const Params& P, cudaStream_t s) {
         configured_dev = h->device;
         configured_smem = smem;
     }
-    int blocks = (L.B + L.warps_per_block - 1) / L.warps_per_block;
+    int blocks = (P.b1 - P.b0 + L.warps_per_block - 1) / L.warps_per_block;
     env_kernel<MODE, OutT><<<blocks, L.warps_per_block * 32, smem, s>>>(P);
     h->launches++;
     CK(cudaGetLastError(), "env_kernel launch");
@@ -1510,7 +1552,7 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
         configured_dev = h->device;
     }
     const int per_block = S::WARPS * S::EPW;
-    const int blocks = (L.B + per_block - 1) / per_block;
+    const int blocks = (P.b1 - P.b0 + per_block - 1) / per_block;
     env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(P);
     h->launches++;
     CK(cudaGetLastError(), "env_kernel_s launch");
@@ -1559,6 +1601,31 @@ static int launch_prestep(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, con
     return 0;
 }
 
+static int fill_obs(mtfjsp_env* h, Params& P, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src,
+                    uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype) {
+    if (dtype != MTFJSP_F32 && dtype != MTFJSP_F64) return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
+    if (mask_mode != MTFJSP_MASK_ESA && mask_mode != MTFJSP_MASK_FINISHED) return fail(MTFJSP_E_ARG, "bad mask_mode");
+    if ((adj_w == nullptr) != (adj_src == nullptr)) return fail(MTFJSP_E_ARG, "adj_w and adj_src go together");
+    P.tfea = task_fea; P.mfea = mach_fea; P.adj_w = adj_w; P.adj_src = adj_src; P.jmask = job_mask; P.cand = candidate;
+    P.mask_mode = mask_mode;
+    (void)h;
+    return MTFJSP_OK;
+}
+
+// fused step + observation over the env range [b0, b1) (the whole batch, or one chunk of the host-step pipeline)
+static int step_obs_range(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
+                          uint8_t* done, uint8_t* invalid, double* info6, void* task_fea, void* mach_fea, float* adj_w,
+                          int16_t* adj_src, uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype, int b0, int b1,
+                          cudaStream_t s, const int2* act2 = nullptr, unsigned char* rec = nullptr) {
+    Params P = make_params(h);
+    P.op = op; P.mach = mach; P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
+    P.info6 = info6; P.b0 = b0; P.b1 = b1; P.act2 = act2; P.rec = rec; P.rec_stride = h->rec_stride;
+    int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
+    if (rc) return rc;
+    return dtype == MTFJSP_F64 ? launch_env_auto<MODE_STEP | MODE_OBS, double>(h, P, s)
+                               : launch_env_auto<MODE_STEP | MODE_OBS, float>(h, P, s);
+}
+
 extern "C" {
 
 const char* mtfjsp_last_error(void) { return g_err; }
@@ -1605,6 +1672,7 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     {
         const char* fg = getenv("MTFJSP_FORCE_GENERIC");  // test hook: run the generic kernel on every size
         h->force_generic = fg && fg[0] == '1';
+        h->host_chunks = getenv("MTFJSP_HOST_CHUNKS") ? atoi(getenv("MTFJSP_HOST_CHUNKS")) : 4;
     }
     h->cfgw[0] = 0.4; h->cfgw[1] = 0.4; h->cfgw[2] = 0.2; h->divisor = 1.0; h->gamma = 0.99;
     size_t Bs = (size_t)B;
@@ -1628,6 +1696,9 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     ALLOC(h->r5, Bs * 5 * 8);
     ALLOC(h->s4, Bs * 4 * 8);
     ALLOC(h->info6, Bs * 6 * 8);
+    h->rec_stride = (48 + 3 * J + 7) / 8 * 8;
+    ALLOC(h->act2, Bs * 8);
+    ALLOC(h->rec, Bs * h->rec_stride);
     ALLOC(h->dn, Bs);
     ALLOC(h->inv, Bs);
     ALLOC(h->tmp_adj_w, Bs * N * 2 * 4);
@@ -1641,9 +1712,16 @@ int mtfjsp_destroy(mtfjsp_env* h) {
     if (!h) return MTFJSP_OK;
     cudaSetDevice(h->device);
     void* ptrs[] = {h->sd, h->si, h->xs, h->t, h->p, h->edge_id, h->jm_fin, h->jm_esa, h->cand, h->a_op, h->a_mach,
-                    h->r5, h->s4, h->info6, h->dn, h->inv, h->tmp_adj_w, h->tmp_adj_src};
+                    h->r5, h->s4, h->info6, h->dn, h->inv, h->tmp_adj_w, h->tmp_adj_src, h->act2, h->rec};
     for (void* q : ptrs)
         if (q) cudaFree(q);
+    if (h->pipe) {
+        for (auto& e : h->pipe->cache) cudaGraphExecDestroy(e.exec);
+        cudaStreamDestroy(h->pipe->ms);
+        cudaEventDestroy(h->pipe->fork);
+        for (int c = 0; c < HostPipe::MAXC; c++) { cudaStreamDestroy(h->pipe->cs[c]); cudaEventDestroy(h->pipe->join[c]); }
+        delete h->pipe;
+    }
     delete h;
     return MTFJSP_OK;
 }
@@ -1704,16 +1782,6 @@ int mtfjsp_reset(mtfjsp_env* h, const double* weights, void* stream) {
     return rc;
 }
 
-static int fill_obs(mtfjsp_env* h, Params& P, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src,
-                    uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype) {
-    if (dtype != MTFJSP_F32 && dtype != MTFJSP_F64) return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
-    if (mask_mode != MTFJSP_MASK_ESA && mask_mode != MTFJSP_MASK_FINISHED) return fail(MTFJSP_E_ARG, "bad mask_mode");
-    if ((adj_w == nullptr) != (adj_src == nullptr)) return fail(MTFJSP_E_ARG, "adj_w and adj_src go together");
-    P.tfea = task_fea; P.mfea = mach_fea; P.adj_w = adj_w; P.adj_src = adj_src; P.jmask = job_mask; P.cand = candidate;
-    P.mask_mode = mask_mode;
-    (void)h;
-    return MTFJSP_OK;
-}
 
 int mtfjsp_step(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
                 uint8_t* done, uint8_t* invalid, void* stream) {
@@ -1743,12 +1811,8 @@ int mtfjsp_step_obs(mtfjsp_env* h, const int32_t* op, const int32_t* mach, doubl
     if (!h || !op || !mach) return fail(MTFJSP_E_ARG, "mtfjsp_step_obs: bad argument");
     if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_step_obs before mtfjsp_reset");
     CK(cudaSetDevice(h->device), "cudaSetDevice");
-    Params P = make_params(h);
-    P.op = op; P.mach = mach; P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
-    int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
-    if (rc) return rc;
-    return dtype == MTFJSP_F64 ? launch_env_auto<MODE_STEP | MODE_OBS, double>(h, P, (cudaStream_t)stream)
-                               : launch_env_auto<MODE_STEP | MODE_OBS, float>(h, P, (cudaStream_t)stream);
+    return step_obs_range(h, op, mach, reward5, scaled4, done, invalid, nullptr, task_fea, mach_fea, adj_w, adj_src,
+                          job_mask, candidate, mask_mode, dtype, 0, h->L.B, (cudaStream_t)stream);
 }
 
 int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_mask, int dtype, void* stream) {
@@ -1860,32 +1924,148 @@ int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_
                            candidate, mask_mode, dtype, stream);
 }
 
+static bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // extern "C"
+
+// Host-buffer step behind both entry points.  Packed form: act_host [B,2] i32 in, rec_host [B] records out (one copy
+// each way per chunk); split form: op / mach in, info6 / job_mask / candidate out (five copies per chunk).
+struct HostIO {
+    const int32_t *op, *mach, *act;
+    double* info6;
+    uint8_t* jm;
+    int32_t* cand;
+    unsigned char* rec;
+};
+
+static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src,
+                          int mask_mode, int dtype, cudaStream_t s) {
+    const Layout& L = h->L;
+    const bool packed = io.act != nullptr;
+    const uint8_t* jm_dev = mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin;
+    const size_t rs = (size_t)h->rec_stride;
+    // everything one chunk [b0, b1) does, in order, on stream q
+    auto chunk = [&](int b0, int b1, cudaStream_t q) -> int {
+        const size_t n = (size_t)(b1 - b0);
+        if (packed) {
+            CK(cudaMemcpyAsync(h->act2 + b0, io.act + (size_t)b0 * 2, n * 8, cudaMemcpyHostToDevice, q), "H2D actions");
+        } else {
+            CK(cudaMemcpyAsync(h->a_op + b0, io.op + b0, n * 4, cudaMemcpyHostToDevice, q), "H2D op");
+            CK(cudaMemcpyAsync(h->a_mach + b0, io.mach + b0, n * 4, cudaMemcpyHostToDevice, q), "H2D mach");
+        }
+        int rc = step_obs_range(h, h->a_op, h->a_mach, nullptr, nullptr, h->dn, h->inv, io.info6 ? h->info6 : nullptr,
+                                task_fea, mach_fea, adj_w, adj_src, nullptr, nullptr, mask_mode, dtype, b0, b1, q,
+                                packed ? h->act2 : nullptr, io.rec ? h->rec : nullptr);
+        if (rc) return rc;
+        if (io.rec) CK(cudaMemcpyAsync(io.rec + b0 * rs, h->rec + b0 * rs, n * rs, cudaMemcpyDeviceToHost, q), "D2H records");
+        if (io.info6)
+            CK(cudaMemcpyAsync(io.info6 + (size_t)b0 * 6, h->info6 + (size_t)b0 * 6, n * 48, cudaMemcpyDeviceToHost, q), "D2H info6");
+        if (io.jm)
+            CK(cudaMemcpyAsync(io.jm + (size_t)b0 * L.J, jm_dev + (size_t)b0 * L.J, n * L.J, cudaMemcpyDeviceToHost, q), "D2H job_mask");
+        if (io.cand)
+            CK(cudaMemcpyAsync(io.cand + (size_t)b0 * L.J, h->cand + (size_t)b0 * L.J, n * L.J * 4, cudaMemcpyDeviceToHost, q),
+               "D2H candidate");
+        return MTFJSP_OK;
+    };
+    const int want_chunks = h->host_chunks;  // MTFJSP_HOST_CHUNKS, 0: no graph
+    const bool pinned = is_pinned(io.op) && is_pinned(io.mach) && is_pinned(io.act) && is_pinned(io.info6) &&
+                        is_pinned(io.jm) && is_pinned(io.cand) && is_pinned(io.rec);
+    if (!pinned || want_chunks <= 0) {
+        // pageable buffers: the copies are staged by the driver and cannot overlap; plain in-order sequence
+        int rc = chunk(0, L.B, s);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+        return MTFJSP_OK;
+    }
+    if (!h->pipe) {
+        HostPipe* hp = new (std::nothrow) HostPipe();
+        if (!hp) return fail(MTFJSP_E_ARG, "out of host memory");
+        CK(cudaStreamCreateWithFlags(&hp->ms, cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaEventCreateWithFlags(&hp->fork, cudaEventDisableTiming), "cudaEventCreate");
+        for (int c = 0; c < HostPipe::MAXC; c++) {
+            CK(cudaStreamCreateWithFlags(&hp->cs[c], cudaStreamNonBlocking), "cudaStreamCreate");
+            CK(cudaEventCreateWithFlags(&hp->join[c], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        h->pipe = hp;
+    }
+    HostPipe* hp = h->pipe;
+    // chunks of whole 256-env groups, at least 4,096 envs each (below that one launch does not fill the GPU)
+    int chunks = want_chunks > HostPipe::MAXC ? HostPipe::MAXC : want_chunks;
+    while (chunks > 1 && L.B / chunks < 4096) chunks--;
+    const void* key[11] = {io.op, io.mach, io.act, io.info6, io.jm, io.cand, io.rec, task_fea, mach_fea, adj_w, adj_src};
+    HostPipe::Entry* ent = nullptr;
+    for (auto& e : hp->cache)
+        if (!memcmp(e.key, key, sizeof key) && e.mask_mode == mask_mode && e.dtype == dtype && e.chunks == chunks) { ent = &e; break; }
+    if (!ent) {
+        if (hp->cache.size() >= 256) {  // addresses keep changing: start over rather than grow without bound
+            for (auto& e : hp->cache) cudaGraphExecDestroy(e.exec);
+            hp->cache.clear();
+        }
+        const int per = ((L.B + chunks - 1) / chunks + 255) / 256 * 256;
+        const int64_t l0 = h->launches;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(hp->ms, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+        int rc = MTFJSP_OK;
+        cudaError_t ce = cudaEventRecord(hp->fork, hp->ms);
+        for (int c = 0; c < chunks && rc == MTFJSP_OK && ce == cudaSuccess; c++) {
+            const int b0 = c * per, b1 = (c + 1) * per < L.B ? (c + 1) * per : L.B;
+            if (b0 >= b1) break;
+            cudaStream_t q = hp->cs[c];
+            ce = cudaStreamWaitEvent(q, hp->fork, 0);
+            if (ce != cudaSuccess) break;
+            rc = chunk(b0, b1, q);
+            if (rc) break;
+            ce = cudaEventRecord(hp->join[c], q);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(hp->ms, hp->join[c], 0);
+        }
+        cudaError_t ee = cudaStreamEndCapture(hp->ms, &g);
+        const int kernels = (int)(h->launches - l0);
+        h->launches = l0;  // the capture launched nothing; replays are counted below
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MTFJSP_E_CUDA, "host-step capture", ce); }
+        CK(ee, "cudaStreamEndCapture");
+        HostPipe::Entry e;
+        memcpy(e.key, key, sizeof key);
+        e.mask_mode = mask_mode; e.dtype = dtype; e.chunks = chunks; e.kernels = kernels;
+        cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
+        cudaGraphDestroy(g);
+        CK(ie, "cudaGraphInstantiate");
+        hp->cache.push_back(e);
+        ent = &hp->cache.back();
+    }
+    CK(cudaGraphLaunch(ent->exec, s), "cudaGraphLaunch");
+    h->launches += ent->kernels;
+    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return MTFJSP_OK;
+}
+
+extern "C" {
+
 int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_host, double* info6_host,
                      uint8_t* job_mask_host, int32_t* candidate_host, void* task_fea, void* mach_fea, float* adj_w,
                      int16_t* adj_src, int mask_mode, int dtype, void* stream) {
     if (!h || !op_host || !mach_host) return fail(MTFJSP_E_ARG, "mtfjsp_step_host: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_step_host before mtfjsp_reset");
     CK(cudaSetDevice(h->device), "cudaSetDevice");
-    cudaStream_t s = (cudaStream_t)stream;
-    const Layout& L = h->L;
-    CK(cudaMemcpyAsync(h->a_op, op_host, (size_t)L.B * 4, cudaMemcpyHostToDevice, s), "H2D op");
-    CK(cudaMemcpyAsync(h->a_mach, mach_host, (size_t)L.B * 4, cudaMemcpyHostToDevice, s), "H2D mach");
-    int rc = mtfjsp_step_obs(h, h->a_op, h->a_mach, h->r5, h->s4, h->dn, h->inv, task_fea, mach_fea, adj_w, adj_src,
-                             nullptr, nullptr, mask_mode, dtype, stream);
-    if (rc) return rc;
-    if (info6_host) {
-        info6_kernel<<<(L.B + 255) / 256, 256, 0, s>>>(L.B, h->r5, h->s4, h->dn, h->info6);
-        h->launches++;
-        CK(cudaGetLastError(), "info6_kernel");
-        CK(cudaMemcpyAsync(info6_host, h->info6, (size_t)L.B * 48, cudaMemcpyDeviceToHost, s), "D2H info6");
-    }
-    if (job_mask_host)
-        CK(cudaMemcpyAsync(job_mask_host, mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin, (size_t)L.B * L.J,
-                           cudaMemcpyDeviceToHost, s), "D2H job_mask");
-    if (candidate_host)
-        CK(cudaMemcpyAsync(candidate_host, h->cand, (size_t)L.B * L.J * 4, cudaMemcpyDeviceToHost, s), "D2H candidate");
-    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-    return MTFJSP_OK;
+    HostIO io = {op_host, mach_host, nullptr, info6_host, job_mask_host, candidate_host, nullptr};
+    return host_step_impl(h, io, task_fea, mach_fea, adj_w, adj_src, mask_mode, dtype, (cudaStream_t)stream);
 }
+
+int mtfjsp_step_host_packed(mtfjsp_env* h, const int32_t* actions_host, void* records_host, void* task_fea, void* mach_fea,
+                            float* adj_w, int16_t* adj_src, int mask_mode, int dtype, void* stream) {
+    if (!h || !actions_host || !records_host) return fail(MTFJSP_E_ARG, "mtfjsp_step_host_packed: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_step_host_packed before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    HostIO io = {nullptr, nullptr, actions_host, nullptr, nullptr, nullptr, (unsigned char*)records_host};
+    return host_step_impl(h, io, task_fea, mach_fea, adj_w, adj_src, mask_mode, dtype, (cudaStream_t)stream);
+}
+
+int mtfjsp_host_record_bytes(const mtfjsp_env* h) { return h ? h->rec_stride : 0; }
 
 int64_t mtfjsp_launch_count(const mtfjsp_env* h) { return h ? h->launches : 0; }
 

@@ -151,6 +151,27 @@ class BatchedMTFJSPEnv:
                                          _ptr(candidate_host), _ptr(self.task_fea), _ptr(self.mach_fea), _ptr(self.adj_w),
                                          _ptr(self.adj_src), mm, self._dt, _stream()), "mtfjsp_step_host")
 
+    def host_record_dtype(self):
+        """numpy structured dtype of one packed host-step record (include/mtfjsp.h: mtfjsp_step_host_packed)."""
+        nbytes = int(self._lib.mtfjsp_host_record_bytes(self._h))
+        return np.dtype({"names": ["info6", "candidate", "job_mask"], "formats": [("<f8", 6), ("<i2", self.J), ("u1", self.J)],
+                         "offsets": [0, 48, 48 + 2 * self.J], "itemsize": nbytes})
+
+    def host_buffers(self):
+        """Pinned host buffers for step_host_packed: actions [B,2] int32 and records [B, record_bytes] uint8
+        (view the latter with `.numpy().view(env.host_record_dtype())[:, 0]`)."""
+        nbytes = int(self._lib.mtfjsp_host_record_bytes(self._h))
+        return (torch.zeros((self.B, 2), dtype=torch.int32).pin_memory(),
+                torch.zeros((self.B, nbytes), dtype=torch.uint8).pin_memory())
+
+    def step_host_packed(self, actions_host, records_host, mask_mode=None):
+        """Host-buffer step, one copy each way: actions_host [B,2] int32 (op, machine) pairs in, packed step records
+        out (info6, candidates, job mask per env); observations stay on the device."""
+        mm = self.mask_mode if mask_mode is None else mask_mode
+        check(self._lib.mtfjsp_step_host_packed(self._h, _ptr(actions_host), _ptr(records_host), _ptr(self.task_fea),
+                                                _ptr(self.mach_fea), _ptr(self.adj_w), _ptr(self.adj_src), mm, self._dt,
+                                                _stream()), "mtfjsp_step_host_packed")
+
     # ---- views ---------------------------------------------------------------------------------------------------
     def dense_adj(self, dtype=torch.float64):
         adj = torch.empty((self.B, self.N, self.N), dtype=dtype, device=self.device)

@@ -136,6 +136,19 @@ int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_
                      uint8_t* job_mask_host, int32_t* candidate_host, void* task_fea, void* mach_fea, float* adj_w,
                      int16_t* adj_src, int mask_mode, int dtype, void* stream);
 
+/* Packed form of mtfjsp_step_host, one copy each way: `actions_host` [B,2] i32 is the reference's joint-action list
+ * [(task_idx, machine_idx), ...] (trainer/parallel_env.py:217-232) as an array; `records_host` receives B records of
+ * mtfjsp_host_record_bytes(h) bytes each (8-byte aligned):
+ *     f64 info6[6] = (r, done, mk_s, idle_s, pt_s, tt_s)   trainer/parallel_env.py:260
+ *     i16 candidate[J]                                      algorithm/ppo_algorithm.py:202-317
+ *     u8  job_mask[J]   (1 = not selectable), then padding
+ * With pinned buffers the batch is cut into MTFJSP_HOST_CHUNKS (default 4) chunks whose copy-in -> kernel -> copy-out
+ * chains run on separate streams, replayed as one CUDA graph per step, so that the copy-out of chunk c overlaps the
+ * kernel of chunk c+1; pageable buffers take the plain in-order path.  Synchronises `stream` before returning. */
+int mtfjsp_step_host_packed(mtfjsp_env* h, const int32_t* actions_host, void* records_host, void* task_fea, void* mach_fea,
+                            float* adj_w, int16_t* adj_src, int mask_mode, int dtype, void* stream);
+int mtfjsp_host_record_bytes(const mtfjsp_env* h);
+
 /* ---- encoder side --------------------------------------------------------------------------
  * replaces: actor_critic.py:139-140 (dense adj -> sparse COO), gcn_mlp.py:125 (FP64 SpMM A*h) and :133-149 (degree
  * SpMM): out[b,v,:] = (h[b,v,:] + adj_w[b,v,0]*h[b,v-1,:] + adj_w[b,v,1]*h[b,adj_src[b,v],:]) / in_degree, FP32

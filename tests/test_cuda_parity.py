@@ -214,12 +214,14 @@ def test_step_before_reset_is_a_state_error():
         env.step(env.op, env.mach)
 
 
+@pytest.mark.parametrize("B", [4096 + 77, 3 * 4096 + 77])
 @pytest.mark.parametrize("pinned", [True, False])
-def test_host_step_equals_device_step(pinned, kernel_path):
-    """mtfjsp_step_host with pinned and with pageable host buffers must equal the device-pointer call bit for bit,
-    including the all-invalid step after the episode has ended."""
+def test_host_step_equals_device_step(pinned, B, kernel_path):
+    """mtfjsp_step_host with pinned (graph-replayed chunk pipeline; 1 chunk and 3 ragged chunks) and with pageable
+    host buffers (in-order copies) must equal the device-pointer call bit for bit, including the all-invalid step
+    after the episode has ended."""
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
-    B, J, M, E = 4096 + 77, 6, 6, 2
+    J, M, E = 6, 6, 2
     N = J * M
     d = ins.synthetic_instances(0, B, J, M, E, 77)
     w = ins.random_weights(0, B, 77)
@@ -231,6 +233,15 @@ def test_host_step_equals_device_step(pinned, kernel_path):
         env.reset(w)
         envs.append(env)
     dev_env, host_env = envs
+    pk_env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)  # packed-record form
+    pk_env.load(d["t"], d["p"], d["transT"], d["edge"])
+    pk_env.scaler_init()
+    pk_env.reset(w)
+    pk_act, pk_rec = pk_env.host_buffers()
+    if not pinned:
+        pk_act, pk_rec = pk_act.clone(), pk_rec.clone()
+    pk_rec.fill_(0xAB)
+    rec = pk_rec.numpy().view(pk_env.host_record_dtype())[:, 0]
     pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
     info6 = pin(torch.full((B, 6), -7.0, dtype=torch.float64))
     h_jm = pin(torch.full((B, J), 9, dtype=torch.uint8))
@@ -247,11 +258,18 @@ def test_host_step_equals_device_step(pinned, kernel_path):
         eq(info6[:, 2:].numpy(), dev_env.scaled4.cpu().numpy())
         eq(h_jm.numpy(), dev_env.job_mask.cpu().numpy())
         eq(h_cd.numpy(), dev_env.candidate.cpu().numpy())
+        pk_act[:, 0].copy_(op.cpu()); pk_act[:, 1].copy_(mach.cpu())
+        pk_env.step_host_packed(pk_act, pk_rec)
+        eq(rec["info6"], info6.numpy())
+        eq(rec["candidate"].astype(np.int32), h_cd.numpy())
+        eq(rec["job_mask"], h_jm.numpy())
         for name in ("task_fea", "mach_fea", "adj_w", "adj_src"):
             assert torch.equal(getattr(host_env, name), getattr(dev_env, name)), (name, s)
+            assert torch.equal(getattr(pk_env, name), getattr(dev_env, name)), (name, s)
         assert int(dev_env.invalid.sum()) == (B if s == N else 0)
     assert bool(dev_env.done.all()) and float(info6[:, 1].sum()) == B
     eq(host_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
+    eq(pk_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
 
 
 @pytest.mark.parametrize("cfg", [(65536, 6, 6, 2), (16384, 10, 10, 3), (4096, 30, 20, 5)])
