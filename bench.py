@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- MT-FJSP env-steps/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
-A "step" is one pass of the environment hot path over the whole env batch: random valid action
-(policy kernel) -> candidate-machine features (mfea1 kernel) -> fused transition + reward + reward
-scaling + observation + job mask (env kernel), i.e. everything the environment side of Run.py's rollout
-loop does per step.  Episodes wrap inside the timed region: every
-N = J*M steps the batch is reset (one more launch), as the reference's loop does.
+A "step" is one pass of the environment hot path over the whole env batch: random valid action ->
+candidate-machine features -> transition + reward + reward scaling + observation + job mask, i.e.
+everything the environment side of Run.py's rollout loop does per step,
+one launch of the fused kernel for the sizes that have a specialised one.  Episodes wrap inside the timed
+region: every N = J*M steps the batch is reset (two more launches), as the reference's loop does.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|B|C]
 
@@ -234,11 +234,11 @@ def run_ours(args, wl):
     peak, peak_src = measured_peak()
     achieved = bytes_step * B / (k_us * 1e-6) / 1e9
 
-    # ---- e2e: host-buffer C-ABI call per step (pinned H2D actions, D2H step info + mask + candidates) ----
-    h_op = rec_op.cpu().pin_memory(); h_mc = rec_mc.cpu().pin_memory()
-    info6 = torch.empty((B, 6), dtype=torch.float64).pin_memory()
-    h_jm = torch.empty((B, J), dtype=torch.uint8).pin_memory()
-    h_cd = torch.empty((B, J), dtype=torch.int32).pin_memory()
+    # ---- e2e: host-buffer C-ABI call per step (pinned H2D action pairs, D2H packed step records = step info + job
+    # mask + candidates; mtfjsp_step_host_packed cuts the batch into chunks whose copies overlap the other chunks' kernels) ----
+    h_act = torch.stack([rec_op.cpu(), rec_mc.cpu()], dim=2).contiguous().pin_memory()  # [N,B,2] (op, machine)
+    _, h_rec = env.host_buffers()
+    rec_view = h_rec.numpy().view(env.host_record_dtype())[:, 0]
     Ke = min(K, 4 * N)
 
     def e2e_steps(n):
@@ -247,10 +247,10 @@ def run_ours(args, wl):
         for _ in range(n):
             if s == N:
                 env.reset(w); env.scaler_reset(); s = 0
-            env.step_host(h_op[s], h_mc[s], info6, h_jm, h_cd)
+            env.step_host_packed(h_act[s], h_rec)
             s += 1
 
-    e2e_steps(3)
+    e2e_steps(N + 3)  # one whole episode first: every action buffer's graph is instantiated outside the timed region
     barrier()
     t0 = time.perf_counter()
     e2e_steps(Ke)
@@ -258,7 +258,8 @@ def run_ours(args, wl):
     e2e_s = time.perf_counter() - t0
     e2e_s = sh.max_over_ranks(e2e_s, dev)
     e2e_val = B * world * Ke / e2e_s
-    assert float(info6[:, 1].sum()) in (0.0, float(B))
+    assert float(rec_view["info6"][:, 1].sum()) in (0.0, float(B))
+    h_op = rec_op.cpu(); h_mc = rec_mc.cpu()
     # ---- BASELINE.json configs[4] (forward half): the same env slice driven by the MAPPO actors on the device ----
     policy = None
     if not args.no_policy and (J, M) == (6, 6):
@@ -370,9 +371,12 @@ def run_ours(args, wl):
             "config": {"workload": wl["name"], "envs_per_gpu": B, "jobs": J, "machines": M, "edges": E, "obs_dtype": "f32",
                        "mask_mode": "ESA", "left_shift": True, "parallelism": "env-slices x%d (no data-path collective)" % world,
                        "l2": "working set %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (B * (bytes_step + 2000) / 1e6),
-                       "launches_per_step": 2, "kernels": "prestep_kernel (policy + candidate-machine features), env_kernel_s (step + reward + obs + mask)"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * (48 + 5 * J),
-                    "api": "mtfjsp_step_host (C ABI, pinned host buffers; observation tensors stay on the device)",
+                       "launches_per_step": round(launches / K, 3),
+                       "kernels": "env_kernel_s<STEP|OBS|POLICY> (random policy + candidate-machine features + step + reward + "
+                                  "obs + mask in one launch; reset launches env_kernel<RESET> + scaler_kernel every %d steps)" % N},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * h_rec.shape[1],
+                    "api": "mtfjsp_step_host_packed (C ABI, pinned host buffers: [B,2] i32 action pairs in, [B] packed records "
+                           "(f64 info6, i16 candidates, u8 job mask) out; observation tensors stay on the device)",
                     "steps": Ke},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -76,6 +76,14 @@ struct Params {
     uint8_t* invalid;
     double* info6;  // optional [B,6] = (r, done, mk_s, idle_s, pt_s, tt_s), trainer/parallel_env.py:260
     const int2* act2;      // optional packed actions [B] (op, machine); used instead of op / mach when set
+    // MODE_POLICY (random-rollout step): the counter-based random valid action is drawn in the kernel from the masks the
+    // previous launch left in jm_* / cand_int, and the candidate-machine features of the drawn op are written
+    uint64_t seed, env_offset;
+    const int8_t* edge_id;
+    int32_t* op_out;
+    int32_t* mach_out;
+    void* mfea1;     // [B,M,6] OutT or NULL
+    uint8_t* mmask;  // [B,M] or NULL
     unsigned char* rec;    // optional packed step records, rec_stride bytes per env: f64 info6[6] | i16 cand[J] | u8 mask[J]
     int rec_stride;
     int b0, b1;     // env range [b0, b1) of this launch (host-step pipeline launches sub-ranges)
@@ -93,7 +101,7 @@ struct Params {
     int32_t* cand_int;
 };
 
-enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4 };
+enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4, MODE_POLICY = 8 };
 
 // step info (r, done, mk_s, idle_s, pt_s, tt_s) goes to the contiguous [B,6] array and / or the packed host record
 #define INFO6_PUT(b_, k_, v_)                                                                               \
@@ -615,6 +623,7 @@ template <int J_, int M_, int G_, int WARPS_>
 struct Spec {
     static constexpr int J = J_, M = M_, G = G_, N = J_ * M_, EPW = 32 / G_, WARPS = WARPS_;
     static_assert(J_ <= G_ && M_ <= G_, "one lane per job and per machine");
+    static_assert(3 * M_ <= J_ * M_, "the random-step mode parks three compacted machine rows in the op scratch");
     static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 13, 2);
     static constexpr int SI = calign(3 * N + M + 3 + J, 8);
     static constexpr int XS = calign(2 * N + M * M, 2);
@@ -671,6 +680,42 @@ __device__ __forceinline__ double adj_val_t(double w, bool u_assigned, double du
     return trunc(wi - nd) + 1.0;
 }
 
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ uint32_t rand_u32(uint64_t seed, uint64_t env, uint64_t step, uint64_t stream) {
+    uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL + (stream << 56)));
+    return (uint32_t)(x >> 32);
+}
+
+// numpy pairwise sum of up to M (<= 64) values held in registers/local array
+__device__ __forceinline__ double np_sum_small(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r += a[i];
+        return r;
+    }
+    double r[8];
+    for (int i = 0; i < 8; i++) r[i] = a[i];
+    int nb = n - (n & 7), i;
+    for (i = 8; i < nb; i += 8)
+        for (int k = 0; k < 8; k++) r[k] += a[i + k];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+// position of the k-th (0-based) set bit of `bits`, -1 if there are not that many; J, M <= 32 bits
+__device__ __forceinline__ int kth_set_bit(unsigned bits, int k, int maxk) {
+#pragma unroll 4
+    for (int i = 0; i < maxk; i++)
+        if (i < k) bits &= bits - 1;
+    return __ffs(bits) - 1;
+}
+
 template <class S, int MODE, typename OutT>
 __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_constant__ Params P) {
     constexpr int J = S::J, M = S::M, N = S::N, G = S::G, EPW = S::EPW, ITER = S::ITER;
@@ -698,7 +743,17 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
 
     // the action is the head of a dependent chain (op -> t[op][m], mind row of its job): issue it first
     int a = 0, m = 0;
-    if (MODE & MODE_STEP) {
+    bool sel = false;  // MODE_POLICY, lane j: job j selectable
+    int cj = 0;        //              lane j: candidate op of job j
+    int nsel_step = 0; //              ops scheduled so far = the step counter of the random stream
+    if constexpr ((MODE & MODE_POLICY) != 0) {
+        const uint8_t* jsrc = (P.mask_mode == MTFJSP_MASK_ESA ? P.jm_esa : P.jm_fin) + (size_t)bc * J;
+        if (gl < J) {
+            sel = jsrc[gl] == 0;
+            cj = P.cand_int[(size_t)bc * J + gl];
+        }
+        nsel_step = g_si[S::O_MISC + 2];
+    } else if (MODE & MODE_STEP) {
         if (P.act2) { const int2 am = __ldg(P.act2 + bc); a = am.x; m = am.y; }
         else { a = __ldg(P.op + bc); m = __ldg(P.mach + bc); }
     }
@@ -717,11 +772,38 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
 #pragma unroll 4
         for (int i = gl; i < S::SI / 8; i += G) cp_async16(dst + i, src + i);
     }
+    double tr = 0.0, pr = 0.0;  // MODE_POLICY, lane k < M: t[op][k], p[op][k]
+    int nsel = 1;
+    if constexpr ((MODE & MODE_POLICY) != 0) {
+        // uniform random selectable job, then uniform random feasible machine of its candidate op: the draws of
+        // policy_kernel / oracle_policy_random (keyed by seed, global env index, step counter, stream)
+        const unsigned jb = (__ballot_sync(FULL, sel) >> (ge * G)) & S::GMASK;
+        nsel = __popc(jb);
+        const uint64_t genv = P.env_offset + (uint64_t)bc;
+        const int kj = (int)(((uint64_t)rand_u32(P.seed, genv, (uint64_t)nsel_step, 0) * (uint64_t)nsel) >> 32);
+        const int jl = kth_set_bit(jb, kj, J);
+        a = __shfl_sync(FULL, cj, jl < 0 ? 0 : jl, G);
+        if (nsel == 0) a = -1;
+        const int ar = (a >= 0 && a < N) ? a : 0;
+        if (gl < M) {
+            tr = __ldg(P.t + ((size_t)bc * N + ar) * M + gl);
+            pr = __ldg(P.p + ((size_t)bc * N + ar) * M + gl);
+        }
+        const unsigned fb = (__ballot_sync(FULL, gl < M && tr >= 0) >> (ge * G)) & S::GMASK;
+        const int nf = __popc(fb);
+        const int km = (int)(((uint64_t)rand_u32(P.seed, genv, (uint64_t)nsel_step, 1) * (uint64_t)nf) >> 32);
+        m = (nsel == 0) ? -1 : kth_set_bit(fb, km, M);
+        if (active && gl == 0) { P.op_out[b] = a; P.mach_out[b] = m; }
+    }
     bool valid = (MODE & MODE_STEP) && active && a >= 0 && a < N && m >= 0 && m < M;
     const int ac = valid ? a : 0, mc = valid ? m : 0;
     const int apos = ac % M, ja = ac / M;
     double d = 0.0, pa = 0.0, mind_r = 0.0;
-    if (MODE & MODE_STEP) {
+    if constexpr ((MODE & MODE_POLICY) != 0) {
+        d = __shfl_sync(FULL, tr, mc, G);   // an invalid action never uses d / pa
+        pa = __shfl_sync(FULL, pr, mc, G);
+        if (gl < M) mind_r = __ldg(g_xs + S::O_MIND + ja * M + gl);
+    } else if (MODE & MODE_STEP) {
         d = __ldg(P.t + ((size_t)bc * N + ac) * M + mc);
         pa = __ldg(P.p + ((size_t)bc * N + ac) * M + mc);
         if (gl < M) mind_r = __ldg(g_xs + S::O_MIND + ja * M + gl);  // lane c: min duration of op (ja, c)
@@ -743,6 +825,55 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
     int16_t* __restrict__ s_cnt = s_si + S::O_CNT;
     int16_t* __restrict__ s_misc = s_si + S::O_MISC;
     int16_t* __restrict__ s_nxt = s_si + S::O_NXT;
+
+    if constexpr ((MODE & MODE_POLICY) != 0) {
+        // candidate-machine features of the drawn op (trainer/parallel_env.py:152-214), lane k = machine k; the means
+        // run over the positive entries in machine order = numpy's sum of the compacted row (np_sum_small)
+        if (P.mfea1 != nullptr) {
+            const double ptl = tr * fabs(pr);
+            const bool qt = gl < M && tr > 0, qpt = gl < M && ptl > 0, qp = gl < M && pr > 0;
+            const unsigned bt = (__ballot_sync(FULL, qt) >> (ge * G)) & S::GMASK;
+            const unsigned bpt = (__ballot_sync(FULL, qpt) >> (ge * G)) & S::GMASK;
+            const unsigned bp = (__ballot_sync(FULL, qp) >> (ge * G)) & S::GMASK;
+            const unsigned lt = (1u << gl) - 1u;
+            if (qt) s_pt[__popc(bt & lt)] = tr;
+            if (qpt) s_pt[M + __popc(bpt & lt)] = ptl;
+            if (qp) s_pt[2 * M + __popc(bp & lt)] = pr;
+            __syncwarp();
+            const int which = gl % 3;  // lanes 0, 1, 2 of the group: mean t, mean t*|p|, mean p (one division each)
+            const int cnt = which == 0 ? __popc(bt) : which == 1 ? __popc(bpt) : __popc(bp);
+            const double mean_w = np_sum_small(s_pt + which * M, cnt) / (double)cnt;
+            const double mean_t = __shfl_sync(FULL, mean_w, 0, G);
+            const double mean_pt = __shfl_sync(FULL, mean_w, 1, G);
+            const double mean_p = __shfl_sync(FULL, mean_w, 2, G);
+            if (active && nsel > 0 && gl < M) {
+                int pm_row = M - 1;  // int(tfea[a-1][5]) - 1 wraps to the last row while the predecessor is unscheduled
+                if (a % M != 0) {
+                    const int mp = s_mach[a - 1];
+                    if (mp >= 0) pm_row = mp;
+                }
+                const int infeasible = !(tr >= 0);
+                const double f0 = tr > 0 ? tr : mean_t, f1 = ptl > 0 ? ptl : mean_pt;
+                const double f2 = (a % M == 0) ? 0.0 : s_tt[pm_row * M + gl];
+                const double f3 = (double)(1 - infeasible), f4 = pr > 0 ? pr : mean_p;
+                const double f5 = (double)P.edge_id[(size_t)b * M + gl];
+                OutT* o = reinterpret_cast<OutT*>(P.mfea1) + ((size_t)b * M + gl) * 6;
+                if constexpr (sizeof(OutT) == 4) {
+                    float2* o2 = reinterpret_cast<float2*>(o);
+                    o2[0] = make_float2((float)f0, (float)f1);
+                    o2[1] = make_float2((float)f2, (float)f3);
+                    o2[2] = make_float2((float)f4, (float)f5);
+                } else {
+                    double2* o2 = reinterpret_cast<double2*>(o);
+                    o2[0] = make_double2(f0, f1);
+                    o2[1] = make_double2(f2, f3);
+                    o2[2] = make_double2(f4, f5);
+                }
+                if (P.mmask) P.mmask[(size_t)b * M + gl] = (uint8_t)infeasible;
+            }
+            __syncwarp();  // s_pt is reused by the idle terms
+        }
+    }
 
     bool done = false;
     double idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;
@@ -1145,23 +1276,6 @@ __global__ void scaler_kernel(Layout L, double* sd, int full) {
     }
 }
 
-// numpy pairwise sum of up to M (<= 64) values held in registers/local array
-__device__ __forceinline__ double np_sum_small(const double* a, int n) {
-    if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; i++) r += a[i];
-        return r;
-    }
-    double r[8];
-    for (int i = 0; i < 8; i++) r[i] = a[i];
-    int nb = n - (n & 7), i;
-    for (i = 8; i < nb; i += 8)
-        for (int k = 0; k < 8; k++) r[k] += a[i + k];
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; i++) res += a[i];
-    return res;
-}
-
 // cal_cur_task_machine_feature, trainer/parallel_env.py:152-214.  One thread per env.
 template <typename OutT>
 __global__ void mfea1_kernel(Layout L, const double* __restrict__ t, const double* __restrict__ p,
@@ -1210,17 +1324,6 @@ __global__ void mfea1_kernel(Layout L, const double* __restrict__ t, const doubl
         f[5] = (OutT)edge_id[(size_t)b * M + m];
         if (mmask) mmask[(size_t)b * M + m] = (uint8_t)infeasible;
     }
-}
-
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    return x ^ (x >> 31);
-}
-__device__ __forceinline__ uint32_t rand_u32(uint64_t seed, uint64_t env, uint64_t step, uint64_t stream) {
-    uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL + (stream << 56)));
-    return (uint32_t)(x >> 32);
 }
 
 // uniform random valid action from the current masks; one thread per env
@@ -1479,7 +1582,7 @@ struct mtfjsp_env {
     float* tmp_adj_w;
     int16_t* tmp_adj_src;
     bool loaded, reset_done, force_generic;
-    int host_chunks;  // tuning knobs read from the environment at create time (tests compare the settings)
+    int host_chunks, fuse_policy;  // tuning knobs read from the environment at create time (tests compare the settings)
     int64_t launches;
     struct HostPipe* pipe;  // host-step pipeline (streams, events, instantiated graphs), created on first use
 };
@@ -1571,6 +1674,21 @@ static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
         if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 2>, MODE, OutT>(h, P, s);
     }
     return launch_env<MODE, OutT>(h, P, s);
+}
+
+// random-rollout step in one launch (policy + candidate-machine features + step + observation): sizes with a
+// specialised kernel only.  Returns 1 if launched, 0 if the size has none (caller runs the separate kernels), <0 on error.
+template <typename OutT>
+static int launch_random_fused(mtfjsp_env* h, const Params& P, cudaStream_t s) {
+    if (h->force_generic || !h->fuse_policy) return 0;
+    constexpr int MD = MODE_STEP | MODE_OBS | MODE_POLICY;
+    const int J = h->L.J, M = h->L.M;
+    int rc;
+    if (J == 6 && M == 6) rc = launch_spec<Spec<6, 6, 8, 4>, MD, OutT>(h, P, s);
+    else if (J == 10 && M == 10) rc = launch_spec<Spec<10, 10, 16, 1>, MD, OutT>(h, P, s);
+    else if (J == 30 && M == 20) rc = launch_spec<Spec<30, 20, 32, 2>, MD, OutT>(h, P, s);
+    else return 0;
+    return rc == MTFJSP_OK ? 1 : rc;
 }
 
 // pre-step dispatch: returns 1 if a size-templated kernel was launched, 0 if the size has none, <0 on error
@@ -1673,6 +1791,7 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
         const char* fg = getenv("MTFJSP_FORCE_GENERIC");  // test hook: run the generic kernel on every size
         h->force_generic = fg && fg[0] == '1';
         h->host_chunks = getenv("MTFJSP_HOST_CHUNKS") ? atoi(getenv("MTFJSP_HOST_CHUNKS")) : 4;
+        h->fuse_policy = getenv("MTFJSP_FUSE_POLICY") ? atoi(getenv("MTFJSP_FUSE_POLICY")) : 1;
     }
     h->cfgw[0] = 0.4; h->cfgw[1] = 0.4; h->cfgw[2] = 0.2; h->divisor = 1.0; h->gamma = 0.99;
     size_t Bs = (size_t)B;
@@ -1909,6 +2028,17 @@ int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_
     if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_random_step before mtfjsp_reset");
     if (dtype != MTFJSP_F32 && dtype != MTFJSP_F64) return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
     CK(cudaSetDevice(h->device), "cudaSetDevice");
+    {
+        Params P = make_params(h);
+        P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
+        P.seed = seed; P.env_offset = env_offset; P.edge_id = h->edge_id; P.op_out = o; P.mach_out = mc;
+        P.mfea1 = mfea1; P.mmask = mach_mask;
+        int rf = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
+        if (rf) return rf;
+        rf = dtype == MTFJSP_F64 ? launch_random_fused<double>(h, P, (cudaStream_t)stream)
+                                 : launch_random_fused<float>(h, P, (cudaStream_t)stream);
+        if (rf != 0) return rf < 0 ? rf : MTFJSP_OK;
+    }
     int rc = launch_prestep<true>(h, seed, env_offset, mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin, o, mc, mfea1,
                                   mach_mask, dtype, (cudaStream_t)stream);
     if (rc < 0) return rc;

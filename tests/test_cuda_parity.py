@@ -21,10 +21,13 @@ ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
 eq = np.testing.assert_array_equal
 
 
-@pytest.fixture(params=["auto", "generic"])
+@pytest.fixture(params=["auto", "generic", "unfused"])
 def kernel_path(request, monkeypatch):
-    """'auto' = size-specialised kernel where one exists; 'generic' forces the one-warp-per-env kernel."""
+    """'auto' = size-specialised kernel where one exists (random_step = one launch: policy + candidate-machine
+    features + step + observation); 'unfused' = the same kernels with the pre-step kernel launched separately;
+    'generic' forces the one-warp-per-env kernel."""
     monkeypatch.setenv("MTFJSP_FORCE_GENERIC", "1" if request.param == "generic" else "0")
+    monkeypatch.setenv("MTFJSP_FUSE_POLICY", "0" if request.param == "unfused" else "1")
     return request.param
 
 
@@ -37,6 +40,8 @@ def _adapter():
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name", [os.path.basename(p) for p in sorted(glob.glob(os.path.join(GOLD, "replay_*.npz")))])
 def test_replay_matches_reference_dump(name, fused, kernel_path):
+    if kernel_path == "unfused":
+        pytest.skip("recorded actions: no random_step here, 'auto' covers it")
     ad = _adapter()
     check_replay(lambda B, J, M, E, ls: ad.NumpyEnvAdapter(B, J, M, E, left_shift=ls, fused=fused), os.path.join(GOLD, name))
 
@@ -109,7 +114,7 @@ def _ell_to_dense(adj_w, adj_src):
 ])
 def test_random_rollout_matches_oracle_every_step(cfg, kernel_path):
     B, J, M, E, ls, mm, scale, episodes = cfg
-    if kernel_path == "generic" and (J, M) not in ((6, 6), (10, 10), (30, 20)):
+    if kernel_path != "auto" and (J, M) not in ((6, 6), (10, 10), (30, 20)):
         pytest.skip("size has no specialised kernel: 'auto' already ran the generic one")
     N = J * M
     env, ora, d, w = _mk(B, J, M, E, seed=1000 + J * M, left_shift=ls, mask_mode=mm, scale=scale)
@@ -220,6 +225,8 @@ def test_host_step_equals_device_step(pinned, B, kernel_path):
     """mtfjsp_step_host with pinned (graph-replayed chunk pipeline; 1 chunk and 3 ragged chunks) and with pageable
     host buffers (in-order copies) must equal the device-pointer call bit for bit, including the all-invalid step
     after the episode has ended."""
+    if kernel_path == "unfused":
+        pytest.skip("no random_step here, 'auto' covers it")
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
     J, M, E = 6, 6, 2
     N = J * M
