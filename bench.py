@@ -300,32 +300,40 @@ def run_ours(args, wl):
         tm = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M, trainable=True)
         tc = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(128), 13), J, M, trainable=True)
         tro = rom.Rollout(env_t, tj.inference_twin("tf32"), tm.inference_twin("tf32"), greedy=False, seed=2 + rank)
-        up = ppo.MAPPOUpdate(tj, tm, tc, ppo.PPOConfig(k_epochs=1))
         wt = [w[:Bt]]
-        tms, cms, ams = [], [], []
-        for it in range(3):  # first iteration is warm-up (library initialisation)
-            barrier()
-            t0e, t1e, t2e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            t0e.record()
-            btc = ppo.collect(tro, wt)
-            t1e.record()
-            losses, _ = up.update(btc, N)
-            tro.job.refresh(); tro.mch.refresh()
-            t2e.record()
-            barrier()
-            a_ms = up.allreduce_ms()
-            if it > 0:
-                cms.append(sh.max_over_ranks(t0e.elapsed_time(t1e), dev)); tms.append(sh.max_over_ranks(t0e.elapsed_time(t2e), dev))
-                ams.append(a_ms)
-            del btc
-        tot = sum(tms) / len(tms)
+        runs = {}
+        for variant, enc_tf32 in (("tcgen05_tf32", True), ("library_fp32", False)):
+            up = ppo.MAPPOUpdate(tj, tm, tc, ppo.PPOConfig(k_epochs=1, encoder_tf32=enc_tf32))
+            tms, cms, ams = [], [], []
+            for it in range(3):  # first iteration is warm-up (library initialisation)
+                barrier()
+                t0e, t1e, t2e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                t0e.record()
+                btc = ppo.collect(tro, wt)
+                t1e.record()
+                losses, _ = up.update(btc, N)
+                tro.job.refresh(); tro.mch.refresh()
+                t2e.record()
+                barrier()
+                a_ms = up.allreduce_ms()
+                if it > 0:
+                    cms.append(sh.max_over_ranks(t0e.elapsed_time(t1e), dev)); tms.append(sh.max_over_ranks(t0e.elapsed_time(t2e), dev))
+                    ams.append(a_ms)
+                del btc
+            runs[variant] = (sum(tms) / len(tms), sum(cms) / len(cms), sum(ams) / len(ams), [float(x) for x in losses],
+                             up.allreduce_bytes // 3)
+        tot, col, arm, losses, arb = runs["tcgen05_tf32"]
         train = {"value": Bt * world * N / (tot * 1e-3), "unit": UNIT, "envs_per_gpu": Bt, "buffer_steps": N, "k_epochs": 1,
-                 "mini_bs": N, "collect_ms": sum(cms) / len(cms), "update_ms": tot - sum(cms) / len(cms),
-                 "allreduce_ms": sum(ams) / len(ams), "allreduce_share": (sum(ams) / len(ams)) / tot,
-                 "allreduce_bytes_per_update": up.allreduce_bytes // 3, "losses": [float(x) for x in losses],
-                 "what": "one buffer (1 episode) collected with the tcgen05 rollout twins + one batched PPO update "
-                         "(FP32 library GEMMs under autograd; aggregation, grouped BatchNorm and GAE kernels hand-written; "
-                         "NCCL gradient allreduce when n_gpus > 1)"}
+                 "mini_bs": N, "collect_ms": col, "update_ms": tot - col,
+                 "allreduce_ms": arm, "allreduce_share": arm / tot,
+                 "allreduce_bytes_per_update": arb, "losses": losses,
+                 "update_ms_library_fp32": runs["library_fp32"][0] - runs["library_fp32"][1],
+                 "value_library_fp32": Bt * world * N / (runs["library_fp32"][0] * 1e-3),
+                 "what": "one buffer (1 episode) collected with the tcgen05 rollout twins + one batched PPO update; the graph "
+                         "encoders' Linear layers run forward / input-gradient / weight-gradient on the hand-written tcgen05 "
+                         "TF32 kernels (PPOConfig.encoder_tf32), heads on library FP32 GEMMs; aggregation, grouped BatchNorm "
+                         "and GAE kernels hand-written; NCCL gradient allreduce when n_gpus > 1.  *_library_fp32 = the same "
+                         "update with every GEMM on the FP32 library path (the reference's arithmetic)"}
         del env_t, up, tro
         torch.cuda.empty_cache()
 

@@ -376,6 +376,170 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double inv_
     shift[c] = (float)((double)beta[c] - mean * sc);
 }
 
+
+// =====================================================================================================================
+// Weight gradient of the layer above, for the PPO update (ppo_algorithm.py:918-1003 backward passes):
+//     dW[128, K] = dY^T X        db[128] = column sums of dY          dY [rows,128], X [rows,K] row-major f32
+// The reduction runs over ROWS, so both operands enter the MMA transposed: A(m, r) = dY[r, m], B(n, r) = X[r, n], both
+// "K-major" with K = r.  Four consecutive r of one feature must sit in one 16-byte piece, while global memory has four
+// consecutive FEATURES of one r in a piece: every thread loads a 4 x 4 block (four rows, one feature quad; a warp
+// instruction reads one whole 512-byte row), transposes it by register naming and stores four 16-byte pieces.  The
+// 8-feature groups are 16 bytes further apart than the data needs (SBO = 2064), which makes those stores
+// bank-conflict-free.  One CTA per SM walks 64-row stages (ring of 3), accumulates ALL of them into one TMEM
+// accumulator and writes its partial [128, NP] once; a second small kernel adds the partials in CTA order, so the
+// result does not depend on scheduling.
+constexpr int WG_KS = 64, WG_NSTAGE = 3, WG_WARPS = 16;
+constexpr int WG_SBO = (WG_KS / 4) * 128 + 16;
+
+__device__ __forceinline__ void umma_tf32_desc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+
+template <int NP>
+__global__ void __launch_bounds__(WG_WARPS * 32, 1) wgrad_tf32_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+                                                                      long long rows, int K, float* __restrict__ parts,
+                                                                      float* __restrict__ dbparts, long long num_stages) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int A_BYTES = 16 * WG_SBO, B_BYTES = (NP / 8) * WG_SBO;
+    constexpr int TCOLS = NP < 32 ? 32 : NP;
+    constexpr uint32_t IDESC_W = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((TILE_M >> 4) << 24);
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + WG_NSTAGE * A_BYTES;
+    double* s_db = reinterpret_cast<double*>(sB + WG_NSTAGE * B_BYTES);          // [WG_WARPS][128]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_db + WG_WARPS * 128);         // sfree[NSTAGE], done
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + WG_NSTAGE + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int st = 0; st <= WG_NSTAGE; st++) mbar_init(smem_u32(s_bar + st), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t bar_free = smem_u32(s_bar), bar_done = smem_u32(s_bar + WG_NSTAGE);
+
+    // unit of this thread: A (dY): row quad `warp`, feature quad `lane`;  B (X): NP/4 feature quads x 16 row quads
+    constexpr int BQ = NP / 4;
+    const bool b_on = tid < BQ * 16;
+    const int b_fq = tid % BQ, b_rq = tid / BQ;
+    const bool b_col_ok = b_fq * 4 < K;
+
+    float4 va[4], vb[4];
+    auto load = [&](long long stage, float4* a, float4* b) {
+        const long long r0 = stage * WG_KS;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long ra = r0 + warp * 4 + j;
+            a[j] = ra < rows ? __ldg(reinterpret_cast<const float4*>(dY + ra * TILE_N + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const long long rb = r0 + b_rq * 4 + j;
+            b[j] = (b_on && b_col_ok && rb < rows) ? __ldg(reinterpret_cast<const float4*>(X + rb * K + b_fq * 4))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // transposed store of a 4 x 4 block: piece i = feature 4*fq + i, rows 4*rq .. 4*rq+3
+    auto store = [&](unsigned char* base, int fq, int rq, const float4* v) {
+        const int f0 = fq * 4;
+        unsigned char* p = base + (f0 >> 3) * WG_SBO + rq * 128 + (f0 & 7) * 16;
+        *reinterpret_cast<float4*>(p) = make_float4(to_tf32(v[0].x), to_tf32(v[1].x), to_tf32(v[2].x), to_tf32(v[3].x));
+        *reinterpret_cast<float4*>(p + 16) = make_float4(to_tf32(v[0].y), to_tf32(v[1].y), to_tf32(v[2].y), to_tf32(v[3].y));
+        *reinterpret_cast<float4*>(p + 32) = make_float4(to_tf32(v[0].z), to_tf32(v[1].z), to_tf32(v[2].z), to_tf32(v[3].z));
+        *reinterpret_cast<float4*>(p + 48) = make_float4(to_tf32(v[0].w), to_tf32(v[1].w), to_tf32(v[2].w), to_tf32(v[3].w));
+    };
+
+    double dbacc[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long my_n = (num_stages - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    if (my_n > 0) load(blockIdx.x, va, vb);
+    for (long long i = 0; i < my_n; i++) {
+        float4 na[4], nb[4];
+        const bool more = i + 1 < my_n;
+        if (more) load(blockIdx.x + (i + 1) * (long long)gridDim.x, na, nb);
+        const int slot = (int)(i % WG_NSTAGE);
+        if (i >= WG_NSTAGE) mbar_wait(bar_free + slot * 8, (uint32_t)((i / WG_NSTAGE - 1) & 1));  // the MMAs that read it are done
+        store(sA + slot * A_BYTES, lane, warp, va);
+        if (b_on) store(sB + slot * B_BYTES, b_fq, b_rq, vb);
+        dbacc[0] += (double)((va[0].x + va[1].x) + (va[2].x + va[3].x));
+        dbacc[1] += (double)((va[0].y + va[1].y) + (va[2].y + va[3].y));
+        dbacc[2] += (double)((va[0].z + va[1].z) + (va[2].z + va[3].z));
+        dbacc[3] += (double)((va[0].w + va[1].w) + (va[2].w + va[3].w));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t aA = smem_u32(sA + slot * A_BYTES), aB = smem_u32(sB + slot * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < WG_KS / 8; k++)
+                umma_tf32_desc(tmem_base, make_desc(aA + k * 256, 128, WG_SBO), make_desc(aB + k * 256, 128, WG_SBO), IDESC_W,
+                               (i > 0 || k > 0) ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_free + slot * 8)
+                         : "memory");
+            if (!more)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done) : "memory");
+        }
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { va[j] = na[j]; vb[j] = nb[j]; }
+        }
+    }
+    // bias gradient: warp partials in a fixed order
+#pragma unroll
+    for (int j = 0; j < 4; j++) s_db[warp * 128 + lane * 4 + j] = dbacc[j];
+    __syncthreads();
+    if (tid < 128 && dbparts) {
+        double t = 0.0;
+        for (int w = 0; w < WG_WARPS; w++) t += s_db[w * 128 + tid];
+        dbparts[(size_t)blockIdx.x * 128 + tid] = (float)t;
+    }
+    // accumulator -> this CTA's partial
+    if (warp < 4) {
+        float* out = parts + ((size_t)blockIdx.x * TILE_M + warp * 32 + lane) * NP;
+        if (my_n > 0) {
+            mbar_wait(bar_done, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < NP; c0 += 32) {
+                uint32_t r[32];
+                TMEM_LD32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32 && c0 + j < NP; j += 4)
+                    *reinterpret_cast<uint4*>(out + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+        } else {
+            for (int j = 0; j < NP; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+}
+
+// dW[m, k] = sum over CTAs (in order) of parts[c][m][k]; db likewise
+__global__ void wgrad_reduce_kernel(const float* __restrict__ parts, const float* __restrict__ dbparts, int nparts, int NP, int K,
+                                    float* __restrict__ dW, float* __restrict__ db) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < TILE_M * K) {
+        const int m = idx / K, k = idx % K;
+        float t = 0.f;
+        for (int c = 0; c < nparts; c++) t += parts[((size_t)c * TILE_M + m) * NP + k];
+        dW[idx] = t;
+    }
+    if (db && idx < TILE_M) {
+        float t = 0.f;
+        for (int c = 0; c < nparts; c++) t += dbparts[(size_t)c * 128 + idx];
+        db[idx] = t;
+    }
+}
+
 }  // namespace
 
 template <int KP>
@@ -418,6 +582,56 @@ int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, 1.0 / (double)rows, gamma, beta, eps, scale,
                                                                         shift, C);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+}  // extern "C"
+
+template <int NP>
+static int launch_wgrad(const float* dY, const float* X, int64_t rows, int K, float* dW, float* db, float* ws, int sms,
+                        cudaStream_t stream) {
+    const size_t smem = (size_t)WG_NSTAGE * (16 + NP / 8) * WG_SBO + (size_t)WG_WARPS * 128 * 8 + (WG_NSTAGE + 1) * 8 + 16;
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(wgrad_tf32_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MTFJSP_E_CUDA;
+        configured = true;
+    }
+    const long long stages = (rows + WG_KS - 1) / WG_KS;
+    const int grid = (int)(stages < sms ? stages : sms);
+    float* parts = ws;
+    float* dbparts = ws + (size_t)sms * TILE_M * NP;
+    wgrad_tf32_kernel<NP><<<grid, WG_WARPS * 32, smem, stream>>>(dY, X, rows, K, parts, dbparts, stages);
+    if (cudaGetLastError() != cudaSuccess) return MTFJSP_E_CUDA;
+    wgrad_reduce_kernel<<<(TILE_M * K + 255) / 256, 256, 0, stream>>>(parts, dbparts, grid, NP, K, dW, db);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+static int wgrad_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+static int wgrad_np(int K) { return K <= 16 ? 16 : K <= 32 ? 32 : K <= 64 ? 64 : 128; }
+
+extern "C" {
+
+int64_t mtfjsp_enc_wgrad_workspace_floats(int K) {
+    if (K < 4 || K > 128) return 0;
+    return (int64_t)wgrad_sms() * (TILE_M * wgrad_np(K) + 128);
+}
+
+int mtfjsp_enc_wgrad_tf32(const float* dY, const float* X, int64_t rows, int K, float* dW, float* db, float* workspace,
+                          void* stream) {
+    if (!dY || !X || !dW || !workspace || rows < 1 || K < 4 || K > 128 || (K % 4) != 0) return MTFJSP_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sms = wgrad_sms();
+    switch (wgrad_np(K)) {
+        case 16: return launch_wgrad<16>(dY, X, rows, K, dW, db, workspace, sms, s);
+        case 32: return launch_wgrad<32>(dY, X, rows, K, dW, db, workspace, sms, s);
+        case 64: return launch_wgrad<64>(dY, X, rows, K, dW, db, workspace, sms, s);
+        default: return launch_wgrad<128>(dY, X, rows, K, dW, db, workspace, sms, s);
+    }
 }
 
 }  // extern "C"

@@ -126,6 +126,55 @@ def linear_tf32(x, weight, bias, in_scale=None, in_shift=None, relu=False, stats
     return z
 
 
+_WGRAD_WS = {}
+
+
+def wgrad_tf32(gz, x, want_bias=True):
+    """Weight / bias gradient of Z = x @ W.T + b on the tcgen05 tensor cores: dW [128,K] = gz.T @ x (TF32 operands,
+    FP32 accumulate, partials of the 148 CTAs added in a fixed order), db [128] = column sums of gz."""
+    rows, K = x.shape
+    assert gz.shape == (rows, 128) and gz.dtype == torch.float32 and x.dtype == torch.float32
+    lib = _lib.lib()
+    key = (x.device.index, K)
+    if key not in _WGRAD_WS:
+        _WGRAD_WS[key] = torch.empty(int(lib.mtfjsp_enc_wgrad_workspace_floats(K)), dtype=torch.float32, device=x.device)
+    dW = torch.empty((128, K), dtype=torch.float32, device=x.device)
+    db = torch.empty(128, dtype=torch.float32, device=x.device) if want_bias else None
+    check(lib.mtfjsp_enc_wgrad_tf32(_ptr(gz.contiguous()), _ptr(x.contiguous()), rows, K, _ptr(dW), _optr(db),
+                                    _ptr(_WGRAD_WS[key]), _stream()), "mtfjsp_enc_wgrad_tf32")
+    return dW, db
+
+
+class _LinearTF32Fn(torch.autograd.Function):
+    """nn.Linear (128 outputs) of the PPO re-forward with all three GEMMs on the hand-written tcgen05 kernels:
+    forward and input gradient on linear_tf32_kernel (dX = gZ @ W is the same product with W.T as the weight),
+    weight / bias gradient on wgrad_tf32_kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return linear_tf32(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, weight = ctx.saved_tensors
+        gz = gz.contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = linear_tf32(gz, weight.t().contiguous(), None) if weight.shape[1] == 128 else gz @ weight
+        gw, gb = wgrad_tf32(gz, x, ctx.has_bias)
+        return gx, gw, gb
+
+
+def linear_train(x, weight, bias, tf32):
+    """F.linear, or its tcgen05 twin when `tf32` and the shape fits the kernels (128 outputs, K <= 128, K % 4 == 0)."""
+    if tf32 and x.is_cuda and weight.shape[0] == 128 and weight.shape[1] <= 128 and weight.shape[1] % 4 == 0 and x.dim() == 2:
+        return _LinearTF32Fn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
 def bn_finalize(stats, rows, gamma, beta, eps=1e-5):
     Cc = gamma.shape[0]
     scale = torch.empty(Cc, dtype=torch.float32, device=gamma.device)
@@ -312,10 +361,11 @@ class _GraphEncoder:
         w = self.w
         p = "encoder.feature_extract.mlps.%d." % l
         h = x
+        tf32 = getattr(self, "train_tf32", False)  # PPOConfig.encoder_tf32: the update's encoder GEMMs on tcgen05
         for i in (0, 1):
-            h = F.linear(h, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i])
+            h = linear_train(h, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i], tf32)
             h = _bn_train(h, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i], groups=groups, relu=True)
-        return F.linear(h, w[p + "linears.2.weight"], w[p + "linears.2.bias"])
+        return linear_train(h, w[p + "linears.2.weight"], w[p + "linears.2.bias"], tf32)
 
     def encode(self, task_fea, adj_w, adj_src, groups=1, adj_dst=None):
         """GraphCNN.forward (gcn_mlp.py:160-197): two rounds of aggregate -> MLP -> BN -> ReLU, then mean pooling.
@@ -418,6 +468,22 @@ class _Twin:
         return F.linear(z, w[prefix + "linears.2.weight"], w[prefix + "linears.2.bias"]).view(B, rows_per_env)
 
 
+def _head_train(self, prefix, per_row, env_terms, rows_per_env):
+    """Training-path twin of _Twin._head_tf32 (PPOConfig.encoder_tf32): the same decomposition of the first layer of a
+    3-layer tanh MLP over cat(per_row, env_term_0, env_term_1) -- per-env column blocks applied once per env instead of
+    once per row -- with the two [rows,128] x [128,128] products on the tcgen05 kernels under autograd (linear_train)."""
+    w, H = self.w, self.H
+    W0 = w[prefix + "linears.0.weight"]
+    z = linear_train(per_row, W0[:, :H].contiguous(), None, True)
+    bias = w[prefix + "linears.0.bias"]
+    for k, e in enumerate(env_terms):
+        bias = bias + F.linear(e, W0[:, (k + 1) * H:(k + 2) * H])
+    B = per_row.shape[0] // rows_per_env
+    z = torch.tanh(z.view(B, rows_per_env, H) + (bias.unsqueeze(1) if bias.dim() == 2 else bias)).view(-1, H)
+    z = torch.tanh(linear_train(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"], True))
+    return F.linear(z, w[prefix + "linears.2.weight"], w[prefix + "linears.2.bias"]).view(B, rows_per_env)
+
+
 def _check_precision(precision, hidden):
     if precision not in ("fp32", "tf32"):
         raise ValueError("precision must be 'fp32' or 'tf32'")
@@ -448,6 +514,10 @@ class JobActor(_GraphEncoder, _Twin):
             sc, sh = self._pending
             gmv = w["_input"].unsqueeze(0) if h_g_m_pooled is None else h_g_m_pooled
             s = self._head_tf32("o_policy.", cf, (pooled, gmv), self.J, sc, sh)
+        elif getattr(self, "train_tf32", False):
+            cf = self.candidate_features(nodes, candidate)
+            gmv = w["_input"].unsqueeze(0) if h_g_m_pooled is None else h_g_m_pooled
+            s = _head_train(self, "o_policy.", cf.reshape(-1, self.H), (pooled, gmv), self.J)
         else:
             cf = self.candidate_features(nodes, candidate)
             gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
@@ -482,6 +552,9 @@ class _MachineTrunk:
         if self.precision == "tf32":  # both node sets in one [2*rows,128] x [128,128] tensor-core launch
             Wt = self._derived("gat_Wt", lambda: self.w["gat_layer.W"].t())  # [out, in]: the layout the tensor-core layer takes
             t = linear_tf32(torch.cat((h1, h2), dim=0), Wt, None)
+            t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
+        elif getattr(self, "train_tf32", False):  # the PPO update: same product under autograd (linear_train)
+            t = linear_train(torch.cat((h1, h2), dim=0), W.t().contiguous(), None, True)
             t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
         else:
             t1, t2 = h1 @ W, h2 @ W
@@ -526,6 +599,8 @@ class MachineActor(_MachineTrunk, _Twin):
         B = nodes.shape[0]
         if self.precision == "tf32":
             s = self._head_tf32("m_policy.", nodes.reshape(-1, self.H), (pooled, h_pooled_o), self.M) * 10
+        elif getattr(self, "train_tf32", False):
+            s = _head_train(self, "m_policy.", nodes.reshape(-1, self.H), (pooled, h_pooled_o), self.M) * 10
         else:
             x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
             s = _mlp3_tanh(w, "m_policy.", x).squeeze(-1) * 10

@@ -49,6 +49,9 @@ class PPOConfig:
     use_grad_clip: bool = True
     clip_grad: float = 0.5
     matmul_tf32: bool = False   # library GEMMs of the update on TF32 tensor cores (the reference computes in FP32)
+    encoder_tf32: bool = False  # every [rows,128] x [128,<=128] product of the update (graph encoders, GAT projections,
+                                # policy heads; > 95 % of its FLOPs) forward + backward on the hand-written tcgen05 TF32
+                                # kernels instead of library FP32 GEMMs under autograd
 
 
 def _world():
@@ -89,6 +92,7 @@ class MAPPOUpdate:
         self.max_rows = max_rows
         self.cfg = cfg or PPOConfig()
         c = self.cfg
+        self.job.train_tf32 = self.mch.train_tf32 = self.critic.train_tf32 = bool(c.encoder_tf32)
         mk = lambda net: torch.optim.Adam(net.parameters(), lr=c.lr, eps=c.lr_eps)          # ppo_algorithm.py:57-79
         self.opt_job, self.opt_mch, self.opt_critic = mk(self.job), mk(self.mch), mk(self.critic)
         sch = lambda o: torch.optim.lr_scheduler.StepLR(o, step_size=c.decay_step_size, gamma=c.decay_ratio)

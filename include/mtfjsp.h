@@ -183,6 +183,15 @@ int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, c
  * stats[128:256] += column sums of Z^2 (FP64; may be NULL).  4 <= K <= 128, K % 4 == 0. */
 int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
                            const float* in_shift, int in_relu, float* Z, double* stats, void* stream);
+/* Weight / bias gradient of that layer for the PPO update's backward pass (ppo_algorithm.py:918-1003; torch autograd
+ * runs an FP32 library GEMM there): dW[128,K] = dY^T X, db[128] = column sums of dY (may be NULL), dY [rows,128] and
+ * X [rows,K] row-major f32, 4 <= K <= 128, K % 4 == 0.  tcgen05.mma kind::tf32 with the reduction over rows (both
+ * operands transposed while they are staged), one partial per CTA in `workspace`
+ * (mtfjsp_enc_wgrad_workspace_floats(K) floats), partials added in CTA order: run-to-run deterministic.
+ * The input gradient dX = dY W is mtfjsp_enc_linear_tf32 with W^T as the weight. */
+int mtfjsp_enc_wgrad_tf32(const float* dY, const float* X, int64_t rows, int K, float* dW, float* db, float* workspace,
+                          void* stream);
+int64_t mtfjsp_enc_wgrad_workspace_floats(int K);
 /* BatchNorm1d with batch statistics as a per-column affine: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
 int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,
                            float* scale, float* shift, int C, void* stream);

@@ -8,6 +8,7 @@ import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+ENC_TF32 = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
 J, M, E, H = 6, 6, 2, 128
 pkg = importlib.import_module("e2e-mappo-for-mt-fjsp_b200")
 envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
@@ -22,7 +23,7 @@ job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 1), J, M, hidden
 mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 2), M, hidden=H, trainable=True)
 crit = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 3), J, M, hidden=H, trainable=True)
 ro = rom.Rollout(env, job.inference_twin("tf32"), mch.inference_twin("tf32"), greedy=False, seed=3)
-up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=1))
+up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=1, encoder_tf32=ENC_TF32))
 bt = ppo.collect(ro, [pkg.instances.random_weights(0, B, 100)])
 up.update(bt, J * M)
 torch.cuda.synchronize()

@@ -134,3 +134,54 @@ def test_tcgen05_linear_matches_fp32_matmul(K, rows, affine):
     scale, shift = enc.bn_finalize(stats, rows, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"))
     bn = torch.nn.functional.batch_norm(z, None, None, None, None, True, 0.0, 1e-5)
     np.testing.assert_allclose((z * scale + shift).cpu().numpy(), bn.cpu().numpy(), rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,rows", [(128, 64), (128, 1000), (12, 333), (12, 64 * 200 + 17), (128, 64 * 148 * 3 + 5),
+                                    (64, 777), (32, 4096)])
+def test_tcgen05_weight_gradient_matches_fp64_product(K, rows):
+    """dW = dY^T X and db = column sums of dY on the tensor cores (TF32 operands, FP32 accumulate over the rows of a
+    CTA, fixed-order FP32 sum of the CTA partials) against the FP64 product of the TF32-rounded operands (tight:
+    FP32 accumulation error only) and of the unrounded ones (TF32 tolerance); two runs must agree bit for bit."""
+    torch = pytest.importorskip("torch")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(K * 1000 + rows)
+    x = torch.randn(rows, K, device="cuda", generator=g)
+    gz = torch.randn(rows, 128, device="cuda", generator=g)
+    dW, db = enc.wgrad_tf32(gz, x)
+    dW2, db2 = enc.wgrad_tf32(gz, x)
+    torch.cuda.synchronize()
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)
+
+    def tf32(t):
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    ref_t = tf32(gz).double().T @ tf32(x).double()
+    ref_f = gz.double().T @ x.double()
+    scale = float(rows) ** 0.5  # entries are sums of `rows` products of unit normals
+    np.testing.assert_allclose(dW.double().cpu().numpy() / scale, ref_t.cpu().numpy() / scale, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(dW.double().cpu().numpy() / scale, ref_f.cpu().numpy() / scale, rtol=0, atol=3e-3)
+    np.testing.assert_allclose(db.double().cpu().numpy() / scale, gz.double().sum(0).cpu().numpy() / scale, rtol=0, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [12, 128])
+def test_tcgen05_training_linear_gradients_match_autograd(K):
+    """linear_train(tf32=True): forward, input gradient and weight / bias gradients against torch autograd of F.linear."""
+    torch = pytest.importorskip("torch")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(K)
+    rows = 5000
+    x = torch.randn(rows, K, device="cuda", generator=g)
+    W = (torch.randn(128, K, device="cuda", generator=g) / K ** 0.5)
+    b = torch.randn(128, device="cuda", generator=g)
+    gy = torch.randn(rows, 128, device="cuda", generator=g)
+    outs = []
+    for tf in (False, True):
+        xi, Wi, bi = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        z = enc.linear_train(xi, Wi, bi, tf)
+        z.backward(gy)
+        outs.append((z.detach(), xi.grad, Wi.grad, bi.grad))
+    for a, r, name, sc in zip(outs[1], outs[0], ("z", "dx", "dW", "db"), (1.0, 1.0, rows ** 0.5, rows ** 0.5)):
+        np.testing.assert_allclose(a.cpu().numpy() / sc, r.cpu().numpy() / sc, rtol=0, atol=6e-3, err_msg=name)

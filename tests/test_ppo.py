@@ -275,3 +275,59 @@ def test_grouped_batchnorm_kernels_match_torch_autograd(shape, relu):
     close(y, ref, "y"); close(x.grad, x2.grad, "dx"); close(w.grad, w2.grad, "dgamma"); close(b.grad, b2.grad, "dbeta")
     with torch.no_grad():
         close(enc._bn_train(x, w, b, groups=G, relu=relu), ref, "y (no grad)")
+
+
+@pytest.mark.gpu
+def test_update_with_tcgen05_encoder_gemms_tracks_the_fp32_update():
+    """PPOConfig.encoder_tf32: the graph encoders' Linear layers (forward, input gradient, weight gradient) on the
+    hand-written tcgen05 kernels.  Same buffer, same initial weights, one epoch of two minibatches: the losses of the
+    first minibatch agree to TF32 tolerance, and the accumulated gradients of the encoder weights point the same way
+    (cosine > 0.99 -- 10-bit-mantissa operands through 6 GEMMs and 8 batch norms, then backwards)."""
+    dev = torch.device("cuda", 0)
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
+    rom = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
+    B, J, M, E, H = 256, 6, 6, 2, 128
+    N = J * M
+    d = ins.synthetic_instances(0, B, J, M, E, 5)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+
+    def nets():
+        return (enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 1), J, M, hidden=H, trainable=True),
+                enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 2), M, hidden=H, trainable=True),
+                enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 3), J, M, hidden=H, trainable=True))
+
+    job, mch, crit = nets()
+    ro = rom.Rollout(env, job, mch, greedy=False, seed=9)
+    bt = ppo.collect(ro, [ins.random_weights(0, B, 100)])
+    res = {}
+    for tf in (False, True):
+        j, m, c = nets()
+        up = ppo.MAPPOUpdate(j, m, c, ppo.PPOConfig(k_epochs=1, encoder_tf32=tf))
+        grads = {}
+        step_j, step_c = up.opt_job.step, up.opt_critic.step
+
+        def spy_j(*a, _g=grads, _j=j, **k):
+            _g.setdefault("job", [p.grad.detach().clone() for p in _j.parameters() if p.grad is not None])
+            return step_j(*a, **k)
+
+        def spy_c(*a, _g=grads, _c=c, **k):
+            _g.setdefault("critic", [p.grad.detach().clone() for p in _c.parameters() if p.grad is not None])
+            return step_c(*a, **k)
+
+        up.opt_job.step, up.opt_critic.step = spy_j, spy_c
+        mean, _ = up.update(bt, N // 2, orders=[list(range(N))])
+        res[tf] = (mean, grads, [p.detach().clone() for p in j.parameters()])
+    m0, g0, p0 = res[False]
+    m1, g1, p1 = res[True]
+    assert bool(torch.isfinite(m1).all())
+    np.testing.assert_allclose(m1.cpu().numpy(), m0.cpu().numpy(), rtol=5e-2, atol=5e-3)
+    for net in ("job", "critic"):
+        a = torch.cat([t.reshape(-1) for t in g0[net]]).double()
+        b = torch.cat([t.reshape(-1) for t in g1[net]]).double()
+        cos = float((a @ b) / (a.norm() * b.norm()))
+        assert cos > 0.99, (net, cos)
+    moved = max(float((x - y).abs().max()) for x, y in zip(p1, [p.detach() for p in nets()[0].parameters()]))
+    assert moved > 1e-4
