@@ -87,6 +87,8 @@ SIGNATURES = {
     "mtfjsp_adv_normalize": ([_VP, _VP, C.c_double, _I, C.c_int64, _VP], _I),
     "mtfjsp_launch_count": ([_VP], C.c_int64),
     "mtfjsp_bytes_per_step": ([_VP, _I], C.c_int64),
+    "mtfjsp_bytes_per_random_step": ([_VP, _I], C.c_int64),
+    "mtfjsp_random_step_is_fused": ([_VP], _I),
     "mtfjsp_last_error": ([], C.c_char_p),
     "mtfjsp_version": ([], C.c_char_p),
 }

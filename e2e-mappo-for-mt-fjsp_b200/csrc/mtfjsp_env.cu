@@ -2209,4 +2209,20 @@ int64_t mtfjsp_bytes_per_step(const mtfjsp_env* h, int dtype) {
     return 8 + 2 * b_state + b_out;
 }
 
+// SURVEY.md 8(d) accounting of the one-launch random-rollout step: the fused step + the pre-step's traffic --
+// reads job mask J, candidates 4J, t / p rows 16M, edge ids M; writes the action 8 (instead of reading it), the
+// candidate-machine features 6*fe*M and the machine mask M.
+int64_t mtfjsp_bytes_per_random_step(const mtfjsp_env* h, int dtype) {
+    if (!h) return 0;
+    const int64_t M = h->L.M, J = h->L.J;
+    const int64_t fe = dtype == MTFJSP_F64 ? 8 : 4;
+    return mtfjsp_bytes_per_step(h, dtype) + 5 * J + 17 * M + 6 * fe * M + M;
+}
+
+int mtfjsp_random_step_is_fused(const mtfjsp_env* h) {
+    if (!h || h->force_generic || !h->fuse_policy) return 0;
+    const int J = h->L.J, M = h->L.M;
+    return (J == 6 && M == 6) || (J == 10 && M == 10) || (J == 30 && M == 20);
+}
+
 }  // extern "C"

@@ -208,3 +208,11 @@ class BatchedMTFJSPEnv:
 
     def bytes_per_step(self):
         return int(self._lib.mtfjsp_bytes_per_step(self._h, self._dt))
+
+    def bytes_per_random_step(self):
+        return int(self._lib.mtfjsp_bytes_per_random_step(self._h, self._dt))
+
+    @property
+    def random_step_is_fused(self):
+        """True if random_step is one launch (policy + candidate-machine features + step + observation)."""
+        return bool(self._lib.mtfjsp_random_step_is_fused(self._h))

@@ -208,6 +208,11 @@ int mtfjsp_adv_normalize(float* adv, const double* stats, double count, int T, i
 int64_t mtfjsp_launch_count(const mtfjsp_env* h);
 /* Algorithmic bytes per env-step of the fused step+obs kernel for this handle's sizes. */
 int64_t mtfjsp_bytes_per_step(const mtfjsp_env* h, int dtype);
+/* Same for the one-launch random-rollout step (mtfjsp_random_step on a size with a specialised kernel): the step's
+ * bytes plus the policy / candidate-machine-feature traffic (job mask, candidates, t / p rows, edge ids in; action,
+ * [M,6] features, machine mask out).  mtfjsp_random_step_is_fused: 1 if mtfjsp_random_step is that single launch. */
+int64_t mtfjsp_bytes_per_random_step(const mtfjsp_env* h, int dtype);
+int mtfjsp_random_step_is_fused(const mtfjsp_env* h);
 const char* mtfjsp_last_error(void);
 const char* mtfjsp_version(void);
 
