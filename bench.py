@@ -159,6 +159,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
     sh = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.sharding")
@@ -316,7 +317,8 @@ def run_ours(args, wl):
         tj = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(128), 11), J, M, trainable=True)
         tm = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M, trainable=True)
         tc = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(128), 13), J, M, trainable=True)
-        tro = rom.Rollout(env_t, tj.inference_twin("tf32"), tm.inference_twin("tf32"), greedy=False, seed=2 + rank)
+        tro = rom.Rollout(env_t, tj.inference_twin("tf32"), tm.inference_twin("tf32"), greedy=False, use_cuda_graph=True,
+                          seed=2 + rank)
         wt = [w[:Bt]]
         runs = {}
         for variant, enc_tf32 in (("tcgen05_tf32", True), ("library_fp32", False)):

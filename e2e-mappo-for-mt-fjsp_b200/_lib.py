@@ -80,6 +80,10 @@ SIGNATURES = {
     "mtfjsp_enc_aggregate_bwd": ([_VP, _VP, _VP, _VP, _VP, C.c_int64, _I, _I, _VP], _I),
     "mtfjsp_enc_graph_mean": ([_VP, _VP, C.c_int64, _I, _I, _VP, _VP, _I, _VP], _I),
     "mtfjsp_enc_linear_tf32": ([_VP, C.c_int64, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
+    "mtfjsp_enc_mach_proj": ([_VP, _VP, _VP, _VP, _VP, C.c_int64, _VP], _I),
+    "mtfjsp_enc_gat_attend": ([_VP, _VP, _VP, _VP, C.c_int64, _I, _VP], _I),
+    "mtfjsp_enc_bias_tanh": ([_VP, _VP, C.c_int64, _I, C.c_int64, _VP], _I),
+    "mtfjsp_enc_tanh_dot": ([_VP, _VP, _VP, _VP, C.c_int64, _VP], _I),
     "mtfjsp_enc_wgrad_tf32": ([_VP, _VP, C.c_int64, _I, _VP, _VP, _VP, _VP], _I),
     "mtfjsp_enc_wgrad_workspace_floats": ([_I], C.c_int64),
     "mtfjsp_enc_bn_finalize": ([_VP, C.c_int64, _VP, _VP, C.c_float, _VP, _VP, _I, _VP], _I),

@@ -145,6 +145,39 @@ def wgrad_tf32(gz, x, want_bias=True):
     return dW, db
 
 
+def mach_proj(fea1, fea2, W1, W2):
+    """[fea1 @ W1.T ; fea2 @ W2.T] as one [2R,128] buffer (mtfjsp_enc_mach_proj); fea1 [R,6], fea2 [R,8] f32."""
+    R = fea1.shape[0]
+    out = torch.empty((2 * R, 128), dtype=torch.float32, device=fea1.device)
+    check(_lib.lib().mtfjsp_enc_mach_proj(_ptr(fea1), _ptr(fea2), _ptr(W1), _ptr(W2), _ptr(out), R, _stream()),
+          "mtfjsp_enc_mach_proj")
+    return out
+
+
+def gat_attend(t, a_src, a_dst, mode, out=None):
+    """Attention + combination (+ELU / node-set mean) of the closed-form 2-node GAT layer, see include/mtfjsp.h."""
+    R = t.shape[0] // 2
+    if out is None:
+        out = torch.empty((R if mode == 2 else 2 * R, 128), dtype=torch.float32, device=t.device)
+    check(_lib.lib().mtfjsp_enc_gat_attend(_ptr(t), _ptr(a_src), _ptr(a_dst), _ptr(out), R, mode, _stream()),
+          "mtfjsp_enc_gat_attend")
+    return out
+
+
+def bias_tanh_(z, bias, rows_per_env):
+    """z[r] = tanh(z[r] + bias[r // rows_per_env]) in place; bias [B,128] or [1,128]."""
+    check(_lib.lib().mtfjsp_enc_bias_tanh(_ptr(z), _ptr(bias), z.shape[0], rows_per_env, bias.shape[0], _stream()),
+          "mtfjsp_enc_bias_tanh")
+    return z
+
+
+def tanh_dot(z, w, b):
+    """tanh(z) @ w + b for z [rows,128], w [128], b [1] -> [rows]."""
+    out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+    check(_lib.lib().mtfjsp_enc_tanh_dot(_ptr(z), _ptr(w), _optr(b), _ptr(out), z.shape[0], _stream()), "mtfjsp_enc_tanh_dot")
+    return out
+
+
 class _LinearTF32Fn(torch.autograd.Function):
     """nn.Linear (128 outputs) of the PPO re-forward with all three GEMMs on the hand-written tcgen05 kernels:
     forward and input gradient on linear_tf32_kernel (dX = gZ @ W is the same product with W.T as the weight),
@@ -347,6 +380,13 @@ class _Params:
         return {k: t.detach().clone() for k, t in self.p.items()}
 
 
+def _mlp3_tanh_tf32(w, prefix, x):
+    """_mlp3_tanh with the two 128 -> 128 layers on the tcgen05 kernel (rollout path, value heads on pooled [B,128])."""
+    h = torch.tanh(linear_tf32(x.contiguous(), w[prefix + "linears.0.weight"], w[prefix + "linears.0.bias"]))
+    h = torch.tanh(linear_tf32(h, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"]))
+    return F.linear(h, w[prefix + "linears.2.weight"], w[prefix + "linears.2.bias"])
+
+
 def _mlp3_tanh(w, prefix, x):
     """MLPActor / MLPCritic with three linears and tanh between them (model/gcn_mlp.py:258-320)."""
     h = torch.tanh(F.linear(x, w[prefix + "linears.0.weight"], w[prefix + "linears.0.bias"]))
@@ -461,11 +501,12 @@ class _Twin:
         bias = w[prefix + "linears.0.bias"]
         for k, e in enumerate(env_terms):
             Wk = self._derived(prefix + "W0%d" % (k + 1), lambda k=k: W0[:, (k + 1) * H:(k + 2) * H])
-            bias = bias + F.linear(e, Wk)
+            bias = bias + linear_tf32(e.contiguous(), Wk, None)
         B = per_row.shape[0] // rows_per_env
-        z = torch.tanh(z.view(B, rows_per_env, H) + (bias.unsqueeze(1) if bias.dim() == 2 else bias)).view(-1, H)
-        z = torch.tanh(linear_tf32(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"]))
-        return F.linear(z, w[prefix + "linears.2.weight"], w[prefix + "linears.2.bias"]).view(B, rows_per_env)
+        bias_tanh_(z, (bias if bias.dim() == 2 else bias.unsqueeze(0)).contiguous(), rows_per_env)
+        z = linear_tf32(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"])
+        w2 = self._derived(prefix + "w2", lambda: w[prefix + "linears.2.weight"].reshape(-1))
+        return tanh_dot(z, w2, w[prefix + "linears.2.bias"]).view(B, rows_per_env)
 
 
 def _head_train(self, prefix, per_row, env_terms, rows_per_env):
@@ -525,7 +566,7 @@ class JobActor(_GraphEncoder, _Twin):
             s = _mlp3_tanh(w, "o_policy.", x).squeeze(-1)
         s = s.masked_fill(mask_operation.bool(), float("-inf"))                          # actor_critic.py:266-268
         prob = F.softmax(s, dim=-1)
-        job_v = _mlp3_tanh(w, "job_critic.", pooled)
+        job_v = (_mlp3_tanh_tf32 if self.precision == "tf32" else _mlp3_tanh)(w, "job_critic.", pooled)
         return prob, pooled, job_v
 
     def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None):
@@ -549,11 +590,7 @@ class _MachineTrunk:
         """GATLayer.forward (gat.py:82-159): node 1 attends to {1, 2}, node 2 to itself."""
         W, a = self.w["gat_layer.W"], self.w["gat_layer.a"]
         H = self.H
-        if self.precision == "tf32":  # both node sets in one [2*rows,128] x [128,128] tensor-core launch
-            Wt = self._derived("gat_Wt", lambda: self.w["gat_layer.W"].t())  # [out, in]: the layout the tensor-core layer takes
-            t = linear_tf32(torch.cat((h1, h2), dim=0), Wt, None)
-            t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
-        elif getattr(self, "train_tf32", False):  # the PPO update: same product under autograd (linear_train)
+        if getattr(self, "train_tf32", False):  # the PPO update: same product under autograd (linear_train)
             t = linear_train(torch.cat((h1, h2), dim=0), W.t().contiguous(), None, True)
             t1, t2 = t[: h1.shape[0]], t[h1.shape[0]:]
         else:
@@ -568,6 +605,8 @@ class _MachineTrunk:
         """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] -> (nodes [B,M,H], pooled [B,H])."""
         w = self.w
         B = machine_fea_1.shape[0]
+        if self.precision == "tf32":
+            return self._trunk_tf32(machine_fea_1, machine_fea_2, groups)
         h1 = F.linear(machine_fea_1.to(torch.float32), w["m_fea_1_fcl.weight"]).reshape(B * self.M, self.H)
         h2 = F.linear(machine_fea_2.to(torch.float32), w["m_fea_2_fcl.weight"]).reshape(B * self.M, self.H)
         h1, h2 = self._gat(h1, h2)
@@ -575,6 +614,25 @@ class _MachineTrunk:
         h1, h2 = self._gat(F.elu(h1), F.elu(h2))
         hm = torch.stack((h1, h2), dim=1).mean(dim=-2)                                   # actor_critic.py:420
         nodes = _bn_train(hm, w["bn.weight"], w["bn.bias"], groups=groups).reshape(B, self.M, self.H)   # actor_critic.py:434
+        return nodes, nodes.mean(dim=1)
+
+    def _trunk_tf32(self, machine_fea_1, machine_fea_2, groups):
+        """Rollout path: input projections written as one [2R,128] buffer, then per GAT layer ONE tensor-core
+        projection of both node sets and ONE kernel for attention + combination + ELU (the last one emits the
+        node-set mean); every [rows,128] tensor is written once and read once."""
+        w, H = self.w, self.H
+        B = machine_fea_1.shape[0]
+        R = B * self.M
+        f1 = machine_fea_1.to(torch.float32).reshape(R, 6).contiguous()
+        f2 = machine_fea_2.to(torch.float32).reshape(R, 8).contiguous()
+        buf = mach_proj(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"])
+        Wt = self._derived("gat_Wt", lambda: self.w["gat_layer.W"].t())
+        a_src = self._derived("gat_a_src", lambda: self.w["gat_layer.a"][0, :H, 0])
+        a_dst = self._derived("gat_a_dst", lambda: self.w["gat_layer.a"][0, H:, 0])
+        for layer in range(3):
+            t = linear_tf32(buf, Wt, None)
+            buf = gat_attend(t, a_src, a_dst, 1, out=buf) if layer < 2 else gat_attend(t, a_src, a_dst, 2)
+        nodes = _bn_train(buf, w["bn.weight"], w["bn.bias"], groups=groups).reshape(B, self.M, H)
         return nodes, nodes.mean(dim=1)
 
     def parameters(self):
@@ -605,7 +663,7 @@ class MachineActor(_MachineTrunk, _Twin):
             x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
             s = _mlp3_tanh(w, "m_policy.", x).squeeze(-1) * 10
         s = s.masked_fill(machine_mask.reshape(B, self.M).bool(), float("-inf"))
-        return F.softmax(s, dim=-1), _mlp3_tanh(w, "machine_critic.", pooled)
+        return F.softmax(s, dim=-1), (_mlp3_tanh_tf32 if self.precision == "tf32" else _mlp3_tanh)(w, "machine_critic.", pooled)
 
     def forward(self, machine_fea_1, machine_fea_2, h_pooled_o, machine_mask, groups=1):
         """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] f32, h_pooled_o [B,H], machine_mask [B,M] (1 = infeasible)

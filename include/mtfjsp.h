@@ -177,6 +177,21 @@ int mtfjsp_enc_bn_bwd(const float* x, const float* gy, const float* w, const flo
  * (gcn_mlp.py:154-157) folded into its consumer.  in_scale / in_shift [C] f32 or both NULL. */
 int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, const float* in_scale,
                           const float* in_shift, int in_relu, void* stream);
+/* Rollout-path fusions of the machine actor and the policy heads (hidden = 128, every pointer 16-byte aligned):
+ * mach_proj   replaces m_fea_1_fcl / m_fea_2_fcl (actor_critic.py:381-392) + the concatenation: fea1 [R,6], fea2 [R,8],
+ *             W1 [128,6], W2 [128,8] -> out [2R,128] = [fea1 W1^T ; fea2 W2^T];
+ * gat_attend  replaces everything of GATLayer.forward after the projection (model/gat.py:82-159, closed form on the
+ *             2-node graph) and the ELU / node-set mean around it (actor_critic.py:400-420): t [2R,128] = [t1; t2] ->
+ *             mode 0: [h1'; h2'], mode 1: [elu(h1'); elu(h2')], mode 2: out [R,128] = (h1' + h2') / 2;
+ * bias_tanh   z[r] = tanh(z[r] + bias[r / rows_per_env]) in place (first layer of MLPActor, gcn_mlp.py:305-320, with the
+ *             per-env part of its input applied as a bias), bias [bias_rows,128], bias_rows = rows / rows_per_env or 1;
+ * tanh_dot    out[r] = tanh(z[r]) . w + b (second tanh and the Linear(128,1) of the same MLP). */
+int mtfjsp_enc_mach_proj(const float* fea1, const float* fea2, const float* W1, const float* W2, float* out, int64_t R,
+                         void* stream);
+int mtfjsp_enc_gat_attend(const float* t, const float* a_src, const float* a_dst, float* out, int64_t R, int mode,
+                          void* stream);
+int mtfjsp_enc_bias_tanh(float* z, const float* bias, int64_t rows, int rows_per_env, int64_t bias_rows, void* stream);
+int mtfjsp_enc_tanh_dot(const float* z, const float* w, const float* b, float* out, int64_t rows, void* stream);
 /* replaces: one Linear (+ the BatchNorm statistics pass, + the previous BatchNorm/ReLU apply pass) of
  * gcn_mlp.py:238-249 on the tensor cores (tcgen05.mma kind::tf32, FP32 accumulate in TMEM):
  * Z[rows,128] = act(X[rows,K]*in_scale+in_shift) @ W[128,K]^T + bias; stats[0:128] += column sums of Z,

@@ -185,3 +185,34 @@ def test_tcgen05_training_linear_gradients_match_autograd(K):
         outs.append((z.detach(), xi.grad, Wi.grad, bi.grad))
     for a, r, name, sc in zip(outs[1], outs[0], ("z", "dx", "dW", "db"), (1.0, 1.0, rows ** 0.5, rows ** 0.5)):
         np.testing.assert_allclose(a.cpu().numpy() / sc, r.cpu().numpy() / sc, rtol=0, atol=6e-3, err_msg=name)
+
+
+@pytest.mark.gpu
+def test_machine_trunk_and_head_fusion_kernels_match_torch():
+    """mach_proj / gat_attend / bias_tanh / tanh_dot (rollout-path fusions) against the torch expressions they replace
+    (actor_critic.py:381-420, model/gat.py:82-159, gcn_mlp.py:305-320), FP32 tolerance."""
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    close = lambda a, b, tol=2e-5: np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=tol, atol=tol)
+    R = 1003
+    f1, f2, W1, W2 = rn(R, 6), rn(R, 8), rn(128, 6), rn(128, 8)
+    close(enc.mach_proj(f1, f2, W1, W2), torch.cat((F.linear(f1, W1), F.linear(f2, W2)), 0))
+    t, a_src, a_dst = rn(2 * R, 128), rn(128) * 0.1, rn(128) * 0.1
+    t1, t2 = t[:R], t[R:]
+    e11 = F.leaky_relu(t1 @ a_src + t1 @ a_dst, 0.2)
+    e12 = F.leaky_relu(t1 @ a_src + t2 @ a_dst, 0.2)
+    att = torch.softmax(torch.stack((e11, e12), -1), -1)
+    h1, h2 = att[:, 0:1] * t1 + att[:, 1:2] * t2, t2
+    close(enc.gat_attend(t, a_src, a_dst, 0), torch.cat((h1, h2), 0), 1e-4)
+    close(enc.gat_attend(t, a_src, a_dst, 1), torch.cat((F.elu(h1), F.elu(h2)), 0), 1e-4)
+    close(enc.gat_attend(t, a_src, a_dst, 2), torch.stack((h1, h2), 1).mean(1), 1e-4)
+    B, r = 167, 6
+    z, bias = rn(B * r, 128), rn(B, 128)
+    ref = torch.tanh(z.view(B, r, 128) + bias.unsqueeze(1)).view(-1, 128)
+    close(enc.bias_tanh_(z.clone(), bias, r), ref)
+    close(enc.bias_tanh_(z.clone(), bias[:1].contiguous(), r), torch.tanh(z + bias[:1]))
+    w2, b2 = rn(128) * 0.1, rn(1)
+    close(enc.tanh_dot(z, w2, b2), torch.tanh(z) @ w2 + b2, 1e-4)
