@@ -16,6 +16,7 @@
 // coalesced rows while accumulating the column statistics.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/mtfjsp.h"
 
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
                                                                          const float* __restrict__ in_scale,
                                                                          const float* __restrict__ in_shift, int in_relu,
                                                                          float* __restrict__ Z, double* __restrict__ stats,
-                                                                         long long num_tiles) {
+                                                                         long long num_tiles, int raw_a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int KS = KP > 64 ? 64 : KP, SPT = KP / KS;  // stage width, stages per tile
     constexpr size_t WBYTES = (size_t)TILE_N * KP * 4, SBYTES = (size_t)TILE_M * KS * 4;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
             float* sA = reinterpret_cast<float*>(sRing + slot * SBYTES);
             asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");  // stage g has landed (this thread's pieces)
             if (affine) tile_transform<KS, true>(sA, tile * TILE_M, rows, K, h * KS, s_scale, s_shift, in_relu != 0, pw, lane);
-            else tile_transform<KS, false>(sA, tile * TILE_M, rows, K, h * KS, nullptr, nullptr, false, pw, lane);
+            else if (!raw_a) tile_transform<KS, false>(sA, tile * TILE_M, rows, K, h * KS, nullptr, nullptr, false, pw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
             // refill the slot stage g-1 used: its MMAs ran while this stage was being transformed
             if (g >= 1 && g + NSTAGE - 1 < nst)
@@ -558,8 +559,14 @@ static int launch_linear(const float* X, int64_t rows, int K, const float* W, co
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (rows + TILE_M - 1) / TILE_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
+    // MTFJSP_GEMM_RAW_A=1 (opt-in): without a prologue the A operand stays as the FP32 bits cp.async landed -- kind::tf32
+    // reads the top 19 bits (truncation) -- and the in-place rounding pass in front of every MMA is skipped: 563 -> 476 us
+    // per 2.36 M-row K = 128 layer (65 -> 77 % of the measured HBM peak).  Not the default: truncation is biased towards
+    // zero, and the PPO update's critic gradient moved visibly away from the FP32 one (cosine 0.982 against > 0.99 with
+    // round-to-nearest operands, tests/test_ppo.py); profiles/README.md.
+    static const int raw_a = getenv("MTFJSP_GEMM_RAW_A") ? atoi(getenv("MTFJSP_GEMM_RAW_A")) : 0;
     linear_tf32_kernel<KP><<<grid, GEMM_WARPS * 32, smem, stream>>>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats,
-                                                                   tiles);
+                                                                   tiles, raw_a);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 
