@@ -56,6 +56,7 @@ SIGNATURES = {
     "mtfjsp_create": ([C.POINTER(_VP), _I, _I, _I, _I, _I, _I], _I),
     "mtfjsp_destroy": ([_VP], _I),
     "mtfjsp_set_params": ([_VP, _D, _D, _D, _D, _D], _I),
+    "mtfjsp_set_obs_incremental": ([_VP, _I], _I),
     "mtfjsp_load": ([_VP, _VP, _VP, _VP, _VP, _I, _VP], _I),
     "mtfjsp_scaler_init": ([_VP, _VP], _I),
     "mtfjsp_scaler_reset": ([_VP, _VP], _I),

@@ -95,6 +95,7 @@ struct Params {
     uint8_t* jmask;
     int32_t* cand;
     int mask_mode;
+    int obs_inc;  // fused step+obs only: the output buffers hold the previous observation, rewrite just the rows that changed
     // always-written internal mask / candidate buffers (policy kernel, host step)
     uint8_t* jm_fin;
     uint8_t* jm_esa;
@@ -639,6 +640,11 @@ struct Spec {
     static constexpr int ENV_BYTES = (G_ == 8) ? (RAW + ((64 - RAW % 128) + 128) % 128) : RAW;
     static constexpr int ITER = (N + G - 1) / G;
     static constexpr unsigned GMASK = (G_ == 32) ? 0xffffffffu : ((1u << G_) - 1u);
+    // blocks one SM holds by shared memory (228 KB, 1 KB reserved per block) and by threads: handed to ptxas through
+    // __launch_bounds__ so that registers never become the tighter limit
+    static constexpr int SMEM_BLOCK = WARPS_ * EPW * ENV_BYTES;
+    static constexpr int MINB_S = 233472 / (SMEM_BLOCK + 1024), MINB_T = 2048 / (WARPS_ * 32);
+    static constexpr int MINB = MINB_S < MINB_T ? (MINB_S < 32 ? MINB_S : 32) : (MINB_T < 32 ? MINB_T : 32);
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -717,7 +723,7 @@ __device__ __forceinline__ int kth_set_bit(unsigned bits, int k, int maxk) {
 }
 
 template <class S, int MODE, typename OutT>
-__global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __grid_constant__ Params P) {
     constexpr int J = S::J, M = S::M, N = S::N, G = S::G, EPW = S::EPW, ITER = S::ITER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -877,9 +883,14 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
 
     bool done = false;
     double idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;
+    // for the incremental observation: the op that now follows the stepped op on its machine, the machine's last op,
+    // and the one-step transients (removed job arc, coincident arc) of the PREVIOUS step, whose rows revert now
+    int o_next = -1, o_tail = -1, rem_prev = -1, fresh_prev = -1;
 
     if (MODE & MODE_STEP) {
         const int nsched0 = s_misc[2];
+        rem_prev = s_misc[0];
+        fresh_prev = s_misc[1];
         const bool first = apos == 0;
         const int aprev = first ? ac : ac - 1;
         valid = valid && nsched0 < N && (s_mach[ac] < 0) && (first || s_mach[aprev] >= 0) && !(d < 0);
@@ -937,6 +948,8 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
             }
             if (prev >= 0 && prev == ac - 1 && !first) fresh = ac;
         }
+        o_next = next;
+        o_tail = (where == len || lastop < 0) ? ac : lastop;
         // estimator chain of the job's remaining ops (SS:1964-1995): lane c ends up with op (ja, c)
         double my_st = 0.0, my_ft = 0.0;
         {
@@ -1162,69 +1175,91 @@ __global__ void __launch_bounds__(S::WARPS * 32) env_kernel_s(const __grid_const
         const int rem_head = s_misc[0], fresh = s_misc[1];
         OutT* tf = reinterpret_cast<OutT*>(P.tfea);
         const OutT w0 = (OutT)s_w[0], w1 = (OutT)s_w[1], w2 = (OutT)s_w[2];
-#pragma unroll
-        for (int it = 0; it < ITER; it++) {
-            const int v = gl + it * G;
-            if (v < N) {
-                const int mv = s_mach[v];
-                const bool sch = mv >= 0, vfirst = (v % M) == 0;
-                const int rp = sch ? (int)s_rpred[v] : -1;
-                const bool has_job = !vfirst && v != rem_head;
-                const bool co = has_job && rp == v - 1;
-                const bool has_m = rp >= 0 && !co;
-                if (sch && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
-                const double stv = s_st[v], ftv = s_ft[v], durv = s_dur[v];
-                if (tf && active) {  // SS:2246-2277
-                    const int indeg = (vfirst ? 1 : 0) + (has_job ? 1 : 0) + (has_m ? 1 : 0);
-                    OutT* row = tf + ((size_t)b * N + v) * 12;
-                    if constexpr (sizeof(OutT) == 4) {
-                        float4* r4 = reinterpret_cast<float4*>(row);
-                        r4[0] = make_float4((float)stv, (float)ftv, (float)ept[it], sch ? 1.f : 0.f);
-                        r4[1] = make_float4((float)indeg, (float)(mv + 1), (float)durv, sch ? (float)s_psel[v] : 0.f);
-                        r4[2] = make_float4((float)(v / M + 1), w0, w1, w2);
-                    } else {
-                        double2* r2 = reinterpret_cast<double2*>(row);
-                        r2[0] = make_double2(stv, ftv);
-                        r2[1] = make_double2(ept[it], sch ? 1.0 : 0.0);
-                        r2[2] = make_double2((double)indeg, (double)(mv + 1));
-                        r2[3] = make_double2(durv, sch ? s_psel[v] : 0.0);
-                        r2[4] = make_double2((double)(v / M + 1), w0);
-                        r2[5] = make_double2(w1, w2);
-                    }
-                }
-                if (P.adj_w && active) {  // SS:2019-2073 in compact ELL form
-                    double wj = 0.0, wm = 0.0;
-                    int src = -1;
-                    if (has_job) {
-                        const int u = v - 1, mu = s_mach[u];
-                        const double du = s_dur[u];
-                        double w;
-                        if (fresh == v) w = du + s_tt[mu * M + mv] + (stv - s_ft[u]);                 // SS:1764 / 1644
-                        else if (du != 0.0) w = du + ((mu >= 0 && sch) ? s_tt[mu * M + mv] : 0.0);   // SS:1392-1422
-                        else w = 1.0;                                                                  // SS:625,642
-                        wj = adj_val_t(w, mu >= 0, du);
-                    }
-                    if (has_m) {
-                        const double dr = s_dur[rp];
-                        const double w = dr + ((rp / M == v / M) ? s_tt[mv * M + mv] : 0.0) + (stv - s_ft[rp]);
-                        wm = adj_val_t(w, true, dr);
-                        if (wm != 0.0) src = rp;
-                    }
-                    reinterpret_cast<float2*>(P.adj_w)[(size_t)b * N + v] = make_float2((float)wj, (float)wm);
-                    P.adj_src[(size_t)b * N + v] = (int16_t)src;
+        // feature row (SS:2246-2277) and compact ELL adjacency row (SS:2019-2073) of op v; eptv = its estimated energy
+        auto emit_row = [&](const int v, const double eptv) {
+            const int mv = s_mach[v];
+            const bool sch = mv >= 0, vfirst = (v % M) == 0;
+            const int rp = sch ? (int)s_rpred[v] : -1;
+            const bool has_job = !vfirst && v != rem_head;
+            const bool co = has_job && rp == v - 1;
+            const bool has_m = rp >= 0 && !co;
+            const double stv = s_st[v], ftv = s_ft[v], durv = s_dur[v];
+            if (tf) {
+                const int indeg = (vfirst ? 1 : 0) + (has_job ? 1 : 0) + (has_m ? 1 : 0);
+                OutT* row = tf + ((size_t)b * N + v) * 12;
+                if constexpr (sizeof(OutT) == 4) {
+                    float4* r4 = reinterpret_cast<float4*>(row);
+                    r4[0] = make_float4((float)stv, (float)ftv, (float)eptv, sch ? 1.f : 0.f);
+                    r4[1] = make_float4((float)indeg, (float)(mv + 1), (float)durv, sch ? (float)s_psel[v] : 0.f);
+                    r4[2] = make_float4((float)(v / M + 1), w0, w1, w2);
+                } else {
+                    double2* r2 = reinterpret_cast<double2*>(row);
+                    r2[0] = make_double2(stv, ftv);
+                    r2[1] = make_double2(eptv, sch ? 1.0 : 0.0);
+                    r2[2] = make_double2((double)indeg, (double)(mv + 1));
+                    r2[3] = make_double2(durv, sch ? s_psel[v] : 0.0);
+                    r2[4] = make_double2((double)(v / M + 1), w0);
+                    r2[5] = make_double2(w1, w2);
                 }
             }
-        }
-        __syncwarp();
-        if (P.mfea && gl < M && active) {  // SS:2315-2354
+            if (P.adj_w) {
+                double wj = 0.0, wm = 0.0;
+                int src = -1;
+                if (has_job) {
+                    const int u = v - 1, mu = s_mach[u];
+                    const double du = s_dur[u];
+                    double w;
+                    if (fresh == v) w = du + s_tt[mu * M + mv] + (stv - s_ft[u]);                 // SS:1764 / 1644
+                    else if (du != 0.0) w = du + ((mu >= 0 && sch) ? s_tt[mu * M + mv] : 0.0);   // SS:1392-1422
+                    else w = 1.0;                                                                  // SS:625,642
+                    wj = adj_val_t(w, mu >= 0, du);
+                }
+                if (has_m) {
+                    const double dr = s_dur[rp];
+                    const double w = dr + ((rp / M == v / M) ? s_tt[mv * M + mv] : 0.0) + (stv - s_ft[rp]);
+                    wm = adj_val_t(w, true, dr);
+                    if (wm != 0.0) src = rp;
+                }
+                reinterpret_cast<float2*>(P.adj_w)[(size_t)b * N + v] = make_float2((float)wj, (float)wm);
+                P.adj_src[(size_t)b * N + v] = (int16_t)src;
+            }
+        };
+        // machine feature row k (SS:2315-2354); tail = last op of its route
+        auto emit_mach = [&](const int k, const int tail) {
             OutT* mf = reinterpret_cast<OutT*>(P.mfea);
             double f[8];
-            const int c = s_cnt[gl];
-            f[0] = c > 0 ? s_ft[s_tail[gl]] : 0.0;
-            f[1] = s_macc[gl * 3 + 0]; f[2] = s_macc[gl * 3 + 1]; f[3] = s_macc[gl * 3 + 2];
+            const int c = s_cnt[k];
+            f[0] = c > 0 ? s_ft[tail] : 0.0;
+            f[1] = s_macc[k * 3 + 0]; f[2] = s_macc[k * 3 + 1]; f[3] = s_macc[k * 3 + 2];
             f[4] = (double)c;
             f[5] = s_w[0]; f[6] = s_w[1]; f[7] = s_w[2];
-            store_row<OutT>(mf + ((size_t)b * M + gl) * 8, f, 8);
+            store_row<OutT>(mf + ((size_t)b * M + k) * 8, f, 8);
+        };
+        // Incremental observation (P.obs_inc): the output buffers hold the observation of the previous step.  A step
+        // changes the rows of the stepped job from the stepped op on (its start / finish / machine, the re-estimated chain
+        // behind it, the job arc into the op after it), the row of the op that now follows it on the machine (new machine
+        // predecessor), and the rows the one-step transients touch (this step's are the stepped op and that follower; the
+        // previous step's revert).  Everything else is bit-identical to what is already there, so a lane emits at most two
+        // rows (slot 0: its op of the stepped job, slot 1: one of the three extras) instead of ITER; an invalid action
+        // changed nothing.
+        const bool inc = (MODE & MODE_STEP) && P.obs_inc;
+        const int row0 = (valid && gl >= apos && gl < M) ? ja * M + gl : -1;
+        const int row1 = !valid ? -1 : gl == 0 ? o_next : gl == 1 ? rem_prev : gl == 2 ? fresh_prev : -1;
+#pragma unroll
+        for (int it = 0; it < ITER; it++) {
+            if (inc && it >= 2) break;
+            const int v = inc ? (it == 0 ? row0 : row1) : gl + it * G;
+            if (v >= 0 && v < N) {
+                const int mv = s_mach[v];
+                if (!inc && mv >= 0 && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
+                if (active) emit_row(v, inc ? ((mv >= 0) ? s_dur[v] * s_psel[v] : s_psel[v]) : ept[it]);
+            }
+        }
+        if (inc) {
+            if (P.mfea && valid && gl == 0) emit_mach(mc, o_tail);
+        } else {
+            __syncwarp();
+            if (P.mfea && gl < M && active) emit_mach(gl, s_tail[gl]);
         }
     }
 }
@@ -1582,6 +1617,10 @@ struct mtfjsp_env {
     float* tmp_adj_w;
     int16_t* tmp_adj_src;
     bool loaded, reset_done, force_generic;
+    // incremental observation (mtfjsp_set_obs_incremental): which output buffers currently mirror the env state
+    bool obs_inc_enabled, obs_inc_allowed, obs_synced;
+    const void* obs_ptrs[4];
+    int obs_dtype;
     int host_chunks, fuse_policy;  // tuning knobs read from the environment at create time (tests compare the settings)
     int64_t launches;
     struct HostPipe* pipe;  // host-step pipeline (streams, events, instantiated graphs), created on first use
@@ -1597,7 +1636,7 @@ struct HostPipe {
     cudaEvent_t fork, join[MAXC];
     struct Entry {
         const void* key[11];
-        int mask_mode, dtype, chunks, kernels;
+        int mask_mode, dtype, chunks, kernels, inc;
         cudaGraphExec_t exec;
     };
     std::vector<Entry> cache;
@@ -1730,14 +1769,30 @@ static int fill_obs(mtfjsp_env* h, Params& P, void* task_fea, void* mach_fea, fl
     return MTFJSP_OK;
 }
 
+// Incremental observation bookkeeping.  A fused step may rewrite only the changed rows iff the caller's output buffers
+// already hold the observation of the current state: the same four pointers and dtype received a full observation
+// (mtfjsp_obs, or a fused step that wrote everything) since the last reset / load / observation-less step, and every
+// step since went through them.  obs_inc_now() answers that before a whole-batch step, obs_mark() records it after.
+static int obs_inc_now(const mtfjsp_env* h, const void* tfea, const void* mfea, const void* adj_w, const void* adj_src,
+                       int dtype) {
+    return h->obs_inc_enabled && h->obs_synced && h->obs_dtype == dtype && h->obs_ptrs[0] == tfea &&
+           h->obs_ptrs[1] == mfea && h->obs_ptrs[2] == adj_w && h->obs_ptrs[3] == adj_src;
+}
+static void obs_mark(mtfjsp_env* h, const void* tfea, const void* mfea, const void* adj_w, const void* adj_src, int dtype) {
+    h->obs_synced = true;
+    h->obs_dtype = dtype;
+    h->obs_ptrs[0] = tfea; h->obs_ptrs[1] = mfea; h->obs_ptrs[2] = adj_w; h->obs_ptrs[3] = adj_src;
+}
+
 // fused step + observation over the env range [b0, b1) (the whole batch, or one chunk of the host-step pipeline)
 static int step_obs_range(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
                           uint8_t* done, uint8_t* invalid, double* info6, void* task_fea, void* mach_fea, float* adj_w,
                           int16_t* adj_src, uint8_t* job_mask, int32_t* candidate, int mask_mode, int dtype, int b0, int b1,
-                          cudaStream_t s, const int2* act2 = nullptr, unsigned char* rec = nullptr) {
+                          cudaStream_t s, const int2* act2 = nullptr, unsigned char* rec = nullptr, int obs_inc = 0) {
     Params P = make_params(h);
     P.op = op; P.mach = mach; P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
     P.info6 = info6; P.b0 = b0; P.b1 = b1; P.act2 = act2; P.rec = rec; P.rec_stride = h->rec_stride;
+    P.obs_inc = obs_inc;
     int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
     if (rc) return rc;
     return dtype == MTFJSP_F64 ? launch_env_auto<MODE_STEP | MODE_OBS, double>(h, P, s)
@@ -1792,6 +1847,7 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
         h->force_generic = fg && fg[0] == '1';
         h->host_chunks = getenv("MTFJSP_HOST_CHUNKS") ? atoi(getenv("MTFJSP_HOST_CHUNKS")) : 4;
         h->fuse_policy = getenv("MTFJSP_FUSE_POLICY") ? atoi(getenv("MTFJSP_FUSE_POLICY")) : 1;
+        h->obs_inc_allowed = !(getenv("MTFJSP_OBS_INCREMENTAL") && atoi(getenv("MTFJSP_OBS_INCREMENTAL")) == 0);  // test hook
     }
     h->cfgw[0] = 0.4; h->cfgw[1] = 0.4; h->cfgw[2] = 0.2; h->divisor = 1.0; h->gamma = 0.99;
     size_t Bs = (size_t)B;
@@ -1852,6 +1908,13 @@ int mtfjsp_set_params(mtfjsp_env* h, double w_mk, double w_ec, double w_tt, doub
     return MTFJSP_OK;
 }
 
+int mtfjsp_set_obs_incremental(mtfjsp_env* h, int on) {
+    if (!h) return fail(MTFJSP_E_ARG, "null handle");
+    h->obs_inc_enabled = on != 0 && h->obs_inc_allowed;
+    h->obs_synced = false;
+    return MTFJSP_OK;
+}
+
 int mtfjsp_load(mtfjsp_env* h, const double* t, const double* p, const double* tt, const int32_t* edge, int W,
                 void* stream) {
     if (!h || !t || !p || !tt || !edge || W < 1) return fail(MTFJSP_E_ARG, "mtfjsp_load: bad argument");
@@ -1867,6 +1930,7 @@ int mtfjsp_load(mtfjsp_env* h, const double* t, const double* p, const double* t
     CK(cudaGetLastError(), "load_kernel");
     h->loaded = true;
     h->reset_done = false;
+    h->obs_synced = false;
     return MTFJSP_OK;
 }
 
@@ -1897,6 +1961,7 @@ int mtfjsp_reset(mtfjsp_env* h, const double* weights, void* stream) {
     Params P = make_params(h);
     P.weights = weights;
     int rc = launch_env<MODE_RESET, double>(h, P, (cudaStream_t)stream);
+    h->obs_synced = false;
     if (rc == MTFJSP_OK) h->reset_done = true;
     return rc;
 }
@@ -1909,6 +1974,7 @@ int mtfjsp_step(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* r
     CK(cudaSetDevice(h->device), "cudaSetDevice");
     Params P = make_params(h);
     P.op = op; P.mach = mach; P.reward5 = reward5; P.scaled4 = scaled4; P.done = done; P.invalid = invalid;
+    h->obs_synced = false;  // the state moves on without any observation buffer following it
     return launch_env_auto<MODE_STEP, double>(h, P, (cudaStream_t)stream);
 }
 
@@ -1920,8 +1986,12 @@ int mtfjsp_obs(mtfjsp_env* h, void* task_fea, void* mach_fea, float* adj_w, int1
     Params P = make_params(h);
     int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
     if (rc) return rc;
-    return dtype == MTFJSP_F64 ? launch_env_auto<MODE_OBS, double>(h, P, (cudaStream_t)stream)
-                               : launch_env_auto<MODE_OBS, float>(h, P, (cudaStream_t)stream);
+    rc = dtype == MTFJSP_F64 ? launch_env_auto<MODE_OBS, double>(h, P, (cudaStream_t)stream)
+                             : launch_env_auto<MODE_OBS, float>(h, P, (cudaStream_t)stream);
+    // a full observation into a complete buffer set makes that set the mirror of the state -- unless another set already
+    // is (a side view such as mtfjsp_dense_adj must not break the main buffers' chain)
+    if (rc == MTFJSP_OK && task_fea && mach_fea && adj_w && !h->obs_synced) obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
+    return rc;
 }
 
 int mtfjsp_step_obs(mtfjsp_env* h, const int32_t* op, const int32_t* mach, double* reward5, double* scaled4,
@@ -1930,8 +2000,11 @@ int mtfjsp_step_obs(mtfjsp_env* h, const int32_t* op, const int32_t* mach, doubl
     if (!h || !op || !mach) return fail(MTFJSP_E_ARG, "mtfjsp_step_obs: bad argument");
     if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_step_obs before mtfjsp_reset");
     CK(cudaSetDevice(h->device), "cudaSetDevice");
-    return step_obs_range(h, op, mach, reward5, scaled4, done, invalid, nullptr, task_fea, mach_fea, adj_w, adj_src,
-                          job_mask, candidate, mask_mode, dtype, 0, h->L.B, (cudaStream_t)stream);
+    const int inc = obs_inc_now(h, task_fea, mach_fea, adj_w, adj_src, dtype);
+    int rc = step_obs_range(h, op, mach, reward5, scaled4, done, invalid, nullptr, task_fea, mach_fea, adj_w, adj_src,
+                            job_mask, candidate, mask_mode, dtype, 0, h->L.B, (cudaStream_t)stream, nullptr, nullptr, inc);
+    if (rc == MTFJSP_OK) obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
+    return rc;
 }
 
 int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_mask, int dtype, void* stream) {
@@ -2035,8 +2108,10 @@ int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_
         P.mfea1 = mfea1; P.mmask = mach_mask;
         int rf = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
         if (rf) return rf;
+        P.obs_inc = obs_inc_now(h, task_fea, mach_fea, adj_w, adj_src, dtype);
         rf = dtype == MTFJSP_F64 ? launch_random_fused<double>(h, P, (cudaStream_t)stream)
                                  : launch_random_fused<float>(h, P, (cudaStream_t)stream);
+        if (rf > 0) obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
         if (rf != 0) return rf < 0 ? rf : MTFJSP_OK;
     }
     int rc = launch_prestep<true>(h, seed, env_offset, mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin, o, mc, mfea1,
@@ -2077,6 +2152,7 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
                           int mask_mode, int dtype, cudaStream_t s) {
     const Layout& L = h->L;
     const bool packed = io.act != nullptr;
+    const int inc = obs_inc_now(h, task_fea, mach_fea, adj_w, adj_src, dtype);  // one decision for all chunks of the step
     const uint8_t* jm_dev = mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin;
     const size_t rs = (size_t)h->rec_stride;
     // everything one chunk [b0, b1) does, in order, on stream q
@@ -2090,7 +2166,7 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
         }
         int rc = step_obs_range(h, h->a_op, h->a_mach, nullptr, nullptr, h->dn, h->inv, io.info6 ? h->info6 : nullptr,
                                 task_fea, mach_fea, adj_w, adj_src, nullptr, nullptr, mask_mode, dtype, b0, b1, q,
-                                packed ? h->act2 : nullptr, io.rec ? h->rec : nullptr);
+                                packed ? h->act2 : nullptr, io.rec ? h->rec : nullptr, inc);
         if (rc) return rc;
         if (io.rec) CK(cudaMemcpyAsync(io.rec + b0 * rs, h->rec + b0 * rs, n * rs, cudaMemcpyDeviceToHost, q), "D2H records");
         if (io.info6)
@@ -2109,6 +2185,7 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
         // pageable buffers: the copies are staged by the driver and cannot overlap; plain in-order sequence
         int rc = chunk(0, L.B, s);
         if (rc) return rc;
+        obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
         CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
         return MTFJSP_OK;
     }
@@ -2130,7 +2207,7 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
     const void* key[11] = {io.op, io.mach, io.act, io.info6, io.jm, io.cand, io.rec, task_fea, mach_fea, adj_w, adj_src};
     HostPipe::Entry* ent = nullptr;
     for (auto& e : hp->cache)
-        if (!memcmp(e.key, key, sizeof key) && e.mask_mode == mask_mode && e.dtype == dtype && e.chunks == chunks) { ent = &e; break; }
+        if (!memcmp(e.key, key, sizeof key) && e.mask_mode == mask_mode && e.dtype == dtype && e.chunks == chunks && e.inc == inc) { ent = &e; break; }
     if (!ent) {
         if (hp->cache.size() >= 256) {  // addresses keep changing: start over rather than grow without bound
             for (auto& e : hp->cache) cudaGraphExecDestroy(e.exec);
@@ -2161,7 +2238,7 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
         CK(ee, "cudaStreamEndCapture");
         HostPipe::Entry e;
         memcpy(e.key, key, sizeof key);
-        e.mask_mode = mask_mode; e.dtype = dtype; e.chunks = chunks; e.kernels = kernels;
+        e.mask_mode = mask_mode; e.dtype = dtype; e.chunks = chunks; e.kernels = kernels; e.inc = inc;
         cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
         cudaGraphDestroy(g);
         CK(ie, "cudaGraphInstantiate");
@@ -2170,6 +2247,7 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
     }
     CK(cudaGraphLaunch(ent->exec, s), "cudaGraphLaunch");
     h->launches += ent->kernels;
+    obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
     CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
     return MTFJSP_OK;
 }

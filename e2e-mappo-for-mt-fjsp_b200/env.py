@@ -40,7 +40,9 @@ class BatchedMTFJSPEnv:
     reference locations."""
 
     def __init__(self, B, J, M, E, left_shift=True, weights=(0.4, 0.4, 0.2), scaling_divisor=1.0, gamma=0.99,
-                 device=None, obs_dtype=torch.float32, mask_mode=MASK_ESA):
+                 device=None, obs_dtype=torch.float32, mask_mode=MASK_ESA, incremental_obs=True):
+        """incremental_obs: fused steps rewrite only the observation rows a step changes (the object owns
+        task_fea / mach_fea / adj_w / adj_src; callers read them, or copy them, and never write into them)."""
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedMTFJSPEnv needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -53,6 +55,7 @@ class BatchedMTFJSPEnv:
         check(self._lib.mtfjsp_create(C.byref(h), B, J, M, E, int(bool(left_shift)), self.device.index or 0), "mtfjsp_create")
         self._h = h
         check(self._lib.mtfjsp_set_params(self._h, weights[0], weights[1], weights[2], scaling_divisor, gamma), "mtfjsp_set_params")
+        check(self._lib.mtfjsp_set_obs_incremental(self._h, int(bool(incremental_obs))), "mtfjsp_set_obs_incremental")
         dev, N = self.device, self.N
         self.task_fea = torch.empty((B, N, 12), dtype=obs_dtype, device=dev)
         self.mach_fea = torch.empty((B, M, 8), dtype=obs_dtype, device=dev)

@@ -127,6 +127,16 @@ int mtfjsp_random_step(mtfjsp_env* h, uint64_t seed, uint64_t env_offset, int32_
                        void* task_fea, void* mach_fea, float* adj_w, int16_t* adj_src, uint8_t* job_mask,
                        int32_t* candidate, int mask_mode, int dtype, void* stream);
 
+/* Incremental observation (off by default).  When on, a fused step (mtfjsp_step_obs / mtfjsp_random_step /
+ * mtfjsp_step_host*) whose four observation pointers and dtype are the ones that received the previous observation
+ * rewrites only the rows the step changed -- the stepped job's rows from the stepped op on, the op that now follows it
+ * on its machine, the rows of the previous step's one-step transients, one machine row -- instead of all N + M rows;
+ * the buffers end up bit-identical to a full rewrite.  The library tracks the chain (a reset, a load, an mtfjsp_step
+ * without observation or different pointers force the next fused step to write everything); the CALLER promises not
+ * to modify those buffers between steps.  The reference rebuilds every array every step (SS:2001-2515, 69 % of its
+ * step time). */
+int mtfjsp_set_obs_incremental(mtfjsp_env* h, int on);
+
 /* Host-buffer form of mtfjsp_step_obs, the call a host-side rollout loop (Run.py:411-443) makes:
  * actions come from (pinned) host memory, the step info the host consumes comes back --
  * info6 [B,6] f64 = (r, done, mk_s, idle_s, pt_s, tt_s) exactly as trainer/parallel_env.py:260,

@@ -1,5 +1,5 @@
 """Short driver for ncu captures: config-2 workload (J6M6E2, 65,536 envs), a few rollout steps.
-usage: ncu ... python profiles/prof_step.py [workload] [steps]"""
+usage: ncu ... python profiles/prof_step.py [workload] [steps] [random|replay]"""
 import importlib
 import os
 import sys
@@ -20,7 +20,15 @@ env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
 env.load(d["t"], d["p"], d["transT"], d["edge"])
 env.scaler_init()
 env.reset(w)
-for s in range(steps):
-    env.random_step(seed=1)
+mode = sys.argv[3] if len(sys.argv) > 3 else "random"   # "random": one-launch random step; "replay": step_obs on given actions
+if mode == "random":
+    for s in range(steps):
+        env.random_step(seed=1)
+else:
+    ops, mcs = [], []
+    for s in range(steps):
+        env.policy_random(seed=1)
+        ops.append(env.op.clone()); mcs.append(env.mach.clone())
+        env.step_obs(env.op, env.mach)
 torch.cuda.synchronize()
 print("done", env.launch_count)

@@ -21,13 +21,15 @@ ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
 eq = np.testing.assert_array_equal
 
 
-@pytest.fixture(params=["auto", "generic", "unfused"])
+@pytest.fixture(params=["auto", "generic", "unfused", "fullobs"])
 def kernel_path(request, monkeypatch):
     """'auto' = size-specialised kernel where one exists (random_step = one launch: policy + candidate-machine
-    features + step + observation); 'unfused' = the same kernels with the pre-step kernel launched separately;
-    'generic' forces the one-warp-per-env kernel."""
+    features + step + observation, observation rows rewritten incrementally after the first step of an episode);
+    'unfused' = the same kernels with the pre-step kernel launched separately; 'fullobs' = every step rewrites the
+    whole observation; 'generic' forces the one-warp-per-env kernel."""
     monkeypatch.setenv("MTFJSP_FORCE_GENERIC", "1" if request.param == "generic" else "0")
     monkeypatch.setenv("MTFJSP_FUSE_POLICY", "0" if request.param == "unfused" else "1")
+    monkeypatch.setenv("MTFJSP_OBS_INCREMENTAL", "0" if request.param == "fullobs" else "1")
     return request.param
 
 
