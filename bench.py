@@ -416,6 +416,10 @@ def run_ours(args, wl):
                                     "reward + observation + job mask; the kernel of the timed region)",
                           "kernel_us": fused["kernel_us"], "bytes_per_env_step": fused["bytes_per_env_step"],
                           "peak_source": peak_src, "steps_per_s_kernel_only": B / (fused["kernel_us"] * 1e-6),
+                          "bytes_accounting": "SURVEY.md 8(d): a full rewrite of the observation every step, as the reference "
+                                              "does; with the incremental observation the kernel moves `traffic` bytes per "
+                                              "launch (ncu), i.e. frac_of_peak_moved = traffic / kernel time / peak",
+                          "frac_of_peak_moved": (traffic / (fused["kernel_us"] * 1e-6) / 1e9 / peak) if traffic else None,
                           "step_obs_kernel": {"kernel": "env_kernel_s<STEP|OBS,float> (actions given: the actor-driven and "
                                                         "host-step paths)", "kernel_us": k_us, "bytes_per_env_step": bytes_step,
                                               "achieved": achieved, "frac": achieved / peak, "traffic": traffic_step}}
