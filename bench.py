@@ -348,11 +348,12 @@ def run_ours(args, wl):
                  "allreduce_bytes_per_update": arb, "losses": losses,
                  "update_ms_library_fp32": runs["library_fp32"][0] - runs["library_fp32"][1],
                  "value_library_fp32": Bt * world * N / (runs["library_fp32"][0] * 1e-3),
-                 "what": "one buffer (1 episode) collected with the tcgen05 rollout twins + one batched PPO update; the graph "
-                         "encoders' Linear layers run forward / input-gradient / weight-gradient on the hand-written tcgen05 "
-                         "TF32 kernels (PPOConfig.encoder_tf32), heads on library FP32 GEMMs; aggregation, grouped BatchNorm "
-                         "and GAE kernels hand-written; NCCL gradient allreduce when n_gpus > 1.  *_library_fp32 = the same "
-                         "update with every GEMM on the FP32 library path (the reference's arithmetic)"}
+                 "what": "one buffer (1 episode) collected with the tcgen05 rollout twins (CUDA-graph replay) + one batched PPO "
+                         "update; every [rows,128] x [128,<=128] product of the update (graph encoders, GAT projections, policy "
+                         "heads) runs forward / input-gradient / weight-gradient on the hand-written tcgen05 TF32 kernels "
+                         "(PPOConfig.encoder_tf32); aggregation, grouped BatchNorm and GAE kernels hand-written; NCCL gradient "
+                         "allreduce when n_gpus > 1.  *_library_fp32 = the same update with every GEMM on the FP32 library path "
+                         "(the reference's arithmetic)"}
         del env_t, up, tro
         torch.cuda.empty_cache()
 
