@@ -347,3 +347,50 @@ def test_full_size_rollout_invariants(cfg):
     eq(env.scaled4.cpu().numpy()[sub], s4)
     ob = ora.obs(1)
     eq(env.task_fea.cpu().numpy()[sub], ob["task_fea"].astype(np.float32))
+
+
+def test_incremental_observation_bookkeeping():
+    """The incremental observation may only be used while the SAME output buffers have followed every step since a full
+    observation.  Break the chain in every way the C ABI allows -- other buffers, a step without observation, a reset, a
+    side view (dense_adj), an invalid action -- and compare the buffers with the oracle after every step."""
+    B, J, M, E = 200, 6, 6, 2
+    N = J * M
+    env, ora, d, w = _mk(B, J, M, E, seed=11, dtype=torch.float32)
+    main = (env.task_fea, env.mach_fea, env.adj_w, env.adj_src)
+    other = tuple(torch.full_like(x, 77) for x in main)
+
+    def check(tag):
+        ob = ora.obs(1)
+        eq(env.task_fea.cpu().numpy(), ob["task_fea"].astype(np.float32), err_msg=tag)
+        eq(env.mach_fea.cpu().numpy(), ob["mach_fea"].astype(np.float32), err_msg=tag)
+        eq(_ell_to_dense(env.adj_w.cpu().numpy().astype(np.float64), env.adj_src.cpu().numpy().astype(np.int64)),
+           ora.dense_adj(), err_msg=tag)
+
+    def use(bufs):
+        env.task_fea, env.mach_fea, env.adj_w, env.adj_src = bufs
+
+    for s in range(N):
+        op, mach = env.policy_random(seed=3)
+        o, m = op.cpu().numpy().copy(), mach.cpu().numpy().copy()
+        if s == 5:      # other buffers (filled with garbage): must be rewritten completely
+            use(other)
+        if s == 9:      # ... and back to the main ones, which are 4 steps stale by now
+            use(main)
+        if s == 12:     # a step without observation breaks the chain
+            env.step(op, mach); ora.step(o, m)
+            op, mach = env.policy_random(seed=4)
+            o, m = op.cpu().numpy().copy(), mach.cpu().numpy().copy()
+        if s == 15:     # a side view into other memory must not disturb the chain
+            env.dense_adj()
+        if s == 20:     # invalid actions for half of the envs: their state and rows stay as they are
+            op = op.clone(); op[::2] = -1
+            o = op.cpu().numpy().copy()
+        env.step_obs(op, mach)
+        r5, s4, done, inv = ora.step(o, m)
+        eq(env.invalid.cpu().numpy(), inv)
+        check("step %d" % s)
+    w2 = ins.random_weights(0, B, 99)
+    env.reset(w2); ora.reset(w2)          # a reset breaks the chain: the first step of the episode writes everything
+    env.random_step(seed=8)
+    ora.step(env.op.cpu().numpy(), env.mach.cpu().numpy())
+    check("after reset")
