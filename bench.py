@@ -123,9 +123,13 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.mtfjsp_oracle import max_threads
-
-    cores = max(1, min(max_threads(), os.cpu_count() or 1))
+    # every host core this process may run on (torchrun exports OMP_NUM_THREADS=1; the oracle's parallel loops take an
+    # explicit thread count, so that default does not starve the reference arm)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(1, cores)
     rates = []
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_rate(wl, cores, 1.0)
@@ -157,9 +161,15 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stdout_fd = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
+        # stdout carries the one JSON line only: NCCL prints its version banner with printf when NCCL_DEBUG=VERSION, so
+        # everything the libraries write to fd 1 goes to stderr until the line is printed
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
     sh = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.sharding")
@@ -440,7 +450,12 @@ def run_ours(args, wl):
             line["e2e"]["dropin_parallel_env"] = dropin
         if cpu:
             line["cpu_baseline"] = cpu
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        if stdout_fd is not None:
+            os.dup2(2, 1)  # teardown chatter stays off stdout as well
     if world > 1:
         dist.destroy_process_group()
 
