@@ -83,6 +83,8 @@ SIGNATURES = {
     "mtfjsp_enc_linear_tf32": ([_VP, C.c_int64, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
     "mtfjsp_enc_mach_proj": ([_VP, _VP, _VP, _VP, _VP, C.c_int64, _VP], _I),
     "mtfjsp_enc_gat_attend": ([_VP, _VP, _VP, _VP, C.c_int64, _I, _VP], _I),
+    "mtfjsp_enc_gat_attend_bwd": ([_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _I, _VP], _I),
+    "mtfjsp_enc_gat_attend_bwd_blocks": ([C.c_int64], _I),
     "mtfjsp_enc_bias_tanh": ([_VP, _VP, C.c_int64, _I, C.c_int64, _VP], _I),
     "mtfjsp_enc_tanh_dot": ([_VP, _VP, _VP, _VP, C.c_int64, _VP], _I),
     "mtfjsp_enc_wgrad_tf32": ([_VP, _VP, C.c_int64, _I, _VP, _VP, _VP, _VP], _I),

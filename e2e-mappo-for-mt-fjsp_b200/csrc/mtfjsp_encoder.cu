@@ -368,6 +368,68 @@ __global__ void __launch_bounds__(256) gat_attend_kernel(const float4* __restric
     out[(R + row) * 32 + lane] = h2;
 }
 
+// Backward of gat_attend_kernel for the PPO update (torch autograd runs ~20 elementwise kernels per GAT layer there).
+// g: gradient of the forward's output ([2R,128], or [R,128] in mode 2); recomputes the attention from t, writes
+// dt [2R,128] and accumulates the gradients of a_src / a_dst per block (dparts [gridDim.x][2][128], summed by the caller).
+__global__ void __launch_bounds__(256) gat_attend_bwd_kernel(const float4* __restrict__ t, const float4* __restrict__ a_src,
+                                                             const float4* __restrict__ a_dst, const float4* __restrict__ g,
+                                                             float4* __restrict__ dt, float* __restrict__ dparts, long long R,
+                                                             int mode) {
+    __shared__ float4 s_acc[8][2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 as = __ldg(a_src + lane), ad = __ldg(a_dst + lane);
+    float4 das = make_float4(0.f, 0.f, 0.f, 0.f), dad = das;
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < R; row += nw) {
+        const float4 x1 = __ldg(t + row * 32 + lane), x2 = __ldg(t + (R + row) * 32 + lane);
+        const float s1 = warp_sum(dot4(x1, as)), d1 = warp_sum(dot4(x1, ad)), d2 = warp_sum(dot4(x2, ad));
+        const float r11 = s1 + d1, r12 = s1 + d2;
+        const float e11 = r11 > 0.f ? r11 : 0.2f * r11, e12 = r12 > 0.f ? r12 : 0.2f * r12;
+        const float mx = fmaxf(e11, e12);
+        const float p1 = expf(e11 - mx), p2 = expf(e12 - mx);
+        const float a0 = p1 / (p1 + p2), a1 = p2 / (p1 + p2);
+        float4 gh1, gh2;
+        if (mode == 2) {
+            const float4 gv = __ldg(g + row * 32 + lane);
+            gh1 = make_float4(0.5f * gv.x, 0.5f * gv.y, 0.5f * gv.z, 0.5f * gv.w);
+            gh2 = gh1;
+        } else {
+            gh1 = __ldg(g + row * 32 + lane);
+            gh2 = __ldg(g + (R + row) * 32 + lane);
+            if (mode == 1) {  // out = elu(h): d/dh = 1 for h > 0, exp(h) otherwise
+                const float4 h1 = make_float4(a0 * x1.x + a1 * x2.x, a0 * x1.y + a1 * x2.y, a0 * x1.z + a1 * x2.z, a0 * x1.w + a1 * x2.w);
+                gh1.x *= h1.x > 0.f ? 1.f : expf(h1.x); gh1.y *= h1.y > 0.f ? 1.f : expf(h1.y);
+                gh1.z *= h1.z > 0.f ? 1.f : expf(h1.z); gh1.w *= h1.w > 0.f ? 1.f : expf(h1.w);
+                gh2.x *= x2.x > 0.f ? 1.f : expf(x2.x); gh2.y *= x2.y > 0.f ? 1.f : expf(x2.y);
+                gh2.z *= x2.z > 0.f ? 1.f : expf(x2.z); gh2.w *= x2.w > 0.f ? 1.f : expf(x2.w);
+            }
+        }
+        const float da0 = warp_sum(dot4(gh1, x1)), da1 = warp_sum(dot4(gh1, x2));
+        const float mean = a0 * da0 + a1 * da1;
+        const float de11 = a0 * (da0 - mean) * (r11 > 0.f ? 1.f : 0.2f), de12 = a1 * (da1 - mean) * (r12 > 0.f ? 1.f : 0.2f);
+        const float ds1 = de11 + de12;
+        dt[row * 32 + lane] = make_float4(a0 * gh1.x + ds1 * as.x + de11 * ad.x, a0 * gh1.y + ds1 * as.y + de11 * ad.y,
+                                          a0 * gh1.z + ds1 * as.z + de11 * ad.z, a0 * gh1.w + ds1 * as.w + de11 * ad.w);
+        dt[(R + row) * 32 + lane] = make_float4(a1 * gh1.x + gh2.x + de12 * ad.x, a1 * gh1.y + gh2.y + de12 * ad.y,
+                                                a1 * gh1.z + gh2.z + de12 * ad.z, a1 * gh1.w + gh2.w + de12 * ad.w);
+        das.x += ds1 * x1.x; das.y += ds1 * x1.y; das.z += ds1 * x1.z; das.w += ds1 * x1.w;
+        dad.x += de11 * x1.x + de12 * x2.x; dad.y += de11 * x1.y + de12 * x2.y;
+        dad.z += de11 * x1.z + de12 * x2.z; dad.w += de11 * x1.w + de12 * x2.w;
+    }
+    s_acc[warp][0][lane] = das;
+    s_acc[warp][1][lane] = dad;
+    __syncthreads();
+    if (threadIdx.x < 64) {  // warps' partials in a fixed order: deterministic
+        const int which = threadIdx.x >> 5;
+        float4 a = s_acc[0][which][lane];
+        for (int w = 1; w < 8; w++) {
+            const float4 b = s_acc[w][which][lane];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(dparts)[((size_t)blockIdx.x * 2 + which) * 32 + lane] = a;
+    }
+}
+
 // first layer of a policy head after its per-row product (encoder._head_tf32): z[r] = tanh(z[r] + bias[r / rows_per_env]),
 // in place; bias [B,128] or a single row (bias_rows == 1)
 __global__ void __launch_bounds__(256) bias_tanh_kernel(float4* __restrict__ z, const float4* __restrict__ bias, long long rows,
@@ -526,6 +588,20 @@ int mtfjsp_enc_gat_attend(const float* t, const float* a_src, const float* a_dst
     gat_attend_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(a_src), reinterpret_cast<const float4*>(a_dst),
         reinterpret_cast<float4*>(out), R, mode);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_gat_attend_bwd_blocks(int64_t R) {
+    const long long b = (R + 7) / 8;
+    return (int)(b < 148 * 8 ? b : 148 * 8);
+}
+
+int mtfjsp_enc_gat_attend_bwd(const float* t, const float* a_src, const float* a_dst, const float* g, float* dt, float* dparts,
+                              int64_t R, int mode, void* stream) {
+    if (!t || !a_src || !a_dst || !g || !dt || !dparts || R < 1 || mode < 0 || mode > 2) return MTFJSP_E_ARG;
+    gat_attend_bwd_kernel<<<mtfjsp_enc_gat_attend_bwd_blocks(R), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(a_src), reinterpret_cast<const float4*>(a_dst),
+        reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(dt), dparts, R, mode);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 

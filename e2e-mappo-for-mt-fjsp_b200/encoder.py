@@ -164,6 +164,35 @@ def gat_attend(t, a_src, a_dst, mode, out=None):
     return out
 
 
+class _GatAttendFn(torch.autograd.Function):
+    """gat_attend under autograd for the PPO update: forward = the rollout kernel, backward = one kernel that recomputes
+    the attention from t and emits dt plus per-block partial gradients of the two attention vectors."""
+
+    @staticmethod
+    def forward(ctx, t, a_src, a_dst, mode):
+        t, a_src, a_dst = t.contiguous(), a_src.contiguous(), a_dst.contiguous()
+        ctx.save_for_backward(t, a_src, a_dst)
+        ctx.mode = mode
+        return gat_attend(t, a_src, a_dst, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, a_src, a_dst = ctx.saved_tensors
+        R = t.shape[0] // 2
+        lib = _lib.lib()
+        nb = int(lib.mtfjsp_enc_gat_attend_bwd_blocks(R))
+        dt = torch.empty_like(t)
+        parts = torch.empty((nb, 2, 128), dtype=torch.float32, device=t.device)
+        check(lib.mtfjsp_enc_gat_attend_bwd(_ptr(t), _ptr(a_src), _ptr(a_dst), _ptr(g.contiguous()), _ptr(dt), _ptr(parts), R,
+                                            ctx.mode, _stream()), "mtfjsp_enc_gat_attend_bwd")
+        da = parts.sum(dim=0)
+        return dt, da[0], da[1], None
+
+
+def gat_attend_train(t, a_src, a_dst, mode):
+    return _GatAttendFn.apply(t, a_src, a_dst, mode)
+
+
 def bias_tanh_(z, bias, rows_per_env):
     """z[r] = tanh(z[r] + bias[r // rows_per_env]) in place; bias [B,128] or [1,128]."""
     check(_lib.lib().mtfjsp_enc_bias_tanh(_ptr(z), _ptr(bias), z.shape[0], rows_per_env, bias.shape[0], _stream()),
@@ -607,6 +636,8 @@ class _MachineTrunk:
         B = machine_fea_1.shape[0]
         if self.precision == "tf32":
             return self._trunk_tf32(machine_fea_1, machine_fea_2, groups)
+        if getattr(self, "train_tf32", False) and self.H == 128 and machine_fea_1.is_cuda:
+            return self._trunk_train_fused(machine_fea_1, machine_fea_2, groups)
         h1 = F.linear(machine_fea_1.to(torch.float32), w["m_fea_1_fcl.weight"]).reshape(B * self.M, self.H)
         h2 = F.linear(machine_fea_2.to(torch.float32), w["m_fea_2_fcl.weight"]).reshape(B * self.M, self.H)
         h1, h2 = self._gat(h1, h2)
@@ -614,6 +645,25 @@ class _MachineTrunk:
         h1, h2 = self._gat(F.elu(h1), F.elu(h2))
         hm = torch.stack((h1, h2), dim=1).mean(dim=-2)                                   # actor_critic.py:420
         nodes = _bn_train(hm, w["bn.weight"], w["bn.bias"], groups=groups).reshape(B, self.M, self.H)   # actor_critic.py:434
+        return nodes, nodes.mean(dim=1)
+
+    def _trunk_train_fused(self, machine_fea_1, machine_fea_2, groups):
+        """PPO-update twin of _trunk_tf32 (PPOConfig.encoder_tf32): per GAT layer one tcgen05 projection of both node sets
+        and one attention / combination / ELU kernel, each with a hand-written backward, instead of ~20 library
+        elementwise launches forward and as many backward per layer."""
+        w, H = self.w, self.H
+        B = machine_fea_1.shape[0]
+        R = B * self.M
+        h1 = F.linear(machine_fea_1.to(torch.float32).reshape(R, 6), w["m_fea_1_fcl.weight"])
+        h2 = F.linear(machine_fea_2.to(torch.float32).reshape(R, 8), w["m_fea_2_fcl.weight"])
+        buf = torch.cat((h1, h2), dim=0)
+        Wt = w["gat_layer.W"].t().contiguous()
+        a = w["gat_layer.a"]
+        a_src, a_dst = a[0, :H, 0], a[0, H:, 0]
+        for layer in range(3):
+            t = linear_train(buf, Wt, None, True)
+            buf = gat_attend_train(t, a_src, a_dst, 1 if layer < 2 else 2)
+        nodes = _bn_train(buf, w["bn.weight"], w["bn.bias"], groups=groups).reshape(B, self.M, H)
         return nodes, nodes.mean(dim=1)
 
     def _trunk_tf32(self, machine_fea_1, machine_fea_2, groups):

@@ -200,6 +200,11 @@ int mtfjsp_enc_mach_proj(const float* fea1, const float* fea2, const float* W1, 
                          void* stream);
 int mtfjsp_enc_gat_attend(const float* t, const float* a_src, const float* a_dst, float* out, int64_t R, int mode,
                           void* stream);
+/* Backward of mtfjsp_enc_gat_attend for the PPO update: g = gradient of its output, dt [2R,128] = gradient of t,
+ * dparts [mtfjsp_enc_gat_attend_bwd_blocks(R)][2][128] = per-block partial gradients of (a_src, a_dst) to be summed. */
+int mtfjsp_enc_gat_attend_bwd(const float* t, const float* a_src, const float* a_dst, const float* g, float* dt, float* dparts,
+                              int64_t R, int mode, void* stream);
+int mtfjsp_enc_gat_attend_bwd_blocks(int64_t R);
 int mtfjsp_enc_bias_tanh(float* z, const float* bias, int64_t rows, int rows_per_env, int64_t bias_rows, void* stream);
 int mtfjsp_enc_tanh_dot(const float* z, const float* w, const float* b, float* out, int64_t rows, void* stream);
 /* replaces: one Linear (+ the BatchNorm statistics pass, + the previous BatchNorm/ReLU apply pass) of

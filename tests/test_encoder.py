@@ -216,3 +216,39 @@ def test_machine_trunk_and_head_fusion_kernels_match_torch():
     close(enc.bias_tanh_(z.clone(), bias[:1].contiguous(), r), torch.tanh(z + bias[:1]))
     w2, b2 = rn(128) * 0.1, rn(1)
     close(enc.tanh_dot(z, w2, b2), torch.tanh(z) @ w2 + b2, 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gat_attend_backward_matches_torch_autograd(mode):
+    """gat_attend_train (forward kernel + hand-written backward) against autograd of the torch expression it replaces."""
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(3 + mode)
+    R = 2051
+    t0 = torch.randn(2 * R, 128, device="cuda", generator=g)
+    as0 = torch.randn(128, device="cuda", generator=g) * 0.1
+    ad0 = torch.randn(128, device="cuda", generator=g) * 0.1
+
+    def ref(t, a_src, a_dst):
+        t1, t2 = t[:R], t[R:]
+        e11 = F.leaky_relu(t1 @ a_src + t1 @ a_dst, 0.2)
+        e12 = F.leaky_relu(t1 @ a_src + t2 @ a_dst, 0.2)
+        att = torch.softmax(torch.stack((e11, e12), -1), -1)
+        h1, h2 = att[:, 0:1] * t1 + att[:, 1:2] * t2, t2
+        if mode == 0:
+            return torch.cat((h1, h2), 0)
+        if mode == 1:
+            return torch.cat((F.elu(h1), F.elu(h2)), 0)
+        return torch.stack((h1, h2), 1).mean(1)
+
+    outs = []
+    for fn in (ref, lambda t, a, b: enc.gat_attend_train(t, a, b, mode)):
+        t, a, b = t0.clone().requires_grad_(True), as0.clone().requires_grad_(True), ad0.clone().requires_grad_(True)
+        y = fn(t, a, b)
+        gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(99))
+        y.backward(gy)
+        outs.append((y.detach(), t.grad, a.grad, b.grad))
+    for x, r, name, sc in zip(outs[1], outs[0], ("y", "dt", "da_src", "da_dst"), (1.0, 1.0, R ** 0.5, R ** 0.5)):
+        np.testing.assert_allclose(x.cpu().numpy() / sc, r.cpu().numpy() / sc, rtol=0, atol=2e-4, err_msg=name)
