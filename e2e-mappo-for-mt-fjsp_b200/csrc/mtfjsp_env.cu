@@ -633,8 +633,12 @@ struct Spec {
                          O_W = O_MACC + 3 * M, O_SC = O_W + 3;
     static constexpr int O_MACH = 0, O_POS = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
     static constexpr int O_MIND = 0, O_TT = 2 * N;
+    // large instances: the pairwise-sum leaf scratch is idle at both ends of the kernel, so the warp's mbarrier (start)
+    // and the route-tail table (end) live in it -- at J30M20 that is what lets a seventh warp fit on an SM
+    static constexpr bool ALIAS = N > 128;
     static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 2) * 8, B_SI = SI * 2,
-                         B_TAIL = calign(M, 8) * 2, B_LEAF = (N > 128) ? (MAX_LEAVES + 32) * 8 : 0;
+                         B_TAIL = ALIAS ? 0 : calign(M, 8) * 2, B_LEAF = ALIAS ? (MAX_LEAVES + 32) * 8 : 0;
+    static_assert(!ALIAS || 16 + calign(M_, 8) * 2 <= (MAX_LEAVES + 32) * 8, "aliased scratch");
     static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_LEAF + B_SI + B_TAIL, 16);
     // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
     static constexpr int ENV_BYTES = (G_ == 8) ? (RAW + ((64 - RAW % 128) + 128) % 128) : RAW;
@@ -744,7 +748,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     double* __restrict__ s_pt = reinterpret_cast<double*>(base + S::B_SD + S::B_TT);
     double* s_leaf = reinterpret_cast<double*>(base + S::B_SD + S::B_TT + S::B_PT);
     int16_t* __restrict__ s_si = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF);
-    int16_t* __restrict__ s_tail = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF + S::B_SI);
+    int16_t* __restrict__ s_tail = S::ALIAS ? reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + 16)
+                                            : reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF + S::B_SI);
 
     double* g_sd = P.sd + (size_t)bc * S::SD;
     int16_t* g_si = P.si + (size_t)bc * S::SI;
@@ -771,7 +776,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     // were 5 % slower: 74.4 -> 70.5 us.)
     // the warp's mbarrier lives in the bank padding of its first env where there is one (J6M6: shared memory is exactly
     // what six blocks per SM leave), else behind the env regions
-    uint64_t* s_bar = S::BAR_IN_PAD
+    uint64_t* s_bar = S::ALIAS ? reinterpret_cast<uint64_t*>(smem_raw + (size_t)(warp * EPW) * S::ENV_BYTES + S::B_SD + S::B_TT + S::B_PT)
+                      : S::BAR_IN_PAD
                           ? reinterpret_cast<uint64_t*>(smem_raw + (size_t)(warp * EPW) * S::ENV_BYTES + S::RAW)
                           : reinterpret_cast<uint64_t*>(smem_raw + (size_t)S::WARPS * EPW * S::ENV_BYTES) + warp;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
@@ -1707,7 +1713,7 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     if (L.sd_stride != S::SD || L.si_stride != S::SI || L.xs_stride != S::XS || L.o_sc != S::O_SC || L.o_misc != S::O_MISC)
         return fail(MTFJSP_E_STATE, "specialised kernel layout mismatch");
     static const size_t extra = getenv("MTFJSP_EXTRA_SMEM") ? (size_t)atoi(getenv("MTFJSP_EXTRA_SMEM")) : 0;  // occupancy experiments
-    const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES + (S::BAR_IN_PAD ? 0 : 16 * ((S::WARPS * 8 + 15) / 16)) + extra;
+    const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES + ((S::BAR_IN_PAD || S::ALIAS) ? 0 : 16 * ((S::WARPS * 8 + 15) / 16)) + extra;
     static thread_local int configured_dev = -1;
     if (configured_dev != h->device) {
         CK(cudaFuncSetAttribute(env_kernel_s<S, MODE, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -1731,7 +1737,7 @@ static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
         if (J == 6 && M == 6) return launch_spec<Spec<6, 6, 8, 4>, MODE, OutT>(h, P, s);
         // warps per block = what keeps the most envs resident: shared memory per env is the limiter (2.4 / 5.9 / 29 KB)
         if (J == 10 && M == 10) return launch_spec<Spec<10, 10, 16, 1>, MODE, OutT>(h, P, s);
-        if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 2>, MODE, OutT>(h, P, s);
+        if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 1>, MODE, OutT>(h, P, s);
     }
     return launch_env<MODE, OutT>(h, P, s);
 }
@@ -1746,7 +1752,7 @@ static int launch_random_fused(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     int rc;
     if (J == 6 && M == 6) rc = launch_spec<Spec<6, 6, 8, 4>, MD, OutT>(h, P, s);
     else if (J == 10 && M == 10) rc = launch_spec<Spec<10, 10, 16, 1>, MD, OutT>(h, P, s);
-    else if (J == 30 && M == 20) rc = launch_spec<Spec<30, 20, 32, 2>, MD, OutT>(h, P, s);
+    else if (J == 30 && M == 20) rc = launch_spec<Spec<30, 20, 32, 1>, MD, OutT>(h, P, s);
     else return 0;
     return rc == MTFJSP_OK ? 1 : rc;
 }
