@@ -721,13 +721,8 @@ __device__ __forceinline__ double np_sum_small(const double* a, int n) {
     return res;
 }
 
-// position of the k-th (0-based) set bit of `bits`, -1 if there are not that many; J, M <= 32 bits
-__device__ __forceinline__ int kth_set_bit(unsigned bits, int k, int maxk) {
-#pragma unroll 4
-    for (int i = 0; i < maxk; i++)
-        if (i < k) bits &= bits - 1;
-    return __ffs(bits) - 1;
-}
+// position of the k-th (0-based) set bit of `bits`, -1 if there are not that many (fns.b32: n-th set bit from bit 0 up)
+__device__ __forceinline__ int kth_set_bit(unsigned bits, int k, int /*maxk*/) { return (int)__fns(bits, 0u, k + 1); }
 
 template <class S, int MODE, typename OutT>
 __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __grid_constant__ Params P) {
@@ -1048,14 +1043,20 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                     s_pt[offv + s_pos[v]] = term * 1.0;
                 }
             }
+            // the sum is a chain of dependent additions in the reference's order; x + 0.0 == x exactly (gaps are never
+            // -0.0), so the slots between this env's term count and the warp's trip count are zero-filled and the loop
+            // needs no per-term predicates: two 16-byte loads and four additions per four terms
+            const int nmax4 = (__reduce_max_sync(FULL, nsched) + 3) & ~3;
+            static_assert(N % 4 == 0, "the padded idle sum reads whole groups of four terms");
+            for (int g = nsched + gl; g < nmax4; g += G) s_pt[g] = 0.0;
             __syncwarp();
-            const int nmax = __reduce_max_sync(FULL, nsched);
             const double2* t2 = reinterpret_cast<const double2*>(s_pt);
-#pragma unroll 2
-            for (int g = 0; g < nmax; g += 2) {
-                const double2 tv = t2[g >> 1];
-                if (g < nsched) idle = idle + tv.x;
-                if (g + 1 < nsched) idle = idle + tv.y;
+            for (int g = 0; g < nmax4; g += 4) {
+                const double2 ta = t2[g >> 1], tb = t2[(g >> 1) + 1];
+                idle = idle + ta.x;
+                idle = idle + ta.y;
+                idle = idle + tb.x;
+                idle = idle + tb.y;
             }
         }
         nt = first ? 0.0 : s_tt[mp * M + mc];  // SS:872-877
