@@ -1,8 +1,11 @@
 // mtfjsp_env.cu -- batched MT-FJSP disjunctive-graph environment for sm_100a (B200).
 //
-// One warp owns one environment instance.  Per launch a warp stages its instance's records from HBM
-// into shared memory with 128-bit coalesced loads, applies the (operation, machine) action, rebuilds
-// the reward and (optionally) the observation, and writes back only the words that changed.
+// Two kernels share one algorithm.  env_kernel: one warp per environment, run-time sizes (reset, and sizes without a
+// specialisation).  env_kernel_s: compile-time (J, M), G lanes per environment and 32/G environments per warp -- the
+// hot kernel.  Per launch a lane group stages its instance's records from HBM into shared memory (one TMA bulk copy per
+// record), draws the random action itself when asked to (MODE_POLICY: random-rollout step in one launch), applies the
+// (operation, machine) action, recomputes the reward, rewrites the observation rows the step changed (or all of them)
+// and writes back only the state words that changed.
 //
 // What this replaces in the reference (file:line, "SS" = graph-jsp-env/src/graph_jsp_env/
 // disjunctive_graph_jsp_env_singlestep.py):

@@ -1,7 +1,7 @@
 """Knob experiments for the env kernel and the host-step pipeline (one process per setting; the knobs are read from
 the environment when the handle is created):
 
-    MTFJSP_PERSIST=0|1|2  MTFJSP_HOST_CHUNKS=0|1|2|4|8  python profiles/exp_knobs.py [workload] [reps]
+    MTFJSP_HOST_CHUNKS=0|1|2|4|8  MTFJSP_FUSE_POLICY=0|1  MTFJSP_OBS_INCREMENTAL=0|1  python profiles/exp_knobs.py [workload] [reps]
 
 Prints one JSON line: fused-kernel time per launch (CUDA events around each launch, recorded actions replayed),
 whole random-rollout step time, and the host-buffer step rate."""
@@ -103,7 +103,7 @@ recv = p_rec.numpy().view(env.host_record_dtype())[:, 0]
 assert float(recv["info6"][:, 1].sum()) == B and torch.equal(env.costs(), costs_ref)
 bytes_step = env.bytes_per_step()
 print(json.dumps({"workload": sys.argv[1] if len(sys.argv) > 1 else "A",
-                  "persist": os.environ.get("MTFJSP_PERSIST", "default"), "chunks": os.environ.get("MTFJSP_HOST_CHUNKS", "default"),
+                  "knobs": {k: v for k, v in os.environ.items() if k.startswith("MTFJSP_")},
                   "kernel_us": round(k_us, 2), "hbm_frac": round(bytes_step * B / (k_us * 1e-6) / 1e9 / bench.measured_peak()[0], 4),
                   "rollout_step_us": round(r_us, 2), "host_step_us": round(h_us, 2), "host_steps_per_s": round(B / (h_us * 1e-6)),
                   "packed_step_us": round(p_us, 2), "packed_steps_per_s": round(B / (p_us * 1e-6))}))
