@@ -174,6 +174,8 @@ def run_ours(args, wl):
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
     sh = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.sharding")
     J, M, E, B = wl["J"], wl["M"], wl["E"], args.batch or wl["B"]
+    if args.scaling == "strong":  # fixed total batch: the workload's env count is split over the ranks
+        B = max(1, B // world)
     N = J * M
     # weak scaling: B envs per GPU, env i of the B*world job lives on rank i // B (contiguous slices)
     first, count, d, w = sh.make_shard(B * world, rank, world, J, M, E, wl["seed"])
@@ -408,7 +410,7 @@ def run_ours(args, wl):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl["name"], "envs_per_gpu": B, "jobs": J, "machines": M, "edges": E, "obs_dtype": "f32",
                        "mask_mode": "ESA", "left_shift": True, "parallelism": "env-slices x%d (no data-path collective)" % world,
@@ -468,6 +470,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver measures): the workload's env count per GPU; strong: that count in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy", action="store_true", help="skip the actor-driven rollout measurement")
     ap.add_argument("--no-dropin", action="store_true", help="skip the Parallel_env (reference-typed) call measurement")
