@@ -1601,6 +1601,33 @@ __global__ void export_scaler_kernel(Layout L, const double* __restrict__ sd, do
     n[b] = (int64_t)s[12];
 }
 
+// Episode reset from the snapshot of the first one: the reset image of an env (initial estimates, counters, links,
+// initial makespan / energy estimates) depends on the instance only, so later resets are one coalesced copy of the env
+// part of `sd` (everything in front of the reward-scaler block; the three reward weights come from the caller), the
+// whole `si` record and the initial job masks / candidates -- instead of re-deriving them per env.
+__global__ void reset_copy_kernel(Layout L, const double* __restrict__ sd0, const int16_t* __restrict__ si0,
+                                  const double* __restrict__ weights, double* __restrict__ sd, int16_t* __restrict__ si,
+                                  uint8_t* __restrict__ jm_fin, uint8_t* __restrict__ jm_esa, int32_t* __restrict__ cand) {
+    const int wsi = L.si_stride / 4;  // si record in 8-byte words
+    const int per = L.o_sc + wsi + L.J;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)L.B * per) return;
+    const size_t b = gid / per;
+    const int i = (int)(gid - b * per);
+    if (i < L.o_sc) {
+        const size_t k = b * L.sd_stride + i;
+        sd[k] = (i >= L.o_w && i < L.o_w + 3) ? weights[b * 3 + (i - L.o_w)] : sd0[k];
+    } else if (i < L.o_sc + wsi) {
+        const size_t k = b * wsi + (i - L.o_sc);
+        reinterpret_cast<uint2*>(si)[k] = reinterpret_cast<const uint2*>(si0)[k];
+    } else {
+        const int j = i - L.o_sc - wsi;
+        jm_fin[b * L.J + j] = 0;
+        jm_esa[b * L.J + j] = 0;
+        cand[b * L.J + j] = j * L.M;
+    }
+}
+
 thread_local char g_err[512] = "";
 
 int fail(int code, const char* msg, cudaError_t e = cudaSuccess) {
@@ -1634,6 +1661,9 @@ struct mtfjsp_env {
     int device;
     double cfgw[3], divisor, gamma;
     double *sd, *xs, *t, *p;
+    double* sd0;   // reset snapshot of sd / si (taken after the first reset since the last load)
+    int16_t* si0;
+    bool reset_snap;
     int16_t* si;
     int8_t* edge_id;
     uint8_t *jm_fin, *jm_esa;
@@ -1909,6 +1939,8 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     ALLOC(h->inv, Bs);
     ALLOC(h->tmp_adj_w, Bs * N * 2 * 4);
     ALLOC(h->tmp_adj_src, Bs * N * 2);
+    ALLOC(h->sd0, Bs * L.sd_stride * 8);
+    ALLOC(h->si0, Bs * L.si_stride * 2);
 #undef ALLOC
     *out = h;
     return MTFJSP_OK;
@@ -1918,7 +1950,7 @@ int mtfjsp_destroy(mtfjsp_env* h) {
     if (!h) return MTFJSP_OK;
     cudaSetDevice(h->device);
     void* ptrs[] = {h->sd, h->si, h->xs, h->t, h->p, h->edge_id, h->jm_fin, h->jm_esa, h->cand, h->a_op, h->a_mach,
-                    h->r5, h->s4, h->info6, h->dn, h->inv, h->tmp_adj_w, h->tmp_adj_src, h->act2, h->rec};
+                    h->r5, h->s4, h->info6, h->dn, h->inv, h->tmp_adj_w, h->tmp_adj_src, h->act2, h->rec, h->sd0, h->si0};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (h->pipe) {
@@ -1962,6 +1994,7 @@ int mtfjsp_load(mtfjsp_env* h, const double* t, const double* p, const double* t
     h->loaded = true;
     h->reset_done = false;
     h->obs_synced = false;
+    h->reset_snap = false;
     return MTFJSP_OK;
 }
 
@@ -1989,12 +2022,28 @@ int mtfjsp_reset(mtfjsp_env* h, const double* weights, void* stream) {
     if (!h || !weights) return fail(MTFJSP_E_ARG, "mtfjsp_reset: bad argument");
     if (!h->loaded) return fail(MTFJSP_E_STATE, "mtfjsp_reset before mtfjsp_load");
     CK(cudaSetDevice(h->device), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    h->obs_synced = false;
+    if (h->reset_snap) {
+        const size_t total = (size_t)L.B * (L.o_sc + L.si_stride / 4 + L.J);
+        reset_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L, h->sd0, h->si0, weights, h->sd, h->si, h->jm_fin,
+                                                                      h->jm_esa, h->cand);
+        h->launches++;
+        CK(cudaGetLastError(), "reset_copy_kernel");
+        return MTFJSP_OK;
+    }
     Params P = make_params(h);
     P.weights = weights;
-    int rc = launch_env<MODE_RESET, double>(h, P, (cudaStream_t)stream);
-    h->obs_synced = false;
-    if (rc == MTFJSP_OK) h->reset_done = true;
-    return rc;
+    int rc = launch_env<MODE_RESET, double>(h, P, s);
+    if (rc != MTFJSP_OK) return rc;
+    h->reset_done = true;
+    if (!getenv("MTFJSP_RESET_SNAPSHOT") || atoi(getenv("MTFJSP_RESET_SNAPSHOT")) != 0) {
+        CK(cudaMemcpyAsync(h->sd0, h->sd, (size_t)L.B * L.sd_stride * 8, cudaMemcpyDeviceToDevice, s), "snapshot sd");
+        CK(cudaMemcpyAsync(h->si0, h->si, (size_t)L.B * L.si_stride * 2, cudaMemcpyDeviceToDevice, s), "snapshot si");
+        h->reset_snap = true;
+    }
+    return MTFJSP_OK;
 }
 
 
