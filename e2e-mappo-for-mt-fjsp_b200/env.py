@@ -175,6 +175,26 @@ class BatchedMTFJSPEnv:
                                                 _ptr(self.mach_fea), _ptr(self.adj_w), _ptr(self.adj_src), mm, self._dt,
                                                 _stream()), "mtfjsp_step_host_packed")
 
+    def host_stepper(self, records_host, mask_mode=None):
+        """Prepared form of step_host_packed for a host loop that reuses its buffers: binds everything that does not
+        change between steps once and returns `step(actions_ptr)`, where actions_ptr is the address (int) of a pinned
+        [B,2] int32 action array, e.g. `acts[s].data_ptr()`.  Saves the per-call argument marshalling (6 pointer
+        objects, stream lookup by attribute chain) of the general method -- a few microseconds of a ~170 us step."""
+        mm = self.mask_mode if mask_mode is None else mask_mode
+        fn, h = self._lib.mtfjsp_step_host_packed, self._h
+        rec, tf, mf, aw, asrc = (_ptr(x) for x in (records_host, self.task_fea, self.mach_fea, self.adj_w, self.adj_src))
+        dt = self._dt
+        keep = records_host  # the closure keeps the record buffer alive
+        cur = torch.cuda.current_stream
+
+        def step(actions_ptr):
+            rc = fn(h, actions_ptr, rec, tf, mf, aw, asrc, mm, dt, cur().cuda_stream)
+            if rc:
+                check(rc, "mtfjsp_step_host_packed")
+            return keep
+
+        return step
+
     # ---- views ---------------------------------------------------------------------------------------------------
     def dense_adj(self, dtype=torch.float64):
         adj = torch.empty((self.B, self.N, self.N), dtype=dtype, device=self.device)

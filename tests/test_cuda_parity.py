@@ -268,7 +268,10 @@ def test_host_step_equals_device_step(pinned, B, kernel_path):
         eq(h_jm.numpy(), dev_env.job_mask.cpu().numpy())
         eq(h_cd.numpy(), dev_env.candidate.cpu().numpy())
         pk_act[:, 0].copy_(op.cpu()); pk_act[:, 1].copy_(mach.cpu())
-        pk_env.step_host_packed(pk_act, pk_rec)
+        if s % 2:   # the prepared-call form and the general method are interchangeable
+            pk_env.host_stepper(pk_rec)(pk_act.data_ptr())
+        else:
+            pk_env.step_host_packed(pk_act, pk_rec)
         eq(rec["info6"], info6.numpy())
         eq(rec["candidate"].astype(np.int32), h_cd.numpy())
         eq(rec["job_mask"], h_jm.numpy())
