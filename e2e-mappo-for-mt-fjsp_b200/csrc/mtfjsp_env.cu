@@ -628,6 +628,7 @@ struct Spec {
     static constexpr int J = J_, M = M_, G = G_, N = J_ * M_, EPW = 32 / G_, WARPS = WARPS_;
     static_assert(J_ <= G_ && M_ <= G_, "one lane per job and per machine");
     static_assert(3 * M_ <= J_ * M_, "the random-step mode parks three compacted machine rows in the op scratch");
+    static_assert(J_ * M_ <= 128 || G_ == 32, "more than one numpy leaf: pairwise_sum works on a whole warp per env");
     static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 13, 2);
     static constexpr int SI = calign(3 * N + M + 3 + J, 8);
     static constexpr int XS = calign(2 * N + M * M, 2);
@@ -639,7 +640,7 @@ struct Spec {
     // large instances: the pairwise-sum leaf scratch is idle at both ends of the kernel, so the warp's mbarrier (start)
     // and the route-tail table (end) live in it -- at J30M20 that is what lets a seventh warp fit on an SM
     static constexpr bool ALIAS = N > 128;
-    static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 2) * 8, B_SI = SI * 2,
+    static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 4) * 8, B_SI = SI * 2,
                          B_TAIL = ALIAS ? 0 : calign(M, 8) * 2, B_LEAF = ALIAS ? (MAX_LEAVES + 32) * 8 : 0;
     static_assert(!ALIAS || 16 + calign(M_, 8) * 2 <= (MAX_LEAVES + 32) * 8, "aliased scratch");
     static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_LEAF + B_SI + B_TAIL, 16);
@@ -1050,7 +1051,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             // -0.0), so the slots between this env's term count and the warp's trip count are zero-filled and the loop
             // needs no per-term predicates: two 16-byte loads and four additions per four terms
             const int nmax4 = (__reduce_max_sync(FULL, nsched) + 3) & ~3;
-            static_assert(N % 4 == 0, "the padded idle sum reads whole groups of four terms");
+            static_assert(S::B_PT >= ((N + 3) & ~3) * 8, "the padded idle sum reads whole groups of four terms");
             for (int g = nsched + gl; g < nmax4; g += G) s_pt[g] = 0.0;
             __syncwarp();
             const double2* t2 = reinterpret_cast<const double2*>(s_pt);
@@ -1762,16 +1763,27 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     return MTFJSP_OK;
 }
 
-// sizes with a specialised kernel: the benchmark configurations of BASELINE.json; everything else
-// (and reset) runs the generic one-warp-per-env kernel
+// Sizes with a specialised kernel: the benchmark configurations of BASELINE.json and the size list of the reference's
+// instance generator (instance/generate_allsize_mofjsp_dataset.py:429); everything else (and the first reset) runs the
+// generic one-warp-per-env kernel.  X(J, M, lanes per env, warps per block): lanes >= max(J, M), 32 when N > 128; warps per block = what
+// keeps the most envs resident (shared memory per env is the limiter).
+#define MTFJSP_SPEC_SIZES(X) \
+    X(6, 6, 8, 4) X(10, 6, 16, 1) X(20, 6, 32, 1) X(10, 10, 16, 1) X(15, 10, 32, 1) X(20, 10, 32, 1) X(30, 20, 32, 1)
+
+static bool has_spec(int J, int M) {
+#define X(JJ, MM, GG, WW) if (J == JJ && M == MM) return true;
+    MTFJSP_SPEC_SIZES(X)
+#undef X
+    return false;
+}
+
 template <int MODE, typename OutT>
 static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     if (!(MODE & MODE_RESET) && !h->force_generic) {
         const int J = h->L.J, M = h->L.M;
-        if (J == 6 && M == 6) return launch_spec<Spec<6, 6, 8, 4>, MODE, OutT>(h, P, s);
-        // warps per block = what keeps the most envs resident: shared memory per env is the limiter (2.4 / 5.9 / 29 KB)
-        if (J == 10 && M == 10) return launch_spec<Spec<10, 10, 16, 1>, MODE, OutT>(h, P, s);
-        if (J == 30 && M == 20) return launch_spec<Spec<30, 20, 32, 1>, MODE, OutT>(h, P, s);
+#define X(JJ, MM, GG, WW) if (J == JJ && M == MM) return launch_spec<Spec<JJ, MM, GG, WW>, MODE, OutT>(h, P, s);
+        MTFJSP_SPEC_SIZES(X)
+#undef X
     }
     return launch_env<MODE, OutT>(h, P, s);
 }
@@ -1783,12 +1795,14 @@ static int launch_random_fused(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     if (h->force_generic || !h->fuse_policy) return 0;
     constexpr int MD = MODE_STEP | MODE_OBS | MODE_POLICY;
     const int J = h->L.J, M = h->L.M;
-    int rc;
-    if (J == 6 && M == 6) rc = launch_spec<Spec<6, 6, 8, 4>, MD, OutT>(h, P, s);
-    else if (J == 10 && M == 10) rc = launch_spec<Spec<10, 10, 16, 1>, MD, OutT>(h, P, s);
-    else if (J == 30 && M == 20) rc = launch_spec<Spec<30, 20, 32, 1>, MD, OutT>(h, P, s);
-    else return 0;
-    return rc == MTFJSP_OK ? 1 : rc;
+#define X(JJ, MM, GG, WW)                                                        \
+    if (J == JJ && M == MM) {                                                    \
+        const int rc = launch_spec<Spec<JJ, MM, GG, WW>, MD, OutT>(h, P, s);     \
+        return rc == MTFJSP_OK ? 1 : rc;                                         \
+    }
+    MTFJSP_SPEC_SIZES(X)
+#undef X
+    return 0;
 }
 
 // pre-step dispatch: returns 1 if a size-templated kernel was launched, 0 if the size has none, <0 on error
@@ -2379,8 +2393,7 @@ int64_t mtfjsp_bytes_per_random_step(const mtfjsp_env* h, int dtype) {
 
 int mtfjsp_random_step_is_fused(const mtfjsp_env* h) {
     if (!h || h->force_generic || !h->fuse_policy) return 0;
-    const int J = h->L.J, M = h->L.M;
-    return (J == 6 && M == 6) || (J == 10 && M == 10) || (J == 30 && M == 20);
+    return has_spec(h->L.J, h->L.M) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -13,7 +13,8 @@ envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
 enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
 
 if what in ("env", "all"):
-    for (B, J, M, E) in ((37, 6, 6, 2), (21, 10, 10, 3), (5, 30, 20, 5), (9, 4, 5, 2)):
+    for (B, J, M, E) in ((37, 6, 6, 2), (21, 10, 10, 3), (5, 30, 20, 5), (9, 4, 5, 2), (11, 10, 6, 2), (7, 20, 6, 3), (9, 15, 10, 2),
+                         (5, 20, 10, 5)):
         d = pkg.instances.synthetic_instances(0, B, J, M, E, 3)
         env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
         env.load(d["t"], d["p"], d["transT"], d["edge"])

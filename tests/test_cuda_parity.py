@@ -19,6 +19,7 @@ from tests.test_oracle_golden import check_replay  # noqa: E402
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
 eq = np.testing.assert_array_equal
+SPEC_SIZES = ((6, 6), (10, 6), (20, 6), (10, 10), (15, 10), (20, 10), (30, 20))  # sizes with a specialised kernel
 
 
 @pytest.fixture(params=["auto", "generic", "unfused", "fullobs"])
@@ -113,10 +114,16 @@ def _ell_to_dense(adj_w, adj_src):
     (1, 6, 6, 2, True, 1, 1.0, 1),
     (3, 6, 6, 2, True, 0, 1.0, 1),
     (8, 40, 8, 2, True, 0, 0.05, 1),
+    # the other sizes of the reference's instance generator (generate_allsize_mofjsp_dataset.py:429), specialised kernels
+    (33, 10, 6, 2, True, 1, 1.0, 2),
+    (17, 20, 6, 3, True, 1, 1.0, 1),
+    (13, 15, 10, 2, True, 1, 1.0, 1),
+    (13, 15, 10, 2, False, 0, 1.0, 1),
+    (9, 20, 10, 5, True, 1, 1.0, 1),
 ])
 def test_random_rollout_matches_oracle_every_step(cfg, kernel_path):
     B, J, M, E, ls, mm, scale, episodes = cfg
-    if kernel_path != "auto" and (J, M) not in ((6, 6), (10, 10), (30, 20)):
+    if kernel_path != "auto" and (J, M) not in SPEC_SIZES:
         pytest.skip("size has no specialised kernel: 'auto' already ran the generic one")
     N = J * M
     env, ora, d, w = _mk(B, J, M, E, seed=1000 + J * M, left_shift=ls, mask_mode=mm, scale=scale)
