@@ -265,11 +265,15 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
     bool valid = false, done = false;
     double mkv = 0.0, env = 0.0;
     double idle = 0.0, nt = 0.0, trans = 0.0, ec = 0.0;  // step results kept in registers for the reward epilogue
+    // incremental observation (see env_kernel_s): machine follower and route tail of the stepped op, previous transients
+    int o_next = -1, o_tail = -1, rem_prev = -1, fresh_prev = -1;
 
     if (MODE & MODE_STEP) {
         if (P.act2) { const int2 am = P.act2[b]; a = am.x; m = am.y; }
         else { a = P.op[b]; m = P.mach[b]; }
         const int nsched0 = s_misc[2];
+        rem_prev = s_misc[0];
+        fresh_prev = s_misc[1];
         double d = 0.0, pa = 0.0;
         valid = (a >= 0) && (a < N) && (m >= 0) && (m < M) && (nsched0 < N);
         if (valid) valid = (s_mach[a] < 0) && (((a % M) == 0) || (s_mach[a - 1] >= 0));
@@ -332,7 +336,11 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                     st = (y > arr_a) ? y : arr_a;
                 }
                 if (prev >= 0 && prev == a - 1 && !first) fresh = a;
+                o_tail = (where == len) ? a : lastop;
+            } else {
+                o_tail = a;
             }
+            o_next = next;
             __syncwarp();
             // ---- apply: shift route positions behind the slot, link the op in ----
             for (int v = lane; v < N; v += 32)
@@ -558,14 +566,13 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
         const int rem_head = s_misc[0], fresh = s_misc[1];
         OutT* tf = reinterpret_cast<OutT*>(P.tfea);
         const double w0 = s_w[0], w1 = s_w[1], w2 = s_w[2];
-        for (int v = lane; v < N; v += 32) {
+        auto emit_row = [&](const int v) {
             const int mv = s_mach[v];
             const bool sch = mv >= 0, vfirst = (v % M) == 0;
             const int rp = sch ? (int)s_rpred[v] : -1;
             const bool has_job = !vfirst && v != rem_head;
             const bool co = has_job && rp == v - 1;
             const bool has_m = rp >= 0 && !co;
-            if (sch && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
             if (tf) {  // SS:2246-2277
                 double f[12];
                 f[0] = s_st[v]; f[1] = s_ft[v]; f[2] = s_pt[v];
@@ -597,18 +604,37 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 reinterpret_cast<float2*>(P.adj_w)[(size_t)b * N + v] = make_float2((float)wj, (float)wm);
                 P.adj_src[(size_t)b * N + v] = (int16_t)src;
             }
+        };
+        const bool inc = (MODE & MODE_STEP) && P.obs_inc;
+        if (inc) {  // only the rows this step changed; an invalid action changed nothing
+            if (valid) {
+                for (int c = (a % M) + lane; c < M; c += 32) emit_row((a / M) * M + c);
+                const int xv = lane == 0 ? o_next : lane == 1 ? rem_prev : lane == 2 ? fresh_prev : -1;
+                if (xv >= 0) emit_row(xv);
+            }
+        } else {
+            for (int v = lane; v < N; v += 32) {
+                const int mv = s_mach[v];
+                if (mv >= 0 && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
+                emit_row(v);
+            }
         }
         __syncwarp();
         if (P.mfea) {  // SS:2315-2354
             OutT* mf = reinterpret_cast<OutT*>(P.mfea);
-            for (int mm = lane; mm < M; mm += 32) {
+            auto emit_mach = [&](const int mm, const int tail) {
                 double f[8];
                 const int c = s_cnt[mm];
-                f[0] = c > 0 ? s_ft[s_tail[mm]] : 0.0;
+                f[0] = c > 0 ? s_ft[tail] : 0.0;
                 f[1] = s_macc[mm * 3 + 0]; f[2] = s_macc[mm * 3 + 1]; f[3] = s_macc[mm * 3 + 2];
                 f[4] = (double)c;
                 f[5] = w0; f[6] = w1; f[7] = w2;
                 store_row<OutT>(mf + ((size_t)b * M + mm) * 8, f, 8);
+            };
+            if (inc) {
+                if (valid && lane == 0) emit_mach(m, o_tail);  // the one machine row the step changed
+            } else {
+                for (int mm = lane; mm < M; mm += 32) emit_mach(mm, s_cnt[mm] > 0 ? (int)s_tail[mm] : 0);
             }
         }
     }
