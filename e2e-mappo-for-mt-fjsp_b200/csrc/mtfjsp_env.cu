@@ -729,9 +729,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
+// one 64-bit value per (seed, env, step): the job draw is its high half (stream 0), the machine draw its low half (stream 1)
+__device__ __forceinline__ uint64_t rand_u64(uint64_t seed, uint64_t env, uint64_t step) {
+    return splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL));
+}
 __device__ __forceinline__ uint32_t rand_u32(uint64_t seed, uint64_t env, uint64_t step, uint64_t stream) {
-    uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL + (stream << 56)));
-    return (uint32_t)(x >> 32);
+    const uint64_t x = rand_u64(seed, env, step);
+    return stream == 0 ? (uint32_t)(x >> 32) : (uint32_t)x;
 }
 
 // numpy pairwise sum of up to M (<= 64) values held in registers/local array
@@ -827,7 +831,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const unsigned jb = (__ballot_sync(FULL, sel) >> (ge * G)) & S::GMASK;
         nsel = __popc(jb);
         const uint64_t genv = P.env_offset + (uint64_t)bc;
-        const int kj = (int)(((uint64_t)rand_u32(P.seed, genv, (uint64_t)nsel_step, 0) * (uint64_t)nsel) >> 32);
+        const uint64_t rnd = rand_u64(P.seed, genv, (uint64_t)nsel_step);
+        const int kj = (int)(((rnd >> 32) * (uint64_t)nsel) >> 32);
         const int jl = kth_set_bit(jb, kj, J);
         a = __shfl_sync(FULL, cj, jl < 0 ? 0 : jl, G);
         if (nsel == 0) a = -1;
@@ -838,7 +843,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         }
         const unsigned fb = (__ballot_sync(FULL, gl < M && tr >= 0) >> (ge * G)) & S::GMASK;
         const int nf = __popc(fb);
-        const int km = (int)(((uint64_t)rand_u32(P.seed, genv, (uint64_t)nsel_step, 1) * (uint64_t)nf) >> 32);
+        const int km = (int)(((rnd & 0xffffffffull) * (uint64_t)nf) >> 32);
         m = (nsel == 0) ? -1 : kth_set_bit(fb, km, M);
         if (active && gl == 0) { P.op_out[b] = a; P.mach_out[b] = m; }
     }

@@ -615,10 +615,11 @@ static inline uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
-/* the same counter-based action draw the CUDA policy kernel uses: key (seed, env, step, stream) */
+/* the same counter-based action draw the CUDA policy kernels use: one 64-bit value per (seed, env, step); stream 0 (the
+ * job draw) is its high half, stream 1 (the machine draw) its low half */
 uint32_t oracle_rand_u32(uint64_t seed, uint64_t env, uint64_t step, uint64_t stream) {
-    uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL + (stream << 56)));
-    return (uint32_t)(x >> 32);
+    uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + step * 0x9E3779B1ULL));
+    return stream == 0 ? (uint32_t)(x >> 32) : (uint32_t)x;
 }
 
 /* draws a uniformly random allowed job and feasible machine for env b from its current masks */
