@@ -95,11 +95,16 @@ REPLAYS = [
     ("j3m4_ls_fin_mixed", 3, 4, 2, 4, True, 0, "mixed", 1.0, 2, 105),
     ("j10m10e3_ls_esa_mixed", 10, 10, 3, 2, True, 1, "mixed", 1.0, 1, 106),
     ("j10m10e3_ls_fin_mixed", 10, 10, 3, 1, True, 0, "mixed", 1.0, 1, 107),
+    # two more sizes of the reference generator's list; J15M10 has N = 150 > 128: numpy's pairwise summation splits
+    ("j20m6e3_ls_esa_mixed", 20, 6, 3, 2, True, 1, "mixed", 1.0, 1, 108),
+    ("j15m10e2_ls_fin_mixed", 15, 10, 2, 1, True, 0, "mixed", 1.0, 1, 109),
 ]
 
 
-def gen_replays():
+def gen_replays(only=None):
     for (name, J, M, E, B, ls, mm, pol, scale, eps, seed) in REPLAYS:
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(seed)
         if (J, M, E) == (6, 6, 2):
             d = ins.reference_stream_instances(100, 6, 6, 2, seed=1)  # shipped eval set
@@ -125,5 +130,10 @@ def gen_replays():
 
 
 if __name__ == "__main__":
-    gen_pdr()
-    gen_replays()
+    import sys
+
+    if len(sys.argv) > 1:  # python gen_golden.py replay_name ...: only those fixtures
+        gen_replays(set(sys.argv[1:]))
+    else:
+        gen_pdr()
+        gen_replays()
