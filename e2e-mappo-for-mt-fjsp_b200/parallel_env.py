@@ -181,7 +181,11 @@ class Parallel_env(object):
     def DGFJSPEnv_paral_step(self, joint_actions):
         """trainer/parallel_env.py:217-269.  joint_actions: B pairs (task_index, machine_index), 0-based."""
         self._flush_scaler_reset()
-        acts = np.asarray(joint_actions, dtype=np.int32).reshape(self.batch_size, 2)
+        if isinstance(joint_actions, (list, tuple)):  # the reference's list of (task, machine) pairs: twice as fast as asarray
+            acts = np.fromiter((v for pair in joint_actions for v in pair), dtype=np.int32, count=2 * self.batch_size)
+            acts = acts.reshape(self.batch_size, 2)
+        else:
+            acts = np.asarray(joint_actions, dtype=np.int32).reshape(self.batch_size, 2)
         dev = self._env.device
         op = torch.as_tensor(np.ascontiguousarray(acts[:, 0])).to(dev)
         mc = torch.as_tensor(np.ascontiguousarray(acts[:, 1])).to(dev)
@@ -216,7 +220,8 @@ class Parallel_env(object):
         for dst, src in zip(self._pin, (adj, mfea, tfea)):
             dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return tuple(x.numpy().copy() for x in self._pin)  # fresh arrays, as the reference returns deep copies
+        # fresh arrays, as the reference returns deep copies; torch's CPU copy is multi-threaded, numpy's is not
+        return tuple(torch.empty(x.shape, dtype=x.dtype).copy_(x).numpy() for x in self._pin)
 
     def job_mask_and_candidates(self, mask_mode=MASK_ESA):
         """Kernel-computed equivalent of esa_update_chosenTaskID_CandidateTaskIDx_JobMask's return value."""
