@@ -18,6 +18,7 @@ BatchNorm uses batch statistics exactly as the reference does (its modules are n
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -502,11 +503,24 @@ class _Twin:
         _check_precision(precision, self.H)
         t = object.__new__(type(self))
         t.__dict__.update(self.__dict__)
+        t.__dict__.pop("_twins", None)
         t.w = self.w.detached()
         t.precision = precision
         t._pending = None
         t._dcache = {}
+        self.__dict__.setdefault("_twins", []).append(weakref.ref(t))  # MAPPOUpdate.update refreshes them
         return t
+
+    def refresh_twins(self):
+        """Re-derives the cached weight layouts of every live inference twin of this network (after optimiser steps)."""
+        alive = []
+        for r in self.__dict__.get("_twins", []):
+            t = r()
+            if t is not None:
+                t.refresh()
+                alive.append(r)
+        if "_twins" in self.__dict__:
+            self._twins = alive
 
     def _derived(self, name, fn):
         """Weight layouts derived for the tensor-core path (transposes, column blocks), built once per object."""

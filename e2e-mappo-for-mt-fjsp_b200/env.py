@@ -32,6 +32,13 @@ def _to_dev(x, device, dtype):
     return x.to(device=device, dtype=dtype).contiguous()
 
 
+def _on(device, *tensors):
+    """Every tensor handed to the library must live on the handle's device (raw pointers cross the C ABI)."""
+    for t in tensors:
+        if t is not None and t.device != device:
+            raise ValueError("tensor on %s passed to an environment on %s" % (t.device, device))
+
+
 class BatchedMTFJSPEnv:
     """B environments of J jobs x M operations on M machines on one GPU.
 
@@ -46,13 +53,17 @@ class BatchedMTFJSPEnv:
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedMTFJSPEnv needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedMTFJSPEnv needs a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:  # "cuda" without an index means the CURRENT device, not device 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.B, self.J, self.M, self.E, self.N = B, J, M, E, J * M
         self.obs_dtype = obs_dtype
         self._dt = F64 if obs_dtype == torch.float64 else F32
         self.mask_mode = mask_mode
         self._lib = _lib.lib()
         h = C.c_void_p()
-        check(self._lib.mtfjsp_create(C.byref(h), B, J, M, E, int(bool(left_shift)), self.device.index or 0), "mtfjsp_create")
+        check(self._lib.mtfjsp_create(C.byref(h), B, J, M, E, int(bool(left_shift)), self.device.index), "mtfjsp_create")
         self._h = h
         check(self._lib.mtfjsp_set_params(self._h, weights[0], weights[1], weights[2], scaling_divisor, gamma), "mtfjsp_set_params")
         check(self._lib.mtfjsp_set_obs_incremental(self._h, int(bool(incremental_obs))), "mtfjsp_set_obs_incremental")
@@ -110,6 +121,7 @@ class BatchedMTFJSPEnv:
 
     # ---- hot path ----------------------------------------------------------------------------------------------
     def step(self, op, mach):
+        _on(self.device, op, mach)
         check(self._lib.mtfjsp_step(self._h, _ptr(op), _ptr(mach), _ptr(self.reward5), _ptr(self.scaled4),
                                     _ptr(self.done), _ptr(self.invalid), _stream()), "mtfjsp_step")
         return self.reward5, self.scaled4, self.done, self.invalid
@@ -122,12 +134,14 @@ class BatchedMTFJSPEnv:
 
     def step_obs(self, op, mach, mask_mode=None):
         mm = self.mask_mode if mask_mode is None else mask_mode
+        _on(self.device, op, mach)
         check(self._lib.mtfjsp_step_obs(self._h, _ptr(op), _ptr(mach), _ptr(self.reward5), _ptr(self.scaled4),
                                         _ptr(self.done), _ptr(self.invalid), _ptr(self.task_fea), _ptr(self.mach_fea),
                                         _ptr(self.adj_w), _ptr(self.adj_src), _ptr(self.job_mask), _ptr(self.candidate),
                                         mm, self._dt, _stream()), "mtfjsp_step_obs")
 
     def mfea1(self, op):
+        _on(self.device, op)
         check(self._lib.mtfjsp_mfea1(self._h, _ptr(op), _ptr(self.mfea1_buf), _ptr(self.mach_mask), self._dt, _stream()),
               "mtfjsp_mfea1")
         return self.mfea1_buf, self.mach_mask

@@ -89,6 +89,36 @@ def reference_stream_instances(samples: int, n_job: int, n_machine: int, n_edge:
     return dict(t=t, p=p, transT=tt, edge=edge)
 
 
+def save_instances(path: str, data: dict) -> None:
+    """The reference's wire format (generate_...py:286-296): a pickled list of four arrays
+    ``[t [S,N,M] f64, p [S,N,M] f64, transT [S,M,M] f64, edge [S,E,W] int64]``.  Ragged edge groups (M % E != 0) are
+    written padded with -1, which the reference generator cannot express at all ("J10M10E3")."""
+    import pickle
+
+    arr = [np.asarray(data["t"], dtype=np.float64), np.asarray(data["p"], dtype=np.float64),
+           np.asarray(data["transT"], dtype=np.float64), np.asarray(data["edge"], dtype=np.int64)]
+    with open(path, "wb") as f:
+        pickle.dump(arr, f)
+
+
+def load_instances(path: str) -> dict:
+    """Reads a reference instance pickle (generate_...py:298-316: ``t, p, transT, edge = pickle.load(f)``)."""
+    import pickle
+
+    with open(path, "rb") as f:
+        t, p, tt, edge = pickle.load(f)
+    t, p, tt = (np.ascontiguousarray(x, dtype=np.float64) for x in (t, p, tt))
+    edge = np.asarray(edge)
+    if edge.dtype == object:  # ragged lists written by old numpy: pad with -1
+        W = max(len(g) for inst in edge for g in inst)
+        pad = np.full((len(edge), len(edge[0]), W), -1, dtype=np.int32)
+        for s_, inst in enumerate(edge):
+            for g_, grp in enumerate(inst):
+                pad[s_, g_, :len(grp)] = grp
+        edge = pad
+    return dict(t=t, p=p, transT=tt, edge=np.ascontiguousarray(edge, dtype=np.int32))
+
+
 _BLOCK = 1024
 
 

@@ -49,6 +49,8 @@ class PPOConfig:
     use_grad_clip: bool = True
     clip_grad: float = 0.5
     matmul_tf32: bool = False   # library GEMMs of the update on TF32 tensor cores (the reference computes in FP32)
+    recompute_old_logp: bool = False  # re-evaluate the behaviour log-probabilities with the update's own arithmetic
+                                      # before the first epoch (rollouts collected by a lower-precision twin)
     encoder_tf32: bool = False  # every [rows,128] x [128,<=128] product of the update (graph encoders, GAT projections,
                                 # policy heads; > 95 % of its FLOPs) forward + backward on the hand-written tcgen05 TF32
                                 # kernels instead of library FP32 GEMMs under autograd
@@ -58,9 +60,12 @@ def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def allreduce_mean_grads(params, timer=None):
+def allreduce_mean_grads(params, timer=None, weight=None):
     """One flat NCCL/gloo allreduce over every gradient that exists, then the mean.
-    timer: optional list that receives a (start, end) CUDA event pair around the collective."""
+    timer: optional list that receives a (start, end) CUDA event pair around the collective.
+    weight: this rank's share of the mean times the world size (B_local * world / B_total); None = equal shards.  Each
+    rank's loss is a mean over ITS envs, so with unequal shards (total_envs % world != 0) the plain mean over ranks would
+    over-weight the envs of the smaller shards."""
     ws = _world()
     if ws == 1:
         return 0
@@ -68,6 +73,8 @@ def allreduce_mean_grads(params, timer=None):
     if not grads:
         return 0
     flat = torch.cat([g.reshape(-1) for g in grads])
+    if weight is not None and weight != 1.0:
+        flat.mul_(weight)
     if timer is not None and flat.is_cuda:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -99,6 +106,17 @@ class MAPPOUpdate:
         self.sched = [sch(self.opt_job), sch(self.opt_mch), sch(self.opt_critic)]
         self.allreduce_bytes = 0
         self.allreduce_events = []   # (start, end) CUDA events of every gradient allreduce, for the time-share report
+        self._shard_weight = {}      # B_local -> B_local * world / B_total (one tiny allreduce per batch size)
+
+    def _grad_weight(self, B, device):
+        ws = _world()
+        if ws == 1:
+            return None
+        if B not in self._shard_weight:
+            tot = torch.tensor([float(B)], dtype=torch.float64, device=device)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            self._shard_weight[B] = B * ws / float(tot.item())
+        return self._shard_weight[B]
 
     # ---- values and advantages (ppo_algorithm.py:585-703), no gradients ---------------------------------------------
     def _critic_all(self, task_fea, adj_w, adj_src, mf1, mf2):
@@ -205,7 +223,8 @@ class MAPPOUpdate:
             tot_j += lj.detach()
             tot_m += lm.detach()
             del nodes_m, pooled_m, pm, gm, prob_j, prob_m, pooled_o, job_v, mch_v, dist_j, dist_m, ratio_j, ratio_m, glob_j, glob_m, loc_j, loc_m, crit_j, crit_m, lj, lm
-        self.allreduce_bytes += allreduce_mean_grads(self.job.parameters() + self.mch.parameters(), self.allreduce_events)
+        gw = self._grad_weight(B, dev)
+        self.allreduce_bytes += allreduce_mean_grads(self.job.parameters() + self.mch.parameters(), self.allreduce_events, gw)
         self.opt_job.step()
         self.opt_mch.step()
 
@@ -224,7 +243,7 @@ class MAPPOUpdate:
             crit.backward()
             tot_c += crit.detach()
             del v_s, crit
-        self.allreduce_bytes += allreduce_mean_grads(self.critic.parameters(), self.allreduce_events)
+        self.allreduce_bytes += allreduce_mean_grads(self.critic.parameters(), self.allreduce_events, gw)
         if c.use_grad_clip:
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), c.clip_grad)                   # :993-996
         self.opt_critic.step()
@@ -240,9 +259,51 @@ class MAPPOUpdate:
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(c.matmul_tf32)
         try:
+            if c.recompute_old_logp:
+                self.recompute_old_logp(bt)
             return self._update(bt, mini_bs, orders, generator, T, dev)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+            # the rollout twins cache re-laid-out copies of some weights (first-layer column blocks, GAT transpose):
+            # without this the next rollout would mix stale and fresh weights
+            for net in (self.job, self.mch, self.critic):
+                if hasattr(net, "refresh_twins"):
+                    net.refresh_twins()
+
+    def recompute_old_logp(self, bt):
+        """Overwrites bt["log_a"] / bt["m_log_a"] with the log-probabilities of the stored actions under the CURRENT
+        weights evaluated by the update's own arithmetic (FP32 library GEMMs, or the tcgen05 training path), in rollout
+        order: step t's job head receives the machine embedding of step t-1, the first step of an episode the learned
+        `_input` vector (Run.py:316-363).  The reference rolls out and updates with one network, so its importance ratio
+        starts at exactly 1; a rollout collected by the TF32 inference twin would otherwise start a few percent off."""
+        T, B, N = bt["task_fea"].shape[:3]
+        J, M, H = self.job.J, self.job.M, self.job.H
+        cs = max(1, self.max_rows // (B * N))
+        ep0 = bt.get("episode_start")
+        with torch.no_grad():
+            inp = self.job.w["_input"].detach()[None, None, :].expand(1, B, H)
+            prev = None  # pooled machine embedding of the step before the chunk
+            for s0 in range(0, T, cs):
+                s1 = min(T, s0 + cs)
+                g = s1 - s0
+                nodes_m, pooled_m = self.mch.trunk(bt["mach_fea1"][s0:s1].reshape(-1, M, 6),
+                                                   bt["mach_fea2"][s0:s1].reshape(-1, M, 8), groups=g)
+                pm = pooled_m.reshape(g, B, H)
+                gm = torch.cat((inp if prev is None else prev, pm[:-1]), dim=0).clone()
+                for t in range(s0, s1):
+                    first = (t % N == 0) if ep0 is None else bool(ep0[t])
+                    if first:
+                        gm[t - s0] = inp[0]
+                prev = pm[-1:].clone()
+                prob_j, pooled_o, _ = self.job.evaluate(
+                    bt["task_fea"][s0:s1].reshape(g * B, N, -1), bt["adj_w"][s0:s1].reshape(g * B, N, 2),
+                    bt["adj_src"][s0:s1].reshape(g * B, N), bt["candidate"][s0:s1].reshape(g * B, J), gm.reshape(g * B, H),
+                    bt["job_mask"][s0:s1].reshape(g * B, J), groups=g)
+                prob_m, _ = self.mch.heads(nodes_m, pooled_m, pooled_o, bt["mach_mask"][s0:s1].reshape(g * B, M))
+                la = torch.log(prob_j.gather(1, bt["a_job"][s0:s1].reshape(-1, 1).long()).squeeze(-1))
+                mla = torch.log(prob_m.gather(1, bt["a_mach"][s0:s1].reshape(-1, 1).long()).squeeze(-1))
+                bt["log_a"][s0:s1].copy_(la.reshape(g, B))
+                bt["m_log_a"][s0:s1].copy_(mla.reshape(g, B))
 
     def _update(self, bt, mini_bs, orders, generator, T, dev):
         c = self.cfg
@@ -328,6 +389,11 @@ def collect(rollout, weights_per_episode):
 
 
 def train_iteration(rollout, updater, weights_per_episode, mini_bs=None):
-    """One buffer of experience followed by one PPO update (the body of the reference's training loop, Run.py:530-560)."""
+    """One buffer of experience followed by one PPO update (the body of the reference's training loop, Run.py:530-560).
+    `update` refreshes the rollout's inference twins afterwards, so the next call rolls out with the new weights.  When
+    the rollout runs on a different arithmetic path than the update (TF32 twin vs FP32 / tcgen05 training path), the
+    behaviour log-probabilities are re-evaluated on the update's path first (MAPPOUpdate.recompute_old_logp)."""
     bt = collect(rollout, weights_per_episode)
+    if getattr(rollout.job, "precision", "fp32") != "fp32" and not updater.cfg.recompute_old_logp:
+        updater.recompute_old_logp(bt)
     return updater.update(bt, mini_bs or rollout.env.N)

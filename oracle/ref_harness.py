@@ -143,6 +143,78 @@ class RefJobMask:
         return cand, mask
 
 
+def load_ppo_algorithm():
+    """The reference's ``algorithm.ppo_algorithm`` module, importable on CPU with two module shims
+    (trainer.train_device, trainer.fig_kpi)."""
+    if "ppo" in _loaded:
+        return _loaded["ppo"]
+    load_reference()
+    import contextlib
+    import io
+
+    import torch
+
+    td = types.ModuleType("trainer.train_device")
+    td.device = torch.device("cpu")
+    sys.modules.setdefault("trainer.train_device", td)
+    if "trainer.fig_kpi" not in sys.modules:
+        fk = types.ModuleType("trainer.fig_kpi")
+        fk.get_GPU_usage = lambda *a, **k: None
+        fk.result_box_plot = lambda *a, **k: None
+        sys.modules["trainer.fig_kpi"] = fk
+    with contextlib.redirect_stdout(io.StringIO()):
+        from algorithm import ppo_algorithm
+    _loaded["ppo"] = ppo_algorithm
+    return ppo_algorithm
+
+
+class RealJobMask:
+    """The reference's OWN candidate / job-mask method -- ``PPOAlgorithm.esa_update_chosenTaskID_CandidateTaskIDx_JobMask``
+    (algorithm/ppo_algorithm.py:202-317) and ``set_to_0`` (:1126-1165) -- called on an instance made with
+    ``object.__new__`` (the constructor builds all networks and calls ``.cuda()``).  The method's own ``.cuda()`` calls
+    are answered by a no-op ``Tensor.cuda`` while it runs (this container has no GPU).  Same interface as RefJobMask."""
+
+    def __init__(self, n_job, n_machine, batch):
+        pa = load_ppo_algorithm()
+        self.J, self.M, self.B = n_job, n_machine, batch
+        ppo = object.__new__(pa.PPOAlgorithm)
+        ppo.n_job, ppo.n_machine, ppo.n_total_task, ppo.batch_size = n_job, n_machine, n_job * n_machine, batch
+        ppo.pool_task_list = [1 + n_machine * i for i in range(n_job)]  # ppo_algorithm.py:158
+        self.ppo = ppo
+        self.set_to_0()
+
+    class _cpu_cuda:
+        def __enter__(self):
+            import torch
+
+            self._orig = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda t, *a, **k: t
+        def __exit__(self, *exc):
+            import torch
+
+            torch.Tensor.cuda = self._orig
+
+    def set_to_0(self):
+        with self._cpu_cuda():
+            self.ppo.set_to_0(None)
+
+    @property
+    def mask_new(self):
+        return self.ppo.mask_new_batch.numpy()
+
+    def initial(self):
+        cand = np.array([list(d.values()) for d in self.ppo.pool_task_dict_batch]) - 1
+        return cand, self.ppo.mask_new_batch.bool().numpy().copy()
+
+    def update(self, paralenv, action_batch, mask_value=1):
+        import torch
+
+        with self._cpu_cuda():
+            cand, mask = self.ppo.esa_update_chosenTaskID_CandidateTaskIDx_JobMask(
+                paralenv, torch.as_tensor(np.asarray(action_batch)), mask_value)
+        return np.asarray(cand), mask.numpy().copy()
+
+
 def ref_state_dump(env, N, M):
     """Schedule state of one reference env in array form (0-based op indices)."""
     mach = np.array([env.G.nodes[i + 1]["machine"] for i in range(N)], dtype=np.int32)
@@ -158,7 +230,7 @@ def ref_state_dump(env, N, M):
 
 def replay(n_job, n_machine, n_edge, t, p, tt, edge, weights, actions=None, left_shift=True, rng=None,
            mask_mode=1, cfg_weights=(0.4, 0.4, 0.2), gamma=0.99, episodes=1, dump_state=True,
-           machine_policy="random"):
+           machine_policy="random", obs_steps=None):
     """Runs the reference ``Parallel_env`` on the given instance batch and records every output.
 
     t, p: [B,N,M]; tt: [B,M,M]; edge: list of B ragged lists (E groups of machine ids);
@@ -166,7 +238,10 @@ def replay(n_job, n_machine, n_edge, t, p, tt, edge, weights, actions=None, left
     from python's global ``random``; injecting keeps the run reproducible);
     actions: optional [episodes,N,B,2] (op, machine); if None, uniformly random valid actions
     under the job mask (mask_mode 1 = ESA rule, 0 = finished-only) are drawn from ``rng``;
-    machine_policy "random" | "lowest" | "mixed" picks among the feasible machines.
+    machine_policy "random" | "lowest" | "mixed" picks among the feasible machines;
+    obs_steps: optional sorted list of step indices -- the bulky per-step dumps (observation arrays, full schedule
+    state) are then kept for those steps only (large instances: a J30M20 episode is 600 steps of 600-row arrays);
+    actions, candidate-machine features, step info, candidates and masks are always kept for every step.
     Returns a dict of stacked numpy arrays.
     """
     ref = load_reference()
@@ -203,8 +278,13 @@ def replay(n_job, n_machine, n_edge, t, p, tt, edge, weights, actions=None, left
         tfea_cur = np.concatenate(tf_l, 0)
         for rs in pe.paral_Rscaling_instance:
             rs.reset()
-        jm = RefJobMask(J, M, B)
+        # the golden masks / candidates come from the reference's own method; the restated rule (RefJobMask) rides along
+        # and must agree with it at every step
+        jm = RealJobMask(J, M, B)
+        jm_restated = RefJobMask(J, M, B)
         cand, mask = jm.initial()
+        c2, m2 = jm_restated.initial()
+        assert np.array_equal(cand, c2) and np.array_equal(mask, m2)
         for step in range(N):
             if actions is not None:
                 act = np.asarray(actions[ep][step])
@@ -228,11 +308,16 @@ def replay(n_job, n_machine, n_edge, t, p, tt, edge, weights, actions=None, left
             mfea1 = pe.cal_cur_task_machine_feature(torch.tensor(ops), mmask, tfea_cur)
             adj_, info, mfea2_, tfea_ = pe.DGFJSPEnv_paral_step(list(zip(ops.tolist(), mch.tolist())))
             cand, mask = jm.update(pe, jobs)
+            c2, m2 = jm_restated.update(pe, jobs)
+            assert np.array_equal(cand, c2) and np.array_equal(mask, m2) and np.array_equal(jm.mask_new, jm_restated.mask_new), \
+                ("restated job-mask rule differs from PPOAlgorithm.esa_update_chosenTaskID_CandidateTaskIDx_JobMask", ep, step)
             tfea_cur = tfea_
             out["actions"].append(np.stack([ops, mch], 1)); out["mfea1"].append(mfea1)
-            out["adj"].append(adj_); out["tfea"].append(tfea_); out["mfea2"].append(mfea2_)
             out["info"].append(np.array(info, dtype=np.float64)); out["cand"].append(cand.copy()); out["mask"].append(mask.copy())
-            if dump_state:
+            keep = obs_steps is None or step in obs_steps
+            if keep:
+                out["adj"].append(adj_); out["tfea"].append(tfea_); out["mfea2"].append(mfea2_)
+            if dump_state and keep:
                 ds = [ref_state_dump(e, N, M) for e in pe.paral_env_DG]
                 out["mach"].append(np.stack([d[0] for d in ds])); out["st"].append(np.stack([d[2] for d in ds]))
                 out["ft"].append(np.stack([d[3] for d in ds])); out["routes"].append(np.stack([d[4] for d in ds]))
@@ -245,6 +330,10 @@ def replay(n_job, n_machine, n_edge, t, p, tt, edge, weights, actions=None, left
         a = np.stack(v)
         if k in ("adj0", "tfea0", "mfea20", "costs"):
             res[k] = a  # [episodes, ...]
+        elif obs_steps is not None and k in ("adj", "tfea", "mfea2", "mach", "st", "ft", "routes"):
+            res[k] = a.reshape((episodes, len(obs_steps)) + a.shape[1:])
         else:
             res[k] = a.reshape((episodes, N) + a.shape[1:])
+    if obs_steps is not None:
+        res["obs_steps"] = np.asarray(sorted(obs_steps), dtype=np.int32)
     return res

@@ -98,7 +98,12 @@ REPLAYS = [
     # two more sizes of the reference generator's list; J15M10 has N = 150 > 128: numpy's pairwise summation splits
     ("j20m6e3_ls_esa_mixed", 20, 6, 3, 2, True, 1, "mixed", 1.0, 1, 108),
     ("j15m10e2_ls_fin_mixed", 15, 10, 2, 1, True, 0, "mixed", 1.0, 1, 109),
+    # BASELINE.json configs[3]: N = 600 (5 numpy pairwise leaves, the 32-lane kernel with aliased scratch).  One env, one
+    # episode = 600 reference steps at ~0.3 s; the bulky dumps are kept at SPARSE_STEPS only
+    ("j30m20e5_ls_esa_mixed", 30, 20, 5, 1, True, 1, "mixed", 1.0, 1, 110),
 ]
+# steps whose full observation / schedule state a large fixture keeps (all steps below N = 200)
+SPARSE_STEPS = sorted(set(range(0, 24)) | set(range(24, 600, 24)) | set(range(585, 600)))
 
 
 def gen_replays(only=None):
@@ -116,7 +121,7 @@ def gen_replays(only=None):
         w = rng.random((eps, B, 3))
         w = w / w.sum(-1, keepdims=True)
         r = rh.replay(J, M, E, t, p, tt, [edge[b] for b in range(B)], w, rng=rng, left_shift=ls, mask_mode=mm,
-                      episodes=eps, machine_policy=pol)
+                      episodes=eps, machine_policy=pol, obs_steps=SPARSE_STEPS if J * M > 200 else None)
         adj = r.pop("adj"); adj0 = r.pop("adj0")
         assert np.array_equal(adj, adj.astype(np.int32)) and np.array_equal(adj0, adj0.astype(np.int32))
         out = dict(t=t, p=p, transT=tt, edge=edge, weights=w, J=J, M=M, E=E, left_shift=ls, mask_mode=mm,

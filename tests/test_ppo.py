@@ -169,6 +169,28 @@ def test_parameters_actually_move():
     assert np.abs(p["job/" + k] - sd[k].numpy()).max() > 1e-3
 
 
+def test_refresh_twins_rederives_cached_layouts():
+    """an inference twin caches re-laid-out copies of some weights; after the optimiser moved the
+    shared storage, `refresh_twins()` on the trained network (called by MAPPOUpdate.update) must bring them up to date."""
+    H, J, M = 32, 3, 3
+    job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 1), J, M, hidden=H, device="cpu", trainable=True)
+    twin = job.inference_twin("fp32")
+    W0 = twin.w["o_policy.linears.0.weight"]
+    blk = twin._derived("o_policy.W0a", lambda: W0[:, :H])
+    assert blk.data_ptr() != W0.data_ptr() and torch.equal(blk, W0[:, :H])
+    with torch.no_grad():
+        job.w["o_policy.linears.0.weight"].add_(1.0)          # what an optimiser step does: in place, same storage
+    assert not torch.equal(blk, W0[:, :H])                     # the cached copy is stale now ...
+    job.refresh_twins()
+    assert torch.equal(blk, W0[:, :H])                         # ... and current again, in the same tensor (graph-safe)
+    del twin, blk, W0
+    import gc
+
+    gc.collect()
+    job.refresh_twins()                                        # dead twins are dropped, not dereferenced
+    assert job._twins == []
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("max_rows", [1 << 21, 7 * 4 * 36])
 def test_update_matches_reference_on_device(max_rows):
@@ -248,6 +270,55 @@ def test_collect_feeds_update_consistently():
     after = job.state_dict()
     moved = max(float((after[k] - before[k]).abs().max()) for k in before if enc._Params.is_parameter(k))
     assert moved > 1e-4
+
+
+@pytest.mark.gpu
+def test_train_iteration_with_tf32_twins_refreshes_them_and_starts_at_ratio_one():
+    """ADVICE r1: (high) `train_iteration` leaves the TF32 rollout twins consistent with the updated weights;
+    (medium) the behaviour log-probabilities of a TF32-twin rollout are re-evaluated on the update's own path, so the
+    importance ratios of the first minibatch start at 1 (|log ratio| < 2e-4) instead of a few percent off."""
+    dev = torch.device("cuda", 0)
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
+    rom = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
+    B, J, M, E, H = 256, 6, 6, 2, 128
+    N = J * M
+    d = ins.synthetic_instances(0, B, J, M, E, 5)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(H), 1), J, M, hidden=H, trainable=True)
+    mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(H), 2), M, hidden=H, trainable=True)
+    crit = enc.GlobalCritic(enc.seeded_state_dict(enc.global_critic_keys(H), 3), J, M, hidden=H, trainable=True)
+    tj, tm = job.inference_twin("tf32"), mch.inference_twin("tf32")
+    ro = rom.Rollout(env, tj, tm, greedy=False, seed=9)
+    ws = [ins.random_weights(0, B, 100)]
+    bt = ppo.collect(ro, ws)
+    raw_la = bt["log_a"].clone()
+    up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=1))
+    up.recompute_old_logp(bt)
+    drift = float((bt["log_a"] - raw_la).abs().max())
+    assert 0 < drift < 0.2, drift                              # TF32 vs FP32 policies differ, by a bounded amount
+    seen = []
+    orig = torch.exp
+
+    def spy(x):
+        seen.append(x.detach().clone())
+        return orig(x)
+
+    ppo.torch.exp = spy
+    try:
+        up.update(bt, N, orders=[list(range(N))])
+    finally:
+        ppo.torch.exp = orig
+    assert float(seen[0].abs().max()) < 2e-4 and float(seen[1].abs().max()) < 2e-4
+    for twin in (tj, tm):                                      # every cached layout equals its source after the update
+        assert twin._dcache
+        for t, fn in twin._dcache.values():
+            assert torch.equal(t, fn().contiguous())
+    # and a second whole iteration runs on the refreshed twins
+    mean, _ = ppo.train_iteration(ro, up, ws)
+    assert bool(torch.isfinite(mean).all())
 
 
 @pytest.mark.gpu
