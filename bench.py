@@ -7,7 +7,12 @@ everything the environment side of Run.py's rollout loop does per step (SURVEY.m
 one launch of the fused kernel for the sizes that have a specialised one.  Episodes wrap inside the timed
 region: every N = J*M steps the batch is reset (two more launches), as the reference's loop does.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|B|C]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|B|C] [--repeats R]
+
+The K-step timed region (barrier + synchronize on both sides, CUDA events, max over ranks) is repeated R >= 15 times
+and the MEDIAN is reported, so that short runs (--steps 20 is a 1.8 ms region) are stable to < 2 %.  At N = 1 the same
+invocation also measures BASELINE.json's configs[2] and configs[3] (`workloads`: J10M10E3 / 16,384 envs and J30M20E5 /
+4,096 envs) and the transition kernel alone (`roofline.step_only`, north_star's ">= 50 % on the step kernel").
 
 N > 1 is launched by the driver with torch.distributed.run; each rank owns its own env slice (weak
 scaling, no data-path collective; NCCL is used only for the barrier and the max-over-ranks time).
@@ -35,6 +40,46 @@ WORKLOADS = {
 }
 METRIC = "MT-FJSP env-steps/sec"
 UNIT = "env-steps/s"
+
+
+def workload_config(wl, B, world):
+    """The `config` object of both arms (ours and --impl reference): it names the workload only, so the driver's
+    same-config check compares like with like."""
+    J, M, E = wl["J"], wl["M"], wl["E"]
+    N = J * M
+    survey = 8 + 2 * (18 * N + 42 * M + 8 * J + (N + 7) // 8 + 160) + (48 * N + 18 * N + 32 * M + 5 * J + 41)
+    return {"workload": wl["name"], "envs_per_gpu": B, "jobs": J, "machines": M, "edges": E, "obs_dtype": "f32",
+            "mask_mode": "ESA", "left_shift": True, "n_gpus": world,
+            "l2": "working set %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (B * (survey + 2000) / 1e6)}
+
+
+def needed_bytes(J, M, fe, policy, rows_t, rows_a, rows_m):
+    """Bytes ONE env-step of the incremental algorithm has to move (DESIGN.md "Roofline accounting"): the whole state is
+    read (the reward needs the makespan and energy estimates over all ops), only what the step changes is written.
+    State sizes are SURVEY.md 8(d)'s minimal array form, not this implementation's (fatter) records.
+      read    B_state = 18N + 42M + 8J + ceil(N/8) + 160; the action (8) and t, p at (op, machine) (16) -- or, when the
+              kernel draws the random action itself: job mask J + candidates 4J + step counter 2 + the op's t / p rows 16M
+              + edge ids M
+      write   changed state words 206 (op: machine, start, finish, link + successor's link 19; route count 2; scheduled
+              bit 1; job's last finish 8; 4 scalars 32; one machine's accumulators 40; reward scaler 104)
+              + 5 rewards, done 41 + 4 scaled rewards 32 + job mask and candidates 5J
+              + changed observation rows (measured by diffing consecutive observations over one episode):
+                rows_t x 12 fe + rows_a x 10 (ELL adjacency) + rows_m x 8 fe
+              + with the in-kernel policy: the action 8, candidate-machine features 6 fe M, machine mask M"""
+    N = J * M
+    b_state = 18 * N + 42 * M + 8 * J + (N + 7) // 8 + 160
+    rd = b_state + ((5 * J + 2 + 17 * M) if policy else 24)
+    wr = 206 + 41 + 32 + 5 * J + rows_t * 12 * fe + rows_a * 10 + rows_m * 8 * fe
+    if policy:
+        wr += 8 + 6 * fe * M + M
+    return {"total": rd + wr, "read": rd, "write": wr, "b_state": b_state,
+            "changed_rows_per_step": {"task_fea": rows_t, "adjacency": rows_a, "mach_fea": rows_m}}
+
+
+def median(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return xs[n // 2] if n % 2 else 0.5 * (xs[n // 2 - 1] + xs[n // 2])
 
 
 def measured_peak():
@@ -116,13 +161,56 @@ def cpu_port_rate(wl, nthreads, target_seconds):
     return rate, "%d envs x 4 episodes x %d steps (%s), %d thread(s)" % (B, N, wl["name"].split(",")[0], nthreads)
 
 
+def real_reference_rate(seconds=12.0):
+    """SURVEY.md 8(d) i-ii: the UNMODIFIED Python reference (trainer/parallel_env.Parallel_env over networkx, batch 16,
+    J6M6E2 instances of the shipped generator's seed-0 stream, random valid actions under the ESA mask) timed on this
+    box's host cores: one process = one core (how the reference runs), then one process per core.  Needs the reference
+    tree under baseline/_ref (git-ignored copy made by __graft_entry__.build() where /root/reference exists)."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "graph-jsp-env", "src", "graph_jsp_env")):
+        return None
+    script = os.path.join(ROOT, "oracle", "time_reference.py")
+    env = dict(os.environ, MTFJSP_REFERENCE_ROOT=ref_root, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+
+    def run(nproc):
+        ps = [subprocess.Popen([sys.executable, script, "--seconds", str(seconds), "--seed", str(p)], env=env,
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for p in range(nproc)]
+        rates = []
+        for pr in ps:
+            out, _ = pr.communicate(timeout=seconds * 6 + 120)
+            for ln in out.splitlines():
+                if ln.startswith("{"):
+                    rates.append(json.loads(ln)["env_steps_per_s"])
+        return rates
+
+    try:
+        one = run(1)
+        allc = run(cores)
+    except Exception as e:  # a baseline leg must never take the bench line down
+        return {"error": repr(e)[:200]}
+    if not one or not allc:
+        return {"error": "reference timing produced no output"}
+    return {"value": one[0], "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "unmodified trainer/parallel_env.Parallel_env, 16 envs J6M6E2 (generator seed 0), whole random "
+                      "episodes for %.0f s incl. cal_cur_task_machine_feature + job-mask update" % seconds,
+            "all_cores": {"value": sum(allc), "cores": cores, "processes": len(allc)}}
+
+
 def run_reference(args, wl):
-    """--impl reference: the reference's algorithm on the host cores.  The reference itself is Python over
-    networkx and cannot travel to the GPU box; this times its C restatement (oracle/, kind 'port') with all
-    host threads on a bounded sample per step."""
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself is Python over networkx
+    (157 env-steps/s per core); this arm times its C restatement (oracle/, kind 'port') with all host
+    threads on the SAME workload, batch and step definition as our arm: one step = one env-step of every env of the
+    batch (random valid action + candidate-machine features + transition + reward + scaling + observation + mask)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle.mtfjsp_oracle import OracleEnv
+
+    ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
     # every host core this process may run on (torchrun exports OMP_NUM_THREADS=1; the oracle's parallel loops take an
     # explicit thread count, so that default does not starve the reference arm)
     try:
@@ -130,25 +218,201 @@ def run_reference(args, wl):
     except AttributeError:
         cores = os.cpu_count() or 1
     cores = max(1, cores)
-    rates = []
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_port_rate(wl, cores, 1.0)
-    t0 = time.perf_counter()
-    sample = ""
-    for _ in range(max(1, min(args.steps, 5))):
-        r, sample = cpu_port_rate(wl, cores, 4.0)
-        rates.append(r)
-    rates.sort()
-    val = rates[len(rates) // 2]
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": wl["name"], "note": "CPU restatement of the reference env (oracle/, OpenMP over envs); "
-                       "the Python reference itself measured ~157 env-steps/s/core at survey time (BASELINE.md)"},
+    J, M, E, B = wl["J"], wl["M"], wl["E"], args.batch or wl["B"]
+    N = J * M
+    d = ins.synthetic_instances(0, B, J, M, E, wl["seed"])
+    w = ins.random_weights(0, B, wl["seed"])
+    o = OracleEnv(B, J, M, E, left_shift=True, nthreads=cores)
+    o.load(d["t"], d["p"], d["transT"], d["edge"])
+    o.scaler_init()
+    o.reset(w)
+    st = {"s": 0}
+
+    def steps(n):
+        while n > 0:
+            if st["s"] == N:
+                o.reset(w); o.scaler_reset(); st["s"] = 0
+            k = min(n, N - st["s"])
+            o.rollout_random(k, seed=1234)
+            st["s"] += k
+            n -= k
+
+    K, W = args.steps, max(args.warmup, 3)
+    t_all = time.perf_counter()
+    steps(W)
+    times = []
+    # bounded: the whole arm ends within a few minutes whatever K is
+    while len(times) < args.repeats and (len(times) < 3 or time.perf_counter() - t_all < 150.0):
+        t0 = time.perf_counter()
+        steps(K)
+        times.append(time.perf_counter() - t0)
+    sec = median(times)
+    val = B * K / sec
+    sample = "%d envs x %d steps per timed region, median of %d regions (%s), %d thread(s)" % (
+        B, K, len(times), wl["name"].split(",")[0], cores)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": sec * 1e3 / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "config": workload_config(wl, B, args.gpus),
+            "note": "CPU restatement of the reference env (oracle/, OpenMP over envs); the Python reference itself runs "
+                    "~157 env-steps/s/core (BASELINE.md; re-timed on this box in our arm's cpu_baseline_reference)",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.perf_counter() - t0}
+            "repeats": len(times), "wall_s": time.perf_counter() - t_all}
     print(json.dumps(line), flush=True)
+
+
+def measure_env(wl, B, K, W, repeats, rank, world, dev, barrier, sh, envm, torch, want_e2e):
+    """Everything measured on one workload: whole-job throughput of the timed region, the kernels alone (one CUDA-event
+    pair per launch on the launching stream), changed observation rows, and (want_e2e) the host-buffer C-ABI call."""
+    J, M, E = wl["J"], wl["M"], wl["E"]
+    N = J * M
+    first, count, d, w = sh.make_shard(B * world, rank, world, J, M, E, wl["seed"])
+    assert count == B and first == rank * B
+    w = torch.as_tensor(w).to(dev)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32, mask_mode=envm.MASK_ESA)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    env.reset(w)
+    state = {"s": 0}
+
+    def one_step(seed=1234):
+        if state["s"] == N:  # episode finished for every env: next episode (Run.py:615-665)
+            env.reset(w)
+            env.scaler_reset()
+            state["s"] = 0
+        env.random_step(seed=seed, env_offset=first)
+        state["s"] += 1
+
+    for _ in range(max(W, 3)):
+        one_step()
+    times, launches = [], 0
+    for _ in range(repeats):
+        barrier()
+        l0 = env.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            one_step()
+        e1.record()
+        barrier()
+        times.append(sh.max_over_ranks(e0.elapsed_time(e1), dev))
+        launches = env.launch_count - l0
+    ms = median(times)
+    out = {"env": env, "first": first, "w": w, "d": d, "ms": ms, "times": times, "launches": launches,
+           "value": B * world * K / (ms * 1e-3)}
+
+    # ---- record one episode of actions; count the observation rows a step changes (diff of consecutive observations) ----
+    env.reset(w); env.scaler_reset()
+    env.obs()
+    rec_op = torch.empty((N, B), dtype=torch.int32, device=dev)
+    rec_mc = torch.empty((N, B), dtype=torch.int32, device=dev)
+    prev = [x.clone() for x in (env.task_fea, env.adj_w, env.adj_src, env.mach_fea)]
+    rows = [0.0, 0.0, 0.0]
+    for s in range(N):
+        env.random_step(seed=99, env_offset=first)
+        rec_op[s].copy_(env.op); rec_mc[s].copy_(env.mach)
+        cur = (env.task_fea, env.adj_w, env.adj_src, env.mach_fea)
+        rows[0] += float((cur[0] != prev[0]).any(-1).sum())
+        rows[1] += float(((cur[1] != prev[1]).any(-1) | (cur[2] != prev[2])).sum())
+        rows[2] += float((cur[3] != prev[3]).any(-1).sum())
+        for a, b in zip(prev, cur):
+            a.copy_(b)
+    del prev
+    assert int(env.done.sum().item()) == B and int(env.invalid.sum().item()) == 0
+    rows = [r / (N * B) for r in rows]
+    out["rec_op"], out["rec_mc"] = rec_op, rec_mc
+
+    # ---- kernels alone ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(N)]
+    reps = max(2, min(6, (4 * 36) // N + 1))
+
+    def per_launch_us(launch):
+        tot, n = 0.0, 0
+        for rep in range(reps + 1):
+            env.reset(w); env.scaler_reset()
+            for s in range(N):
+                evs[s][0].record()
+                launch(s, rep)
+                evs[s][1].record()
+            torch.cuda.synchronize()
+            if rep > 0:  # first replay is warm-up
+                tot += sum(a.elapsed_time(b) for a, b in evs)
+                n += N
+        return tot * 1e3 / n
+
+    peak, peak_src = measured_peak()
+    gbs = lambda nbytes, us: nbytes * B / (us * 1e-6) / 1e9
+    b_state = 18 * N + 42 * M + 8 * J + (N + 7) // 8 + 160
+    kern = {}
+    us = per_launch_us(lambda s, rep: env.step_obs(rec_op[s], rec_mc[s]))
+    nb, sb = needed_bytes(J, M, 4, False, *rows), env.bytes_per_step()
+    kern["step_obs"] = {"kernel": "env_kernel_s<STEP|OBS,float> (actions given: the actor-driven and host-step paths)",
+                        "kernel_us": us, "bytes_per_env_step": nb["total"], "achieved": gbs(nb["total"], us),
+                        "frac": gbs(nb["total"], us) / peak, "bytes_survey_full_rewrite": sb,
+                        "frac_survey_bytes": gbs(sb, us) / peak}
+    us = per_launch_us(lambda s, rep: env.step(rec_op[s], rec_mc[s]))
+    so = 8 + 2 * b_state + 41
+    kern["step_only"] = {"kernel": "env_kernel_s<STEP,double> (mtfjsp_step: transition + reward + reward scaling + job mask, "
+                                   "no observation)", "kernel_us": us, "bytes_per_env_step": so,
+                         "bytes_accounting": "SURVEY.md 8(d): 8 + 2*B_state + 41", "achieved": gbs(so, us),
+                         "frac": gbs(so, us) / peak, "steps_per_s_kernel_only": B / (us * 1e-6)}
+    if env.random_step_is_fused:
+        us = per_launch_us(lambda s, rep: env.random_step(seed=500 + rep, env_offset=first))
+        nb, sb = needed_bytes(J, M, 4, True, *rows), env.bytes_per_random_step()
+        kern["random_step"] = {"kernel": "env_kernel_s<STEP|OBS|POLICY,float> (random policy + candidate-machine features + "
+                                         "step + reward + observation + job mask; the kernel of the timed region)",
+                               "kernel_us": us, "bytes_per_env_step": nb["total"], "achieved": gbs(nb["total"], us),
+                               "frac": gbs(nb["total"], us) / peak, "bytes_terms": nb, "bytes_survey_full_rewrite": sb,
+                               "frac_survey_bytes": gbs(sb, us) / peak, "steps_per_s_kernel_only": B / (us * 1e-6)}
+    out["kern"], out["peak"], out["peak_src"], out["rows"] = kern, peak, peak_src, rows
+
+    # ---- e2e: host-buffer C-ABI call per step (pinned H2D action pairs, D2H packed step records = step info + job
+    # mask + candidates; mtfjsp_step_host_packed cuts the batch into chunks whose copies overlap the other chunks' kernels) ----
+    if want_e2e:
+        h_act = torch.stack([rec_op.cpu(), rec_mc.cpu()], dim=2).contiguous().pin_memory()  # [N,B,2] (op, machine)
+        _, h_rec = env.host_buffers()
+        rec_view = h_rec.numpy().view(env.host_record_dtype())[:, 0]
+        host_step = env.host_stepper(h_rec)                       # prepared call: buffers bound once
+        act_ptr = [h_act[s].data_ptr() for s in range(N)]         # this step's pinned [B,2] action array
+        es = {"s": N}
+
+        def e2e_steps(n):
+            for _ in range(n):
+                if es["s"] == N:
+                    env.reset(w); env.scaler_reset(); es["s"] = 0
+                host_step(act_ptr[es["s"]])
+                es["s"] += 1
+
+        e2e_steps(N + 3)  # one whole episode first: every action buffer's graph is instantiated outside the timed region
+        Ke = min(K, 4 * N)
+        et = []
+        for _ in range(repeats):
+            barrier()
+            t0 = time.perf_counter()
+            e2e_steps(Ke)
+            torch.cuda.synchronize()
+            et.append(sh.max_over_ranks(time.perf_counter() - t0, dev))
+        e2e_s = median(et)
+        out["e2e"] = {"value": B * world * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 8,
+                      "d2h_bytes_per_step": B * h_rec.shape[1],
+                      "api": "mtfjsp_step_host_packed (C ABI, pinned host buffers: [B,2] i32 action pairs in, [B] packed "
+                             "records (f64 info6, i16 candidates, u8 job mask) out; observation tensors stay on the device)",
+                      "steps": Ke, "repeats": repeats, "us_per_step": e2e_s * 1e6 / Ke}
+        assert float(rec_view["info6"][:, 1].sum()) in (0.0, float(B))
+    return out
+
+
+def kernel_traffic(J, M, B):
+    """ncu --set full DRAM bytes per launch of the env kernels on this workload (profiles/r02_env_kernel_traffic.json,
+    written from this round's captures by profiles/ncu_traffic.py), or {}."""
+    for name in ("r02_env_kernel_traffic.json",):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            try:
+                return json.load(open(path)).get("J%dM%d_B%d" % (J, M, B), {})
+            except Exception:
+                pass
+    return {}
 
 
 def run_ours(args, wl):
@@ -177,15 +441,7 @@ def run_ours(args, wl):
     if args.scaling == "strong":  # fixed total batch: the workload's env count is split over the ranks
         B = max(1, B // world)
     N = J * M
-    # weak scaling: B envs per GPU, env i of the B*world job lives on rank i // B (contiguous slices)
-    first, count, d, w = sh.make_shard(B * world, rank, world, J, M, E, wl["seed"])
-    assert count == B and first == rank * B
-    w = torch.as_tensor(w).to(dev)
-    env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32, mask_mode=envm.MASK_ESA)
-    env.load(d["t"], d["p"], d["transT"], d["edge"])
-    env.scaler_init()
-    env.reset(w)
-    K, W = args.steps, args.warmup
+    K, W, R = args.steps, args.warmup, max(1, args.repeats)
 
     def barrier():
         torch.cuda.synchronize()
@@ -193,105 +449,14 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    state = {"s": 0}
-
-    def one_step(seed=1234):
-        if state["s"] == N:  # episode finished for every env: next episode (Run.py:615-665)
-            env.reset(w)
-            env.scaler_reset()
-            state["s"] = 0
-        env.random_step(seed=seed, env_offset=first)
-        state["s"] += 1
-
-    for _ in range(max(W, 3)):
-        one_step()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = env.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        one_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = env.launch_count - l0
-    ms = sh.max_over_ranks(ms, dev)
-    value = B * world * K / (ms * 1e-3)
-
-    # ---- dominant kernel alone: fused step+obs launches replaying recorded actions (device resident) ----
-    env.reset(w); env.scaler_reset()
-    rec_op = torch.empty((N, B), dtype=torch.int32, device=dev)
-    rec_mc = torch.empty((N, B), dtype=torch.int32, device=dev)
-    for s in range(N):
-        env.random_step(seed=99, env_offset=first)
-        rec_op[s].copy_(env.op); rec_mc[s].copy_(env.mach)
-    assert int(env.done.sum().item()) == B and int(env.invalid.sum().item()) == 0
-    kms, klaunch = 0.0, 0
-    reps = max(1, min(4, K // N))
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(N)]
-    for rep in range(reps + 1):
-        env.reset(w); env.scaler_reset()
-        for s in range(N):
-            evs[s][0].record()
-            env.step_obs(rec_op[s], rec_mc[s])
-            evs[s][1].record()
-        torch.cuda.synchronize()
-        if rep > 0:  # first replay is warm-up
-            kms += sum(a.elapsed_time(b) for a, b in evs)
-            klaunch += N
-    k_us = kms * 1e3 / klaunch
-    bytes_step = env.bytes_per_step()
-    peak, peak_src = measured_peak()
-    achieved = bytes_step * B / (k_us * 1e-6) / 1e9
-    # the kernel the timed region above actually launches: the one-launch random-rollout step (policy + candidate-machine
-    # features + step + obs), one CUDA-event pair per launch on the launching stream
-    fused = None
-    if env.random_step_is_fused:
-        fms = 0.0
-        for rep in range(reps + 1):
-            env.reset(w); env.scaler_reset()
-            for s in range(N):
-                evs[s][0].record()
-                env.random_step(seed=500 + rep, env_offset=first)
-                evs[s][1].record()
-            torch.cuda.synchronize()
-            if rep > 0:
-                fms += sum(a.elapsed_time(b) for a, b in evs)
-        f_us = fms * 1e3 / klaunch
-        fbytes = env.bytes_per_random_step()
-        fused = {"kernel_us": f_us, "bytes_per_env_step": fbytes, "achieved": fbytes * B / (f_us * 1e-6) / 1e9}
-
-    # ---- e2e: host-buffer C-ABI call per step (pinned H2D action pairs, D2H packed step records = step info + job
-    # mask + candidates; mtfjsp_step_host_packed cuts the batch into chunks whose copies overlap the other chunks' kernels) ----
-    h_act = torch.stack([rec_op.cpu(), rec_mc.cpu()], dim=2).contiguous().pin_memory()  # [N,B,2] (op, machine)
-    _, h_rec = env.host_buffers()
-    rec_view = h_rec.numpy().view(env.host_record_dtype())[:, 0]
-    Ke = min(K, 4 * N)
-
-    host_step = env.host_stepper(h_rec)                       # prepared call: buffers bound once
-    act_ptr = [h_act[s].data_ptr() for s in range(N)]         # this step's pinned [B,2] action array
-
-    def e2e_steps(n):
-        s = 0
-        env.reset(w); env.scaler_reset()
-        for _ in range(n):
-            if s == N:
-                env.reset(w); env.scaler_reset(); s = 0
-            host_step(act_ptr[s])
-            s += 1
-
-    e2e_steps(N + 3)  # one whole episode first: every action buffer's graph is instantiated outside the timed region
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(Ke)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_s = sh.max_over_ranks(e2e_s, dev)
-    e2e_val = B * world * Ke / e2e_s
-    assert float(rec_view["info6"][:, 1].sum()) in (0.0, float(B))
+    # weak scaling: B envs per GPU, env i of the B*world job lives on rank i // B (contiguous slices)
+    mm = measure_env(wl, B, K, W, R, rank, world, dev, barrier, sh, envm, torch, want_e2e=True)
+    env, first, w, d = mm["env"], mm["first"], mm["w"], mm["d"]
+    rec_op, rec_mc = mm["rec_op"], mm["rec_mc"]
+    ms, value, launches, peak, peak_src, kern = mm["ms"], mm["value"], mm["launches"], mm["peak"], mm["peak_src"], mm["kern"]
     h_op = rec_op.cpu(); h_mc = rec_mc.cpu()
     # ---- BASELINE.json configs[4] (forward half): the same env slice driven by the MAPPO actors on the device ----
     policy = None
@@ -345,8 +510,8 @@ def run_ours(args, wl):
                 t0e.record()
                 btc = ppo.collect(tro, wt)
                 t1e.record()
-                losses, _ = up.update(btc, N)
-                tro.job.refresh(); tro.mch.refresh()
+                up.recompute_old_logp(btc)       # the TF32 twins collected it: behaviour log-probs on the update's path
+                losses, _ = up.update(btc, N)    # (refreshes the twins' cached weight layouts at the end)
                 t2e.record()
                 barrier()
                 a_ms = up.allreduce_ms()
@@ -372,16 +537,30 @@ def run_ours(args, wl):
         del env_t, up, tro
         torch.cuda.empty_cache()
 
+    # ---- BASELINE.json configs[2], configs[3] in the same invocation (N = 1): value + kernel roofline ----
+    others = {}
+    if world == 1 and not args.no_workloads and args.workload == "A" and not args.batch:
+        for key in ("B", "C"):
+            wl2 = WORKLOADS[key]
+            N2 = wl2["J"] * wl2["M"]
+            m2 = measure_env(wl2, wl2["B"], N2, 3, 5, rank, world, dev, barrier, sh, envm, torch, want_e2e=False)
+            k2 = m2["kern"]
+            tr2 = kernel_traffic(wl2["J"], wl2["M"], wl2["B"])
+            head2 = k2.get("random_step", k2["step_obs"])
+            others[key] = {"config": workload_config(wl2, wl2["B"], world), "value": m2["value"], "unit": UNIT,
+                           "steps": N2, "repeats": 5, "ms_per_step": m2["ms"] / N2,
+                           "what": "whole episodes (%d steps) of the one-launch random-rollout step, median of 5" % N2,
+                           "roofline": dict(head2, peak=peak, unit="GB/s", bound="hbm",
+                                            traffic=tr2.get("random_step" if "random_step" in k2 else "step_obs")),
+                           "step_obs_kernel": k2["step_obs"], "step_only": k2["step_only"]}
+            del m2
+            torch.cuda.empty_cache()
+
     clocks = sampler.stop() if sampler else None
-    traffic = traffic_step = None
-    tpath = os.path.join(ROOT, "profiles", "r01_env_kernel_traffic.json")
-    if (J, M, B) == (6, 6, 65536) and os.path.exists(tpath):  # ncu --set full captures of these kernels on this workload
-        tj = json.load(open(tpath))
-        traffic_step = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        if "fused_random_step" in tj:
-            traffic = tj["fused_random_step"]["dram_bytes_read"] + tj["fused_random_step"]["dram_bytes_write"]
-    if fused is None:
-        traffic = traffic_step
+    tr = kernel_traffic(J, M, B)
+    headk = "random_step" if "random_step" in kern else "step_obs"
+    head = kern[headk]
+    traffic = tr.get(headk)
 
     # ---- the strict drop-in call: Parallel_env.DGFJSPEnv_paral_step with the reference's argument / return types
     # (python list of action pairs in, numpy float64 dense adjacency [B,N,N] + features + python info list out) ----
@@ -405,48 +584,42 @@ def run_ours(args, wl):
                          "adjacency + features + python info list out)"}
         del pe
 
-    cpu = None
+    cpu = cpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r1, sample = cpu_port_rate(wl, 1, 8.0)
         cpu = {"value": r1, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+        if (J, M) == (6, 6):
+            cpu_ref = real_reference_rate()
 
     if rank == 0:
+        spread = (max(mm["times"]) - min(mm["times"])) / ms if ms else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "envs_per_gpu": B, "jobs": J, "machines": M, "edges": E, "obs_dtype": "f32",
-                       "mask_mode": "ESA", "left_shift": True, "parallelism": "env-slices x%d (no data-path collective)" % world,
-                       "l2": "working set %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (B * (bytes_step + 2000) / 1e6),
-                       "launches_per_step": round(launches / K, 3),
-                       "kernels": "env_kernel_s<STEP|OBS|POLICY> (random policy + candidate-machine features + step + reward + "
-                                  "obs + mask in one launch; reset launches env_kernel<RESET> + scaler_kernel every %d steps)" % N},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * h_rec.shape[1],
-                    "api": "mtfjsp_step_host_packed (C ABI, pinned host buffers: [B,2] i32 action pairs in, [B] packed records "
-                           "(f64 info6, i16 candidates, u8 job mask) out; observation tensors stay on the device)",
-                    "steps": Ke},
+            "data": "synthetic", "config": workload_config(wl, B, world),
+            "repeats": R, "timing": "median of %d timed regions of %d steps each (CUDA events, barrier + synchronize on "
+                                    "both sides, max over ranks); (max-min)/median = %.3f" % (R, K, spread or 0.0),
+            "impl_notes": {"parallelism": "env-slices x%d (no data-path collective)" % world,
+                           "launches_per_step": round(launches / K, 3),
+                           "kernels": "env_kernel_s<STEP|OBS|POLICY> (random policy + candidate-machine features + step + "
+                                      "reward + obs + mask in one launch; reset launches reset_copy_kernel + scaler_kernel "
+                                      "every %d steps)" % N},
+            "e2e": mm["e2e"],
             "gpu_launches": launches,
-            "roofline": ({"bound": "hbm", "achieved": fused["achieved"], "peak": peak, "unit": "GB/s",
-                          "frac": fused["achieved"] / peak, "traffic": traffic,
-                          "kernel": "env_kernel_s<STEP|OBS|POLICY,float> (random policy + candidate-machine features + step + "
-                                    "reward + observation + job mask; the kernel of the timed region)",
-                          "kernel_us": fused["kernel_us"], "bytes_per_env_step": fused["bytes_per_env_step"],
-                          "peak_source": peak_src, "steps_per_s_kernel_only": B / (fused["kernel_us"] * 1e-6),
-                          "bytes_accounting": "SURVEY.md 8(d): a full rewrite of the observation every step, as the reference "
-                                              "does; with the incremental observation the kernel moves `traffic` bytes per "
-                                              "launch (ncu), i.e. frac_of_peak_moved = traffic / kernel time / peak",
-                          "frac_of_peak_moved": (traffic / (fused["kernel_us"] * 1e-6) / 1e9 / peak) if traffic else None,
-                          "step_obs_kernel": {"kernel": "env_kernel_s<STEP|OBS,float> (actions given: the actor-driven and "
-                                                        "host-step paths)", "kernel_us": k_us, "bytes_per_env_step": bytes_step,
-                                              "achieved": achieved, "frac": achieved / peak, "traffic": traffic_step}}
-                         if fused else
-                         {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                          "traffic": traffic, "kernel": "env_kernel<STEP|OBS,float> (fused step + reward + observation + job mask)",
-                          "kernel_us": k_us, "bytes_per_env_step": bytes_step, "peak_source": peak_src,
-                          "steps_per_s_kernel_only": B / (k_us * 1e-6)}),
+            "roofline": dict(head, bound="hbm", peak=peak, unit="GB/s", traffic=traffic, peak_source=peak_src,
+                             bytes_accounting="frac = bytes the incremental algorithm needs per env-step (needed_bytes() in "
+                                              "bench.py: whole state read once in SURVEY 8(d)'s minimal form, changed state and "
+                                              "changed observation rows written) / kernel time / peak; frac_survey_bytes = SURVEY "
+                                              "8(d)'s full observation rewrite every step (what the reference does; round 1's "
+                                              "headline); frac_of_peak_moved = ncu DRAM bytes of one launch / kernel time / peak",
+                             frac_of_peak_moved=(traffic / (head["kernel_us"] * 1e-6) / 1e9 / peak) if traffic else None,
+                             step_obs_kernel=dict(kern["step_obs"], traffic=tr.get("step_obs")),
+                             step_only=dict(kern["step_only"], traffic=tr.get("step_only"))),
             "clocks": clocks,
             "episode_stats": {k: float(v) for k, v in stats.items()},
         }
+        if others:
+            line["workloads"] = others
         if policy:
             line["policy_rollout"] = policy
         if train:
@@ -455,6 +628,8 @@ def run_ours(args, wl):
             line["e2e"]["dropin_parallel_env"] = dropin
         if cpu:
             line["cpu_baseline"] = cpu
+        if cpu_ref:
+            line["cpu_baseline_reference"] = cpu_ref
         if stdout_fd is not None:
             sys.stdout.flush()
             os.dup2(stdout_fd, 1)
@@ -468,8 +643,9 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3600)
+    ap.add_argument("--steps", type=int, default=360)
     ap.add_argument("--warmup", type=int, default=36)
+    ap.add_argument("--repeats", type=int, default=15, help="timed regions of --steps steps each; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="envs per GPU (default: the workload's)")
@@ -479,6 +655,7 @@ def main():
     ap.add_argument("--no-policy", action="store_true", help="skip the actor-driven rollout measurement")
     ap.add_argument("--no-dropin", action="store_true", help="skip the Parallel_env (reference-typed) call measurement")
     ap.add_argument("--no-train", action="store_true", help="skip the rollout + PPO update measurement")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the J10M10E3 / J30M20E5 lines")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

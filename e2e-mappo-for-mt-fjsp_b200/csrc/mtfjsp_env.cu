@@ -90,6 +90,9 @@ struct Params {
     unsigned char* rec;    // optional packed step records, rec_stride bytes per env: f64 info6[6] | i16 cand[J] | u8 mask[J]
     int rec_stride;
     int b0, b1;     // env range [b0, b1) of this launch (host-step pipeline launches sub-ranges)
+    int rev;        // blocks walk the env range from its END (alternate launches: what the previous launch touched last is
+                    // still in L2 when this one starts -- a batch's working set is larger than the 126 MB L2, and a
+                    // forward walk every launch evicts each line just before it is needed again)
     // obs io
     void* tfea;
     void* mfea;
@@ -702,18 +705,10 @@ __device__ __forceinline__ double gmin_d(double v) {
     for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
-template <int G>
-__device__ __forceinline__ unsigned gmin_u(unsigned v) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-template <int G>
-__device__ __forceinline__ int gmax_i(int v) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
+// 32-bit reductions over a lane group: one redux.sync with the group's member mask (the groups of a warp execute it
+// together, each with its own mask) instead of log2(G) shuffle + min/max pairs
+__device__ __forceinline__ unsigned gmin_u(unsigned v, unsigned gmask) { return __reduce_min_sync(gmask, v); }
+__device__ __forceinline__ int gmax_i(int v, unsigned gmask) { return __reduce_max_sync(gmask, v); }
 
 // adj_val without the 64-bit integer round trip: trunc() is exact for |w| < 2^53
 __device__ __forceinline__ double adj_val_t(double w, bool u_assigned, double dur_u) {
@@ -764,8 +759,10 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (G - 1), ge = lane / G;
+    const unsigned gmask = S::GMASK << (ge * G);  // member mask of this lane's group
     const int B = P.b1;
-    const int wb0 = P.b0 + (blockIdx.x * S::WARPS + warp) * EPW;
+    const int blk = P.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int wb0 = P.b0 + (blk * S::WARPS + warp) * EPW;
     if (wb0 >= B) return;
     const int b = wb0 + ge;
     const bool active = b < B;
@@ -983,8 +980,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 }
             }
         }
-        best = gmin_u<G>(best);
-        lastop = gmax_i<G>(lastop);
+        best = gmin_u(best, gmask);
+        lastop = gmax_i(lastop, gmask);
         double st = arr_a;
         int where = 0, prev = -1, next = -1, rem_head = -1, fresh = -1;
         if (len > 0) {
@@ -1593,6 +1590,43 @@ __global__ void dense_adj_kernel(Layout L, const float* __restrict__ adj_w, cons
     }
 }
 
+// Raw arc weights of the disjunctive graph between real ops: out[b][u][v] = trunc(weight of arc u -> v), 0 = no arc --
+// what nx.to_numpy_array(G)[1:-1, 1:-1].astype(int) holds in the reference (SS:2019) and what its gym `state` vector is
+// made of (SS:2075-2130).  Same arc rules as the observation rows of env_kernel (job arc refresh SS:1356-1434, the
+// machine arcs of SS:1548-1765, the one-step transients); compatibility view of the single-env class, not on the hot path.
+// One thread per (env, destination op); the caller zero-fills `out`.
+__global__ void raw_adj_kernel(Layout L, const double* __restrict__ sd, const int16_t* __restrict__ si,
+                               const double* __restrict__ xs, int32_t* out) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)L.B * L.N) return;
+    const size_t b = gid / L.N;
+    const int v = (int)(gid % L.N), N = L.N, M = L.M;
+    const double* d = sd + b * L.sd_stride;
+    const int16_t* q = si + b * L.si_stride;
+    const double* tt = xs + b * L.xs_stride + L.o_tt;
+    const int rem_head = q[L.o_misc + 0], fresh = q[L.o_misc + 1];
+    const int mv = q[L.o_mach + v];
+    const bool sch = mv >= 0, vfirst = (v % M) == 0;
+    const int rp = sch ? (int)q[L.o_rpred + v] : -1;
+    const bool has_job = !vfirst && v != rem_head;
+    const bool co = has_job && rp == v - 1;
+    const bool has_m = rp >= 0 && !co;
+    int32_t* A = out + b * (size_t)N * N;
+    if (has_job) {
+        const int u = v - 1, mu = q[L.o_mach + u];
+        const double du = d[L.o_dur + u];
+        double w;
+        if (fresh == v) w = du + tt[mu * M + mv] + (d[L.o_st + v] - d[L.o_ft + u]);
+        else if (du != 0.0) w = du + ((mu >= 0 && sch) ? tt[mu * M + mv] : 0.0);
+        else w = 1.0;
+        A[(size_t)u * N + v] = (int32_t)(long long)w;
+    }
+    if (has_m) {
+        const double w = d[L.o_dur + rp] + ((rp / M == v / M) ? tt[mv * M + mv] : 0.0) + (d[L.o_st + v] - d[L.o_ft + rp]);
+        A[(size_t)rp * N + v] = (int32_t)(long long)w;
+    }
+}
+
 __global__ void export_kernel(Layout L, const double* __restrict__ sd, const int16_t* __restrict__ si, int32_t* mach,
                               double* st, double* ft, int32_t* routes) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1715,6 +1749,8 @@ struct mtfjsp_env {
     const void* obs_ptrs[4];
     int obs_dtype;
     int host_chunks, fuse_policy;  // tuning knobs read from the environment at create time (tests compare the settings)
+    int alternate_order, flip;     // MTFJSP_ALTERNATE_ORDER (default on): successive step launches walk the batch in
+                                   // opposite directions for L2 reuse
     int64_t launches;
     struct HostPipe* pipe;  // host-step pipeline (streams, events, instantiated graphs), created on first use
 };
@@ -1788,7 +1824,14 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     }
     const int per_block = S::WARPS * S::EPW;
     const int blocks = (P.b1 - P.b0 + per_block - 1) / per_block;
-    env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(P);
+    if (h->alternate_order && (MODE & MODE_STEP)) {  // eager step launches alternate direction (see Params::rev)
+        Params Q = P;
+        Q.rev = h->flip;
+        h->flip ^= 1;
+        env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(Q);
+    } else {
+        env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(P);
+    }
     h->launches++;
     CK(cudaGetLastError(), "env_kernel_s launch");
     return MTFJSP_OK;
@@ -1953,6 +1996,7 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
         h->force_generic = fg && fg[0] == '1';
         h->host_chunks = getenv("MTFJSP_HOST_CHUNKS") ? atoi(getenv("MTFJSP_HOST_CHUNKS")) : 4;
         h->fuse_policy = getenv("MTFJSP_FUSE_POLICY") ? atoi(getenv("MTFJSP_FUSE_POLICY")) : 1;
+        h->alternate_order = getenv("MTFJSP_ALTERNATE_ORDER") ? atoi(getenv("MTFJSP_ALTERNATE_ORDER")) : 1;
         h->obs_inc_allowed = !(getenv("MTFJSP_OBS_INCREMENTAL") && atoi(getenv("MTFJSP_OBS_INCREMENTAL")) == 0);  // test hook
     }
     h->cfgw[0] = 0.4; h->cfgw[1] = 0.4; h->cfgw[2] = 0.2; h->divisor = 1.0; h->gamma = 0.99;
@@ -2166,6 +2210,20 @@ int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream) {
     else return fail(MTFJSP_E_ARG, "dtype must be MTFJSP_F32 or MTFJSP_F64");
     h->launches++;
     CK(cudaGetLastError(), "dense_adj_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_raw_adj(mtfjsp_env* h, int32_t* adj, void* stream) {
+    if (!h || !adj) return fail(MTFJSP_E_ARG, "mtfjsp_raw_adj: bad argument");
+    if (!h->reset_done) return fail(MTFJSP_E_STATE, "mtfjsp_raw_adj before mtfjsp_reset");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const Layout& L = h->L;
+    CK(cudaMemsetAsync(adj, 0, (size_t)L.B * L.N * L.N * sizeof(int32_t), s), "cudaMemsetAsync");
+    const size_t n = (size_t)L.B * L.N;
+    raw_adj_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, h->sd, h->si, h->xs, adj);
+    h->launches++;
+    CK(cudaGetLastError(), "raw_adj_kernel");
     return MTFJSP_OK;
 }
 

@@ -215,6 +215,12 @@ class BatchedMTFJSPEnv:
         check(self._lib.mtfjsp_dense_adj(self._h, _ptr(adj), F64 if dtype == torch.float64 else F32, _stream()), "mtfjsp_dense_adj")
         return adj
 
+    def raw_adj(self):
+        """int32 [B,N,N], adj[b,u,v] = trunc(weight of arc u -> v): the reference's nx.to_numpy_array(G)[1:-1,1:-1].astype(int)."""
+        adj = torch.empty((self.B, self.N, self.N), dtype=torch.int32, device=self.device)
+        check(self._lib.mtfjsp_raw_adj(self._h, _ptr(adj), _stream()), "mtfjsp_raw_adj")
+        return adj
+
     def costs(self, with_total_e1=False):
         c = torch.empty((self.B, 4), dtype=torch.float64, device=self.device)
         e1 = torch.empty((self.B,), dtype=torch.float64, device=self.device) if with_total_e1 else None

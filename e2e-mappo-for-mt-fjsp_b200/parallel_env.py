@@ -41,6 +41,24 @@ def draw_reward_weights(kind: str, configs: dict):
     raise ValueError("Random_weight_type must be '01', '0.1' or 'eval'")
 
 
+def gantt_text(machine_routes, st, ft, n_machine, width=72):
+    """Console Gantt of a schedule: one line per machine with its ops as `task[start,finish)` in route order and a bar
+    on a common time axis.  Stands in for the reference's visualizer package (rendering is outside the hot path)."""
+    horizon = max([float(ft[int(t) - 1]) for r in machine_routes.values() for t in r] + [1e-9])
+    lines = ["makespan %.3f" % (horizon if horizon > 1e-9 else 0.0)]
+    for m in range(n_machine):
+        route = [int(t) for t in machine_routes.get(m, [])]
+        bar = [" "] * width
+        for t in route:
+            a = int(float(st[t - 1]) / horizon * (width - 1))
+            b = max(a + 1, int(float(ft[t - 1]) / horizon * (width - 1)))
+            for k in range(a, min(b, width)):
+                bar[k] = "#" if bar[k] == " " else "+"
+        ops = " ".join("%d[%.1f,%.1f)" % (t, float(st[t - 1]), float(ft[t - 1])) for t in route)
+        lines.append("M%-2d |%s| %s" % (m, "".join(bar), ops))
+    return "\n".join(lines)
+
+
 class _ScalerHandle:
     """paral_Rscaling_instance[i]: Run.py:283-284 calls .reset() on each one at the start of an episode."""
 
@@ -61,7 +79,9 @@ class _Nodes:
         sched = st["mach"][b, i] >= 0
         return {"finish_time": float(st["ft"][b, i]) if sched else None,
                 "start_time": float(st["st"][b, i]) if sched else None,
-                "machine": int(st["mach"][b, i]), "scheduled": bool(sched), "job": i // self._p._owner.nmachines}
+                "machine": int(st["mach"][b, i]),   # -1 while unscheduled, as the reference's node attribute
+                "duration": float(self._p._owner.ability_instance[b][0][i][st["mach"][b, i]]) if sched else 0,
+                "scheduled": bool(sched), "job": i // self._p._owner.nmachines}
 
 
 class _Graph:
@@ -107,8 +127,13 @@ class _EnvProxy:
         self._owner._weights[self._b] = draw_reward_weights(Random_weight_type, self._owner.args)
         self._owner._dirty = True
 
-    def render(self, *a, **k):
-        return None
+    def render(self, mode="human", *a, **k):
+        """Run.py:653: console Gantt of this env's current schedule."""
+        st = self._owner._host_state()
+        text = gantt_text(self.machine_routes, st["st"][self._b], st["ft"][self._b], self._owner.nmachines)
+        if mode == "human":
+            print(text)
+        return text
 
 
 class Parallel_env(object):

@@ -104,6 +104,11 @@ int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_ma
 /* compatibility view: dense adjacency adj[b,dst,src], diagonal 1 (SS:2019-2073), element type dtype. */
 int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream);
 
+/* compatibility view of the single-env class: raw arc weights between real ops, adj[b,u,v] = trunc(weight of u -> v),
+ * int32 [B,N,N] -- nx.to_numpy_array(G)[1:-1,1:-1].astype(int) of SS:2019, the matrix the reference's gym `state`
+ * vector (first element of the reset 9-tuple / step 14-tuple, SS:2075-2130, 2515) is built from. */
+int mtfjsp_raw_adj(mtfjsp_env* h, int32_t* adj, void* stream);
+
 /* replaces: reading env.makespan_previous_step, total_e1_previous_step/N, trans_t_previous_step,
  * idle_t_previous_step (Run.py:632-633, trainer/validate.py:273-277).  cost4 [B,4] f64 (mk, pt/N, tt, idle);
  * total_e1 [B] f64 = the undivided total_e1_previous_step.  Either may be NULL. */

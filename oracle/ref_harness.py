@@ -1,9 +1,11 @@
 """Import shim + replay driver for the *real* Python reference (read-only, /root/reference).
 
 TEST INFRASTRUCTURE ONLY.  This module exists to (a) validate the C restatement in
-``oracle/mtfjsp_oracle.c`` against the reference implementation and (b) generate the golden
-vectors committed under ``tests/golden/`` (see ``tests/golden/gen_golden.py``).  It only works in
-the build container, where ``/root/reference`` is mounted; nothing on the GPU box imports it.
+``oracle/mtfjsp_oracle.c`` against the reference implementation, (b) generate the golden
+vectors committed under ``tests/golden/`` (see ``tests/golden/gen_golden.py``) and (c) time / drive the
+unmodified reference next to the CUDA path (bench.py's cpu_baseline_reference leg, tests/test_single_env.py).
+It reads ``/root/reference`` in the build container and the git-ignored copy ``baseline/_ref`` on the
+GPU box; the product package never imports it.
 
 Recipe: three stub packages (gym, matplotlib.pyplot, plotly.figure_factory)
 under ``oracle/ref_shims``, a pre-seeded ``graph_jsp_env.wzl_ima_banner`` module, and the reference
@@ -18,8 +20,11 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("MTFJSP_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# the read-only mount in the build container, else the git-ignored copy that travels to the GPU box (made by
+# __graft_entry__.build(); it carries the unmodified tree so the reference can be TIMED and driven there)
+_COPY = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+REF_ROOT = os.environ.get("MTFJSP_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference") else _COPY)
 
 
 def reference_available() -> bool:
@@ -337,3 +342,57 @@ def replay(n_job, n_machine, n_edge, t, p, tt, edge, weights, actions=None, left
     if obs_steps is not None:
         res["obs_steps"] = np.asarray(sorted(obs_steps), dtype=np.int32)
     return res
+
+
+def default_model_args(n_job, n_machine, n_edge=2, env_batch=1):
+    """parameters.py:41-125 defaults that the networks, validate.py and pdrs.py read."""
+    a = make_args(n_job, n_machine, n_edge, env_batch)
+    a.update({"gcn_layer": 3, "mlp_fea_extract_layer": 3, "gcn_hidden_dim": 128, "learn_eps": False,
+              "neighbor_pooling_type": "average", "mlp_actor_layer": 3, "mlp_critic_layer": 3, "critic_input_dim": 128,
+              "critic_hidden_dim": 128, "use_orthogonal": False, "machine_hidden_dim": 128, "LAMDA": 0.98, "epsilon": 0.2,
+              "ENTROPY_BETA": 0.01, "LR": 1e-3, "lr_eps": 1e-5})
+    return a
+
+
+def shipped_checkpoint_paths(n_job=6, n_machine=6, n_edge=2, episode=1000):
+    """tester/IoTJ_MAPPO/PPO_{operation,machine}_actor_J*M*E*_*.pth (the `PPO-G` rows of test_all.py:56-75, 166-167)."""
+    base = os.path.join(REF_ROOT, "tester", "IoTJ_MAPPO")
+    tag = "J%dM%dE%d_%d.pth" % (n_job, n_machine, n_edge, episode)
+    return os.path.join(base, "PPO_operation_actor_" + tag), os.path.join(base, "PPO_machine_actor_" + tag)
+
+
+def make_reference_ppo(n_job, n_machine, device, op_pth=None, mch_pth=None):
+    """A PPOAlgorithm instance holding the REAL actor networks with shipped weights on `device`, built the way
+    tests/golden/gen_ppo_golden.py does (object.__new__: the constructor also builds the unrelated ESA networks).
+    What trainer/validate.py:60-297 needs from it: job_actor, machine_actor_gcn, Eval_esa_update_..., set_to_0."""
+    import contextlib
+    import io
+
+    import torch
+
+    load_reference()
+    td = types.ModuleType("trainer.train_device")
+    td.device = torch.device(device)
+    sys.modules["trainer.train_device"] = td
+    if "trainer.fig_kpi" not in sys.modules:
+        fk = types.ModuleType("trainer.fig_kpi")
+        fk.get_GPU_usage = lambda *a, **k: None
+        fk.result_box_plot = lambda *a, **k: None
+        sys.modules["trainer.fig_kpi"] = fk
+    with contextlib.redirect_stdout(io.StringIO()):
+        from algorithm import ppo_algorithm
+        from model import actor_critic
+    args = default_model_args(n_job, n_machine)
+    with contextlib.redirect_stdout(io.StringIO()):
+        job = actor_critic.Operation_Actor_JointAction_selfCritic(args)
+        mch = actor_critic.Machine_Actor_JointAction_selfGAT_selfCritic(args)
+    if op_pth is None:
+        op_pth, mch_pth = shipped_checkpoint_paths(n_job, n_machine)
+    job.load_state_dict(torch.load(op_pth, map_location="cpu"))
+    mch.load_state_dict(torch.load(mch_pth, map_location="cpu"))
+    ppo = object.__new__(ppo_algorithm.PPOAlgorithm)
+    ppo.n_job, ppo.n_machine, ppo.n_total_task, ppo.batch_size = n_job, n_machine, n_job * n_machine, 1
+    ppo.pool_task_list = [1 + n_machine * i for i in range(n_job)]
+    ppo.job_actor, ppo.machine_actor_gcn = job.to(device), mch.to(device)
+    ppo.set_to_0(None)
+    return ppo, args

@@ -1,5 +1,6 @@
 """Short driver for ncu captures: config-2 workload (J6M6E2, 65,536 envs), a few rollout steps.
-usage: ncu ... python profiles/prof_step.py [workload] [steps] [random|replay]"""
+usage: ncu ... python profiles/prof_step.py [workload] [steps] [random|replay|step]
+  random: the one-launch random-rollout step; replay: mtfjsp_step_obs on given actions; step: mtfjsp_step alone"""
 import importlib
 import os
 import sys
@@ -24,6 +25,10 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "random"   # "random": one-launch r
 if mode == "random":
     for s in range(steps):
         env.random_step(seed=1)
+elif mode == "step":
+    for s in range(steps):
+        env.policy_random(seed=1)
+        env.step(env.op, env.mach)
 else:
     ops, mcs = [], []
     for s in range(steps):

@@ -23,6 +23,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
     assert d["higher_is_better"] is True and d["value"] > 0
     assert d["config"]["workload"] == bench.WORKLOADS["A"]["name"]
+    # same `config` object as the device arm (the driver compares them)
+    assert d["config"] == bench.workload_config(bench.WORKLOADS["A"], bench.WORKLOADS["A"]["B"], 1)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["sample"]
     try:
@@ -38,3 +40,16 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_needed_bytes_accounting():
+    """The headline roofline numerator: bytes the incremental algorithm needs per env-step (bench.needed_bytes)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    nb = bench.needed_bytes(6, 6, 4, False, 4.5, 4.5, 1.0)
+    assert nb["b_state"] == 1113                                   # SURVEY.md 8(d), config A
+    assert nb["read"] == 1113 + 24 and nb["write"] == 206 + 41 + 32 + 30 + 4.5 * 48 + 4.5 * 10 + 32
+    full = 8 + 2 * 1113 + (48 * 36 + 18 * 36 + 32 * 6 + 5 * 6 + 41)
+    assert full == 4873 and nb["total"] < full                     # never credits bytes the kernel does not write
+    assert bench.median([3, 1, 2]) == 2 and bench.median([4, 1, 2, 3]) == 2.5

@@ -50,6 +50,8 @@ def test_parallel_env_reproduces_reference_dump(name):
                          "edge": torch.tensor(g["edge"])})
     paral_env.init_RewardScaling_sameBATCH(shape=4)
     jm = pe_mod.JobMask(paral_env, use_esa=(mm == 1))
+    # large fixtures keep the observation / schedule dumps at g["obs_steps"] only (tests/golden/gen_golden.py)
+    kept = {int(s): k for k, s in enumerate(g["obs_steps"])} if "obs_steps" in g.files else None
     for ep in range(g["weights"].shape[0]):
         adj, mfea2, tfea = paral_env.init_DGFJSPEnv_state0(weights=g["weights"][ep])
         eq(adj, g["adj0"][ep].astype(np.float64)); eq(mfea2, g["mfea20"][ep]); eq(tfea, g["tfea0"][ep])
@@ -65,16 +67,19 @@ def test_parallel_env_reproduces_reference_dump(name):
             eq(mfea1, g["mfea1"][ep, s])
             joint_actions = list(zip(act[:, 0].tolist(), act[:, 1].tolist()))  # Run.py:411
             adj, oenv_info, mfea2, tfea = paral_env.DGFJSPEnv_paral_step(joint_actions)
-            eq(adj, g["adj"][ep, s].astype(np.float64)); eq(mfea2, g["mfea2"][ep, s]); eq(tfea, g["tfea"][ep, s])
             eq(np.array(oenv_info, dtype=np.float64), g["info"][ep, s])
             cand, mask = jm.esa_update_chosenTaskID_CandidateTaskIDx_JobMask(paral_env, None, 1)
             eq(cand, g["cand"][ep, s])
             if mm == 1:
                 eq(mask.cpu().numpy(), g["mask"][ep, s])
+            if kept is not None and s not in kept:
+                continue
+            k = s if kept is None else kept[s]
+            eq(adj, g["adj"][ep, k].astype(np.float64)); eq(mfea2, g["mfea2"][ep, k]); eq(tfea, g["tfea"][ep, k])
             # what algorithm/ppo_algorithm.py:271-273 reads out of the env graphs
             b0 = 0
             ft0 = [paral_env.paral_env_DG[b0].G.nodes[i + 1]["finish_time"] for i in range(N)]
-            ref_ft = [g["ft"][ep, s, b0, i] if g["mach"][ep, s, b0, i] >= 0 else None for i in range(N)]
+            ref_ft = [g["ft"][ep, k, b0, i] if g["mach"][ep, k, b0, i] >= 0 else None for i in range(N)]
             assert ft0 == ref_ft
         envs = paral_env.paral_env_DG  # Run.py:632-633
         costs = np.array([[e.makespan_previous_step, e.total_e1_previous_step / N, e.trans_t_previous_step,
