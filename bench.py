@@ -518,6 +518,7 @@ def run_ours(args, wl):
                 if it > 0:
                     cms.append(sh.max_over_ranks(t0e.elapsed_time(t1e), dev)); tms.append(sh.max_over_ranks(t0e.elapsed_time(t2e), dev))
                     ams.append(a_ms)
+                buf_bytes = btc.bytes_per_env_step()
                 del btc
             runs[variant] = (sum(tms) / len(tms), sum(cms) / len(cms), sum(ams) / len(ams), [float(x) for x in losses],
                              up.allreduce_bytes // 3)
@@ -525,7 +526,7 @@ def run_ours(args, wl):
         train = {"value": Bt * world * N / (tot * 1e-3), "unit": UNIT, "envs_per_gpu": Bt, "buffer_steps": N, "k_epochs": 1,
                  "mini_bs": N, "collect_ms": col, "update_ms": tot - col,
                  "allreduce_ms": arm, "allreduce_share": arm / tot,
-                 "allreduce_bytes_per_update": arb, "losses": losses,
+                 "allreduce_bytes_per_update": arb, "losses": losses, "buffer_bytes_per_env_step": buf_bytes,
                  "update_ms_library_fp32": runs["library_fp32"][0] - runs["library_fp32"][1],
                  "value_library_fp32": Bt * world * N / (runs["library_fp32"][0] * 1e-3),
                  "what": "one buffer (1 episode) collected with the tcgen05 rollout twins (CUDA-graph replay) + one batched PPO "
@@ -582,6 +583,25 @@ def run_ours(args, wl):
         dropin = {"value": Bd * 5 / dt, "unit": UNIT, "envs": Bd, "d2h_bytes_per_step": Bd * (N * N * 8 + N * 96 + M * 64 + 80),
                   "api": "Parallel_env.DGFJSPEnv_paral_step (reference types: python action list in, numpy f64 dense "
                          "adjacency + features + python info list out)"}
+        del pe
+        # the same call with compat="ell": adjacency as (adj_w, adj_src) device tensors, only the [B,6] step info crosses PCIe
+        pe = pem.Parallel_env({"n_job": J, "n_machine": M, "n_edge": E, "env_batch": Bd, "GAMMA": 0.99,
+                               "reward_scaling": {"scaling_divisor": 1}, "weight_mk": 0.4, "weight_ec": 0.4, "weight_tt": 0.2},
+                              compat="ell")
+        pe.get_batch({k2: torch.as_tensor(d[k1][:Bd]) for k1, k2 in (("t", "t"), ("p", "p"), ("transT", "transT"), ("edge", "edge"))})
+        pe.init_RewardScaling_sameBATCH(shape=4)
+        pe.init_DGFJSPEnv_state0(weights=w[:Bd].cpu().numpy())
+        acts_np = [np.stack((h_op[s2][:Bd].numpy(), h_mc[s2][:Bd].numpy()), axis=1) for s2 in range(12)]
+        pe.DGFJSPEnv_paral_step(acts_np[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s2 in range(1, 12):
+            pe.DGFJSPEnv_paral_step(acts_np[s2])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dropin["compat_ell"] = {"value": Bd * 11 / dt, "unit": UNIT, "envs": Bd, "d2h_bytes_per_step": Bd * 48,
+                                "api": "Parallel_env(compat='ell').DGFJSPEnv_paral_step ([B,2] int array in; (adj_w, adj_src), "
+                                       "features as device tensors and the [B,6] float64 step info out)"}
         del pe
 
     cpu = cpu_ref = None

@@ -20,9 +20,13 @@
 //
 // HBM layout (per handle, B environments; every record is 16-byte aligned):
 //   sd  [B][sd_stride] f64   dynamic doubles: st[N] ft[N] dur[N] psel[N] | mk_prev e_prev trans idle_prev |
-//                            macc[M][3] | w[3] | scaler R[4] mean[4] S[4] n
-//                            (for an unscheduled op st/ft hold the current estimate, dur = 0, psel = min energy)
-//   si  [B][si_stride] i16   dynamic ints:    mach[N] pos[N] rpred[N] cnt[M] | removed_head fresh_co nsched | nxt[J]
+//                            macc[M][3] | w[3] | eacc[L][8] eleaf[L] | scaler R[4] mean[4] S[4] n
+//                            (for an unscheduled op st/ft hold the current estimate, dur = 0, psel = min energy;
+//                            eacc / eleaf cache numpy's pairwise summation of the energy estimate: the 8 accumulators
+//                            and the result of each of its L leaves, so a step re-adds one accumulator chain only)
+//   si  [B][si_stride] i16   dynamic ints:    mach[N] ord[N] rpred[N] cnt[M] | removed_head fresh_co nsched | nxt[J]
+//                            (ord = the scheduled ops in (machine, route position) order: machine m's route is
+//                            ord[off_m, off_m + cnt[m]) with off_m = cnt[0] + ... + cnt[m-1]; rpred = route predecessor)
 //   xs  [B][xs_stride] f64   static doubles:  mind[N] minpt[N] tt[M][M]
 //   t,p [B][N][M]      f64   instance tables, touched only at (op, machine) and in the mfea1 kernel
 #include <cuda_runtime.h>
@@ -46,8 +50,8 @@ namespace {
 struct Layout {
     int B, J, M, N, E, left_shift;
     int sd_stride, si_stride, xs_stride;
-    int o_st, o_ft, o_dur, o_psel, o_scal, o_macc, o_w, o_sc;  // sd offsets (doubles)
-    int o_mach, o_pos, o_rpred, o_cnt, o_misc, o_nxt;          // si offsets (int16)
+    int o_st, o_ft, o_dur, o_psel, o_scal, o_macc, o_w, o_eacc, o_eleaf, o_sc;  // sd offsets (doubles)
+    int o_mach, o_ord, o_rpred, o_cnt, o_misc, o_nxt;          // si offsets (int16)
     int o_mind, o_minpt, o_tt;                                 // xs offsets (doubles)
     int sm_sd, sm_xs, sm_pt, sm_v, sm_leaf, sm_si, sm_off, sm_nxt, sm_tail;  // smem byte offsets per warp
     int smem_per_warp, warps_per_block;
@@ -151,8 +155,10 @@ __device__ __forceinline__ void store_row<double>(double* dst, const double* f, 
     for (int k = 0; k < n / 2; k++) d2[k] = make_double2(f[2 * k], f[2 * k + 1]);
 }
 
-// numpy pairwise sum of a[0..N) following the host-built plan; every lane returns the result
-__device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf, int lane) {
+// numpy pairwise sum of a[0..N) following the host-built plan; every lane returns the result.  eacc [nleaves][8] / eleaf
+// [nleaves] receive the 8 accumulators (before their tree) and the result of every leaf: the cache the size-specialised
+// kernel updates incrementally (one accumulator chain per step).
+__device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf, int lane, double* eacc, double* eleaf) {
     const int grp = lane >> 3, k = lane & 7;
     for (int L0 = 0; L0 < pw.nleaves; L0 += 4) {
         int Lx = L0 + grp;
@@ -163,6 +169,7 @@ __device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf
         if (n >= 8) {
             r = a[off + k];
             for (int i = 8 + k; i < nb; i += 8) r += a[off + i];
+            if (act) eacc[Lx * 8 + k] = r;
         }
         // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); every lane takes part in the shuffles
         r = r + __shfl_down_sync(FULL, r, 1, 8);
@@ -171,7 +178,7 @@ __device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf
         double res = r;  // n < 8 (only when N < 8): r is 0 and the loop below is the plain sum
         if (k == 0)
             for (int i = nb; i < n; i++) res += a[off + i];
-        if (act && k == 0) s_leaf[Lx] = res;
+        if (act && k == 0) { s_leaf[Lx] = res; eleaf[Lx] = res; }
     }
     __syncwarp();
     if (pw.nleaves == 1) return s_leaf[0];
@@ -212,7 +219,6 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
     double* s_v = reinterpret_cast<double*>(base + L.sm_v);    // per-job ESA key
     double* s_leaf = reinterpret_cast<double*>(base + L.sm_leaf);
     int16_t* s_si = reinterpret_cast<int16_t*>(base + L.sm_si);
-    int* s_off = reinterpret_cast<int*>(base + L.sm_off);
     int16_t* s_nxt = reinterpret_cast<int16_t*>(base + L.sm_nxt);
     int16_t* s_tail = reinterpret_cast<int16_t*>(base + L.sm_tail);
 
@@ -243,21 +249,24 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
     double* s_w = s_sd + L.o_w;
     double* s_sc = s_sd + L.o_sc;  // R[4] mean[4] S[4] n
     int16_t* s_mach = s_si + L.o_mach;
-    int16_t* s_pos = s_si + L.o_pos;
+    int16_t* s_ord = s_si + L.o_ord;
     int16_t* s_rpred = s_si + L.o_rpred;
     int16_t* s_cnt = s_si + L.o_cnt;
     int16_t* s_misc = s_si + L.o_misc;  // removed_head, fresh_co, nsched
     const double* s_mind = s_xs + L.o_mind;
     const double* s_minpt = s_xs + L.o_minpt;
     const double* s_tt = s_xs + L.o_tt;
+    double* s_eacc = s_sd + L.o_eacc;    // cached pairwise-sum accumulators / leaf results of the energy estimate
+    double* s_eleaf = s_sd + L.o_eleaf;
 
     if (MODE & MODE_RESET) {  // load_instance + reset, SS:397-714, 1183-1245
         __syncwarp();
         for (int i = lane; i < 4 * N; i += 32) s_sd[L.o_st + i] = 0.0;  // st ft dur psel are contiguous
         for (int i = lane; i < 3 * M; i += 32) s_macc[i] = 0.0;
+        for (int i = L.o_eacc + lane; i < L.o_sc; i += 32) s_sd[i] = 0.0;
         if (lane < 3) s_w[lane] = P.weights[(size_t)b * 3 + lane];
         if (lane < 4) s_scal[lane] = 0.0;
-        for (int i = lane; i < N; i += 32) { s_mach[i] = -1; s_pos[i] = -1; s_rpred[i] = -1; }
+        for (int i = lane; i < N; i += 32) { s_mach[i] = -1; s_ord[i] = -1; s_rpred[i] = -1; }
         for (int i = lane; i < M; i += 32) s_cnt[i] = 0;
         if (lane == 0) { s_misc[0] = -1; s_misc[1] = -1; s_misc[2] = 0; }
         for (int i = L.o_misc + 3 + lane; i < L.si_stride; i += 32) s_si[i] = 0;
@@ -295,34 +304,36 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
             const double ttmm = s_tt[m * M + m];
             double st = arr_a;
             int where = 0, prev = -1, next = -1;
+            // machine m's route is ord[offm, offm + len)
+            int offm = 0;
+            for (int m0 = 0; m0 < m; m0 += 32) offm += __reduce_add_sync(FULL, (m0 + lane < m) ? (int)s_cnt[m0 + lane] : 0);
             if (len > 0) {
-                // one pass over the ops of machine m: arrival of each, first feasible slot, route tail
+                // one pass over the route of machine m: arrival of each op, first feasible slot (SS:1548-1601)
                 const double lbft = arr_a + d;
                 unsigned best = 0xffffffffu;
-                int lastop = -1;
-                for (int v0 = 0; v0 < N; v0 += 32) {
-                    int v = v0 + lane;
-                    unsigned key = 0xffffffffu;
-                    if (v < N && s_mach[v] == m) {
-                        int k = s_pos[v], rp = s_rpred[v];
-                        if (k == len - 1) lastop = v;
-                        if (L.left_shift) {
-                            bool vfirst = (v % M) == 0;
+                const int lastop = s_ord[offm + len - 1];
+                if (L.left_shift) {
+                    for (int k0 = 0; k0 < len; k0 += 32) {
+                        const int k = k0 + lane;
+                        unsigned key = 0xffffffffu;
+                        if (k < len) {
+                            const int v = s_ord[offm + k];
+                            const bool vfirst = (v % M) == 0;
                             double nst = vfirst ? 0.0 : s_ft[v - 1] + s_tt[s_mach[v - 1] * M + m];
                             bool ok;
                             if (k == 0) {
                                 ok = (lbft <= nst);  // SS:1548 (route head has no machine in-arc)
                             } else {
+                                const int rp = s_ord[offm + k - 1];
                                 double val = s_ft[rp] + ((rp / M == v / M) ? ttmm : 0.0);
                                 nst = fmax(nst, val);
                                 ok = !(lbft > nst) && !((nst - s_ft[rp]) < d);  // SS:1597-1601
                             }
                             if (ok) key = ((unsigned)k << 16) | (unsigned)v;
                         }
+                        best = min(best, __reduce_min_sync(FULL, key));
                     }
-                    best = min(best, __reduce_min_sync(FULL, key));
                 }
-                lastop = __reduce_max_sync(FULL, lastop);
                 if (best != 0xffffffffu) {
                     where = (int)(best >> 16);
                     next = (int)(best & 0xffffu);
@@ -345,21 +356,23 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
             }
             o_next = next;
             __syncwarp();
-            // ---- apply: shift route positions behind the slot, link the op in ----
-            for (int v = lane; v < N; v += 32)
-                if (s_mach[v] == m && s_pos[v] >= where) {
-                    int16_t np_ = (int16_t)(s_pos[v] + 1);
-                    s_pos[v] = np_;
-                    g_si[L.o_pos + v] = np_;
-                }
-            __syncwarp();
+            // ---- apply: open slot p of the flat order (entries behind it move up by one), link the op in ----
+            const int p = offm + where;
+            for (int g0 = ((nsched0 > 0 ? nsched0 - 1 : 0) / 32) * 32; g0 >= 0 && g0 + 31 >= p; g0 -= 32) {
+                const int g = g0 + lane;
+                const bool mv_ = g >= p && g < nsched0;
+                const int16_t x = mv_ ? s_ord[g] : (int16_t)0;
+                __syncwarp();
+                if (mv_) { s_ord[g + 1] = x; g_si[L.o_ord + g + 1] = x; }
+                __syncwarp();
+            }
             if (lane == 0) {
-                s_mach[a] = (int16_t)m; s_pos[a] = (int16_t)where; s_rpred[a] = (int16_t)prev;
+                s_mach[a] = (int16_t)m; s_ord[p] = (int16_t)a; s_rpred[a] = (int16_t)prev;
                 if (next >= 0) s_rpred[next] = (int16_t)a;
                 s_cnt[m] = (int16_t)(len + 1);
                 s_misc[0] = (int16_t)rem_head; s_misc[1] = (int16_t)fresh; s_misc[2] = (int16_t)(nsched0 + 1);
                 s_st[a] = st; s_ft[a] = st + d; s_dur[a] = d; s_psel[a] = pa;
-                g_si[L.o_mach + a] = (int16_t)m; g_si[L.o_pos + a] = (int16_t)where; g_si[L.o_rpred + a] = (int16_t)prev;
+                g_si[L.o_mach + a] = (int16_t)m; g_si[L.o_ord + p] = (int16_t)a; g_si[L.o_rpred + a] = (int16_t)prev;
                 if (next >= 0) g_si[L.o_rpred + next] = (int16_t)a;
                 g_si[L.o_cnt + m] = (int16_t)(len + 1);
                 g_si[L.o_misc + 0] = (int16_t)rem_head; g_si[L.o_misc + 1] = (int16_t)fresh;
@@ -376,32 +389,13 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
             __syncwarp();
             const int nsched = nsched0 + 1;
             done = (nsched == N);
-            // ---- idle time: sequential sum in (machine, route) order, DGenv_func.py:144-170 ----
-            {
-                int carry = 0;
-                for (int m0 = 0; m0 < M; m0 += 32) {
-                    int mm = m0 + lane;
-                    int c = (mm < M) ? (int)s_cnt[mm] : 0;
-                    int inc = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int n_ = __shfl_up_sync(FULL, inc, o);
-                        if (lane >= o) inc += n_;
-                    }
-                    if (mm < M) s_off[mm] = carry + inc - c;
-                    carry += __shfl_sync(FULL, inc, 31);
-                }
-                __syncwarp();
-                for (int v = lane; v < N; v += 32) {
-                    int mv = s_mach[v];
-                    if (mv >= 0) {
-                        int rp = s_rpred[v];
-                        double term = (rp < 0) ? (s_st[v] - 0.0) : (s_st[v] - s_ft[rp]);
-                        s_pt[s_off[mv] + s_pos[v]] = term * 1.0;
-                    }
-                }
-                __syncwarp();
+            // ---- idle time: sequential sum in (machine, route) order = flat order, DGenv_func.py:144-170 ----
+            for (int g = lane; g < nsched; g += 32) {
+                const int v = s_ord[g], rp = s_rpred[v];
+                const double term = (rp < 0) ? (s_st[v] - 0.0) : (s_st[v] - s_ft[rp]);
+                s_pt[g] = term * 1.0;
             }
+            __syncwarp();
 #pragma unroll 4
             for (int g = 0; g < nsched; g++) idle = idle + s_pt[g];
             __syncwarp();
@@ -441,7 +435,7 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
         __syncwarp();
         if (MODE & (MODE_STEP | MODE_RESET)) {
             mkv = warp_max(mx);
-            env = pairwise_sum(s_pt, P.pw, s_leaf, lane);
+            env = pairwise_sum(s_pt, P.pw, s_leaf, lane, s_eacc, s_eleaf);
         }
     }
 
@@ -509,6 +503,7 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 int idx = lane < 4 ? L.o_scal + lane : lane < 7 ? L.o_macc + m * 3 + (lane - 4) : L.o_sc + (lane - 7);
                 g_sd[idx] = s_sd[idx];
             }
+            for (int i = L.o_eacc + lane; i < L.o_sc; i += 32) g_sd[i] = s_sd[i];  // energy-sum cache (this kernel recomputes all of it)
             if (lane == 0) {
                 if (P.reward5) {
                     double* r5 = P.reward5 + (size_t)b * 5;
@@ -616,11 +611,22 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 if (xv >= 0) emit_row(xv);
             }
         } else {
-            for (int v = lane; v < N; v += 32) {
-                const int mv = s_mach[v];
-                if (mv >= 0 && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
-                emit_row(v);
+            {   // route tails: last entry of each machine's range of the flat order
+                int carry = 0;
+                for (int m0 = 0; m0 < M; m0 += 32) {
+                    const int mm = m0 + lane;
+                    const int c = (mm < M) ? (int)s_cnt[mm] : 0;
+                    int inc_ = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int n_ = __shfl_up_sync(FULL, inc_, o);
+                        if (lane >= o) inc_ += n_;
+                    }
+                    if (mm < M && c > 0) s_tail[mm] = s_ord[carry + inc_ - 1];
+                    carry += __shfl_sync(FULL, inc_, 31);
+                }
             }
+            for (int v = lane; v < N; v += 32) emit_row(v);
         }
         __syncwarp();
         if (P.mfea) {  // SS:2315-2354
@@ -651,28 +657,44 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
 // in st/ft (only the stepped job's chain changes per step), dur = 0 and psel = min feasible energy.
 // =====================================================================================================
 constexpr int calign(int x, int a) { return (x + a - 1) / a * a; }
+// shape of numpy's pairwise summation of n elements (leaves of <= 128 elements, split at n/2 rounded down to a multiple
+// of 8): number of leaves, longest accumulator chain of a leaf, and the combination of the leaf results
+__host__ __device__ constexpr int pw_nleaf(int n) { return n <= 128 ? 1 : pw_nleaf(n / 2 - (n / 2) % 8) + pw_nleaf(n - (n / 2 - (n / 2) % 8)); }
+__host__ __device__ constexpr int pw_maxchain(int n) {
+    if (n <= 128) return (n - n % 8) / 8;
+    const int a = pw_maxchain(n / 2 - (n / 2) % 8), b = pw_maxchain(n - (n / 2 - (n / 2) % 8));
+    return a > b ? a : b;
+}
+template <int N_>
+__device__ __forceinline__ double pw_combine(const double* leaf) {
+    if constexpr (N_ <= 128) {
+        return leaf[0];
+    } else {
+        constexpr int n2 = N_ / 2 - (N_ / 2) % 8;
+        constexpr int nl = pw_nleaf(n2);
+        const double x = pw_combine<n2>(leaf);
+        const double y = pw_combine<N_ - n2>(leaf + nl);
+        return x + y;
+    }
+}
 
 template <int J_, int M_, int G_, int WARPS_>
 struct Spec {
     static constexpr int J = J_, M = M_, G = G_, N = J_ * M_, EPW = 32 / G_, WARPS = WARPS_;
     static_assert(J_ <= G_ && M_ <= G_, "one lane per job and per machine");
     static_assert(3 * M_ <= J_ * M_, "the random-step mode parks three compacted machine rows in the op scratch");
-    static_assert(J_ * M_ <= 128 || G_ == 32, "more than one numpy leaf: pairwise_sum works on a whole warp per env");
-    static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 13, 2);
+    static constexpr int NLEAF = pw_nleaf(N), CHAIN = pw_maxchain(N);
+    static_assert(N >= 8 && CHAIN <= G_, "one lane per term of an accumulator chain");
+    static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 9 * NLEAF + 13, 2);
     static constexpr int SI = calign(3 * N + M + 3 + J, 8);
     static constexpr int XS = calign(2 * N + M * M, 2);
     static constexpr int TT = calign(M * M, 2);  // only the transport table is staged from xs
     static constexpr int O_ST = 0, O_FT = N, O_DUR = 2 * N, O_PSEL = 3 * N, O_SCAL = 4 * N, O_MACC = 4 * N + 4,
-                         O_W = O_MACC + 3 * M, O_SC = O_W + 3;
-    static constexpr int O_MACH = 0, O_POS = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
+                         O_W = O_MACC + 3 * M, O_EACC = O_W + 3, O_ELEAF = O_EACC + 8 * NLEAF, O_SC = O_ELEAF + NLEAF;
+    static constexpr int O_MACH = 0, O_ORD = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
     static constexpr int O_MIND = 0, O_TT = 2 * N;
-    // large instances: the pairwise-sum leaf scratch is idle at both ends of the kernel, so the warp's mbarrier (start)
-    // and the route-tail table (end) live in it -- at J30M20 that is what lets a seventh warp fit on an SM
-    static constexpr bool ALIAS = N > 128;
-    static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 4) * 8, B_SI = SI * 2,
-                         B_TAIL = ALIAS ? 0 : calign(M, 8) * 2, B_LEAF = ALIAS ? (MAX_LEAVES + 32) * 8 : 0;
-    static_assert(!ALIAS || 16 + calign(M_, 8) * 2 <= (MAX_LEAVES + 32) * 8, "aliased scratch");
-    static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_LEAF + B_SI + B_TAIL, 16);
+    static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 4) * 8, B_SI = SI * 2;
+    static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_SI, 16);
     // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
     static constexpr int ENV_BYTES = (G_ == 8) ? (RAW + ((64 - RAW % 128) + 128) % 128) : RAW;
     static constexpr bool BAR_IN_PAD = ENV_BYTES - RAW >= 8;
@@ -708,7 +730,7 @@ __device__ __forceinline__ double gmin_d(double v) {
 // 32-bit reductions over a lane group: one redux.sync with the group's member mask (the groups of a warp execute it
 // together, each with its own mask) instead of log2(G) shuffle + min/max pairs
 __device__ __forceinline__ unsigned gmin_u(unsigned v, unsigned gmask) { return __reduce_min_sync(gmask, v); }
-__device__ __forceinline__ int gmax_i(int v, unsigned gmask) { return __reduce_max_sync(gmask, v); }
+
 
 // adj_val without the 64-bit integer round trip: trunc() is exact for |w| < 2^53
 __device__ __forceinline__ double adj_val_t(double w, bool u_assigned, double dur_u) {
@@ -772,10 +794,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     double* s_sd = reinterpret_cast<double*>(base);
     const double* __restrict__ s_tt = reinterpret_cast<const double*>(base + S::B_SD);
     double* __restrict__ s_pt = reinterpret_cast<double*>(base + S::B_SD + S::B_TT);
-    double* s_leaf = reinterpret_cast<double*>(base + S::B_SD + S::B_TT + S::B_PT);
-    int16_t* __restrict__ s_si = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF);
-    int16_t* __restrict__ s_tail = S::ALIAS ? reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + 16)
-                                            : reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT + S::B_LEAF + S::B_SI);
+    int16_t* __restrict__ s_si = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT);
 
     double* g_sd = P.sd + (size_t)bc * S::SD;
     int16_t* g_si = P.si + (size_t)bc * S::SI;
@@ -802,8 +821,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     // were 5 % slower: 74.4 -> 70.5 us.)
     // the warp's mbarrier lives in the bank padding of its first env where there is one (J6M6: shared memory is exactly
     // what six blocks per SM leave), else behind the env regions
-    uint64_t* s_bar = S::ALIAS ? reinterpret_cast<uint64_t*>(smem_raw + (size_t)(warp * EPW) * S::ENV_BYTES + S::B_SD + S::B_TT + S::B_PT)
-                      : S::BAR_IN_PAD
+    uint64_t* s_bar = S::BAR_IN_PAD
                           ? reinterpret_cast<uint64_t*>(smem_raw + (size_t)(warp * EPW) * S::ENV_BYTES + S::RAW)
                           : reinterpret_cast<uint64_t*>(smem_raw + (size_t)S::WARPS * EPW * S::ENV_BYTES) + warp;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
@@ -880,7 +898,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     const double* __restrict__ s_w = s_sd + S::O_W;
     double* __restrict__ s_sc = s_sd + S::O_SC;
     int16_t* __restrict__ s_mach = s_si + S::O_MACH;
-    int16_t* __restrict__ s_pos = s_si + S::O_POS;
+    int16_t* __restrict__ s_ord = s_si + S::O_ORD;
     int16_t* __restrict__ s_rpred = s_si + S::O_RPRED;
     int16_t* __restrict__ s_cnt = s_si + S::O_CNT;
     int16_t* __restrict__ s_misc = s_si + S::O_MISC;
@@ -954,34 +972,42 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const int len = s_cnt[mc];
         const double ttmm = s_tt[mc * M + mc];
         const double lbft = arr_a + d;
-        unsigned best = 0xffffffffu;
-        int lastop = -1;
+        // machine k's route is ord[off_k, off_k + cnt[k]): exclusive scan of the route lengths over the group's lanes
+        int offm;
+        {
+            const int c = (gl < M) ? (int)s_cnt[gl] : 0;
+            int inc = c;
 #pragma unroll
-        for (int it = 0; it < ITER; it++) {
-            const int v = gl + it * G;
-            if (v < N && s_mach[v] == mc) {
-                const int k = s_pos[v], rp = s_rpred[v];
-                if (k == len - 1) lastop = v;
-                if (P.L.left_shift) {
-                    const bool vfirst = (v % M) == 0;
-                    const int vp = vfirst ? v : v - 1;
-                    int mvp = s_mach[vp];
-                    mvp = mvp < 0 ? 0 : mvp;
-                    double nst = vfirst ? 0.0 : s_ft[vp] + s_tt[mvp * M + mc];
-                    bool ok;
-                    if (k == 0) {
-                        ok = (lbft <= nst);  // SS:1548
-                    } else {
-                        const double val = s_ft[rp] + ((rp / M == v / M) ? ttmm : 0.0);
-                        nst = fmax(nst, val);
-                        ok = !(lbft > nst) && !((nst - s_ft[rp]) < d);  // SS:1597-1601
-                    }
-                    if (ok) best = min(best, ((unsigned)k << 16) | (unsigned)v);
+            for (int o = 1; o < G; o <<= 1) {
+                const int n_ = __shfl_up_sync(FULL, inc, o, G);
+                if (gl >= o) inc += n_;
+            }
+            offm = __shfl_sync(FULL, inc - c, mc, G);
+        }
+        // one pass over the route of machine m (not over all ops): first feasible slot, SS:1548-1601
+        unsigned best = 0xffffffffu;
+        const int lastop = len > 0 ? (int)s_ord[offm + len - 1] : -1;
+        if (P.L.left_shift) {
+            for (int k = gl; k < len; k += G) {
+                const int v = s_ord[offm + k];
+                const bool vfirst = (v % M) == 0;
+                const int vp = vfirst ? v : v - 1;
+                int mvp = s_mach[vp];
+                mvp = mvp < 0 ? 0 : mvp;
+                double nst = vfirst ? 0.0 : s_ft[vp] + s_tt[mvp * M + mc];
+                bool ok;
+                if (k == 0) {
+                    ok = (lbft <= nst);  // SS:1548
+                } else {
+                    const int rp = s_ord[offm + k - 1];
+                    const double val = s_ft[rp] + ((rp / M == v / M) ? ttmm : 0.0);
+                    nst = fmax(nst, val);
+                    ok = !(lbft > nst) && !((nst - s_ft[rp]) < d);  // SS:1597-1601
                 }
+                if (ok) best = min(best, ((unsigned)k << 16) | (unsigned)v);
             }
         }
         best = gmin_u(best, gmask);
-        lastop = gmax_i(lastop, gmask);
         double st = arr_a;
         int where = 0, prev = -1, next = -1, rem_head = -1, fresh = -1;
         if (len > 0) {
@@ -1019,31 +1045,34 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             }
         }
         __syncwarp();
-        if (valid) {
+        // ---- apply: open slot p of the flat order (entries behind it move up by one, highest chunk first) ----
+        const int p = offm + where;
+        {
+            const int it_lo = (G == 32) ? (p / G) : 0;  // one env per warp: the trip count is warp-uniform
 #pragma unroll
-            for (int it = 0; it < ITER; it++) {
-                const int v = gl + it * G;
-                if (v < N && s_mach[v] == mc && s_pos[v] >= where) {
-                    const int16_t np_ = (int16_t)(s_pos[v] + 1);
-                    s_pos[v] = np_;
-                    g_si[S::O_POS + v] = np_;
-                }
+            for (int it = ITER - 1; it >= 0; --it) {
+                if (it < it_lo) break;
+                const int g = gl + it * G;
+                const bool mv_ = valid && g >= p && g < nsched0;
+                const int16_t x = mv_ ? s_ord[g] : (int16_t)0;
+                __syncwarp();
+                if (mv_) { s_ord[g + 1] = x; g_si[S::O_ORD + g + 1] = x; }
             }
-            if (gl > apos && gl < M) {
-                const int idx = ja * M + gl;
-                s_st[idx] = my_st; s_ft[idx] = my_ft;
-                g_sd[S::O_ST + idx] = my_st; g_sd[S::O_FT + idx] = my_ft;
-            }
+        }
+        if (valid && gl > apos && gl < M) {
+            const int idx = ja * M + gl;
+            s_st[idx] = my_st; s_ft[idx] = my_ft;
+            g_sd[S::O_ST + idx] = my_st; g_sd[S::O_FT + idx] = my_ft;
         }
         __syncwarp();
         if (valid && gl == 0) {
-            s_mach[ac] = (int16_t)mc; s_pos[ac] = (int16_t)where; s_rpred[ac] = (int16_t)prev;
+            s_mach[ac] = (int16_t)mc; s_ord[p] = (int16_t)ac; s_rpred[ac] = (int16_t)prev;
             if (next >= 0) s_rpred[next] = (int16_t)ac;
             s_cnt[mc] = (int16_t)(len + 1);
             s_misc[0] = (int16_t)rem_head; s_misc[1] = (int16_t)fresh; s_misc[2] = (int16_t)(nsched0 + 1);
             s_nxt[ja] = (int16_t)(apos + 1);
             s_st[ac] = st; s_ft[ac] = st + d; s_dur[ac] = d; s_psel[ac] = pa;
-            g_si[S::O_MACH + ac] = (int16_t)mc; g_si[S::O_POS + ac] = (int16_t)where; g_si[S::O_RPRED + ac] = (int16_t)prev;
+            g_si[S::O_MACH + ac] = (int16_t)mc; g_si[S::O_ORD + p] = (int16_t)ac; g_si[S::O_RPRED + ac] = (int16_t)prev;
             if (next >= 0) g_si[S::O_RPRED + next] = (int16_t)ac;
             g_si[S::O_CNT + mc] = (int16_t)(len + 1);
             g_si[S::O_MISC + 0] = (int16_t)rem_head; g_si[S::O_MISC + 1] = (int16_t)fresh;
@@ -1056,23 +1085,14 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         done = (nsched == N);
         // ---- idle time: sequential sum in (machine, route) order, DGenv_func.py:144-170 ----
         {
-            const int c = (gl < M) ? (int)s_cnt[gl] : 0;
-            int inc = c;
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) {
-                const int n_ = __shfl_up_sync(FULL, inc, o, G);
-                if (gl >= o) inc += n_;
-            }
-            const int off = inc - c;
+            // terms in (machine, route) order = flat order; a route head's term is its start time
 #pragma unroll
             for (int it = 0; it < ITER; it++) {
-                const int v = gl + it * G;
-                const int mv = (v < N) ? (int)s_mach[v] : -1;
-                const int offv = __shfl_sync(FULL, off, mv >= 0 ? mv : 0, G);
-                if (mv >= 0) {
-                    const int rp = s_rpred[v];
+                const int g = gl + it * G;
+                if (g < nsched) {
+                    const int v = s_ord[g], rp = s_rpred[v];
                     const double term = (rp < 0) ? (s_st[v] - 0.0) : (s_st[v] - s_ft[rp]);
-                    s_pt[offv + s_pos[v]] = term * 1.0;
+                    s_pt[g] = term * 1.0;
                 }
             }
             // the sum is a chain of dependent additions in the reference's order; x + 0.0 == x exactly (gaps are never
@@ -1097,17 +1117,6 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         __syncwarp();
     }
 
-    // ---- estimated energy per op (SS:1995, 2175); lanes keep their own ops in registers ----
-    double ept[ITER];
-#pragma unroll
-    for (int it = 0; it < ITER; it++) {
-        const int v = gl + it * G;
-        ept[it] = 0.0;
-        if (v < N) {
-            ept[it] = (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_psel[v];
-            if (MODE & MODE_STEP) s_pt[v] = ept[it];
-        }
-    }
     // per job (lane j): ops scheduled so far, ESA key = finish of its last scheduled op, row maximum
     int nx = 0;
     double vj = INFINITY, jmx = -INFINITY;
@@ -1121,24 +1130,56 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
 
     if (MODE & MODE_STEP) {
         const double mkv = gmax_d<G>(jmx);  // SS:894
+        // ---- energy estimate (SS:896): np.sum over all ops of (scheduled ? t * p : min energy), numpy's pairwise
+        // summation.  Only the stepped op's term changed, so of the cached per-leaf state (8 accumulators r[k] = a[k] +
+        // a[8+k] + ..., then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail elements one by one) only accumulator
+        // (x mod 8) of the op's leaf is re-added -- every addition in numpy's order, so the total is bit-identical to
+        // a full recomputation (which the generic kernel does, and the parity suite compares).
         double en;
-        if constexpr (N <= 128) {  // one numpy leaf: 8 accumulators, then the tail (SS:896)
-            constexpr int NB = (N >= 8) ? N - (N & 7) : 0;
-            const int k = gl & 7;
-            double r = 0.0;
-            if (N >= 8) {
-                r = s_pt[k];
+        {
+            double* __restrict__ s_eacc = s_sd + S::O_EACC;
+            double* __restrict__ s_eleaf = s_sd + S::O_ELEAF;
+            int lf = 0, loff = 0, ln = N;
+            if constexpr (S::NLEAF > 1) {
 #pragma unroll
-                for (int i = 8; i < NB; i += 8) r += s_pt[i + k];
+                for (int q = 1; q < S::NLEAF; q++)
+                    if (ac >= P.pw.leaf_off[q]) lf = q;
+                loff = P.pw.leaf_off[lf];
+                ln = P.pw.leaf_len[lf];
             }
-            r = r + __shfl_down_sync(FULL, r, 1, 8);
-            r = r + __shfl_down_sync(FULL, r, 2, 8);
-            r = r + __shfl_down_sync(FULL, r, 4, 8);
+            const int nb = ln - (ln & 7), x = ac - loff, k = x & 7;
+            auto ept_of = [&](const int v) { return (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_psel[v]; };
+            // accumulator chain k: lane i fetches term i, the additions run in order on every lane of the group
+            const int nterm = (x < nb) ? (nb >> 3) : 0;
+            const double term = (gl < nterm) ? ept_of(loff + k + 8 * gl) : 0.0;
+            double r = __shfl_sync(FULL, term, 0, G);
 #pragma unroll
-            for (int i = NB; i < N; i++) r += s_pt[i];
-            en = __shfl_sync(FULL, r, 0, G);
-        } else {
-            en = pairwise_sum(s_pt, P.pw, s_leaf, lane);
+            for (int i = 1; i < S::CHAIN; i++) {
+                const double t_ = __shfl_sync(FULL, term, i, G);
+                if (i < nterm) r = r + t_;
+            }
+            if (valid && nterm > 0 && gl == 0) { s_eacc[lf * 8 + k] = r; g_sd[S::O_EACC + lf * 8 + k] = r; }
+            __syncwarp();
+            double e8 = s_eacc[lf * 8 + (gl & 7)];
+            e8 = e8 + __shfl_down_sync(FULL, e8, 1, 8);
+            e8 = e8 + __shfl_down_sync(FULL, e8, 2, 8);
+            e8 = e8 + __shfl_down_sync(FULL, e8, 4, 8);
+            double leaf = __shfl_sync(FULL, e8, 0, G);
+            const int ntail = ln & 7;
+            const double tl = (gl < ntail) ? ept_of(loff + nb + gl) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                const double t_ = __shfl_sync(FULL, tl, i, G);
+                if (i < ntail) leaf = leaf + t_;
+            }
+            if constexpr (S::NLEAF > 1) {
+                if (valid && gl == 0) { s_eleaf[lf] = leaf; g_sd[S::O_ELEAF + lf] = leaf; }
+                __syncwarp();
+                en = pw_combine<N>(s_eleaf);
+            } else {
+                if (valid && gl == 0) g_sd[S::O_ELEAF] = leaf;
+                en = leaf;
+            }
         }
         // ---- reward (SS:1066-1132) and reward scaling (ppo_trick.py:73-88,115-119) ----
         const double mk_prev = s_scal[0], e_prev = s_scal[1], trans_prev = s_scal[2], idle_prev = s_scal[3];
@@ -1309,17 +1350,20 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         for (int it = 0; it < ITER; it++) {
             if (inc && it >= 2) break;
             const int v = inc ? (it == 0 ? row0 : row1) : gl + it * G;
-            if (v >= 0 && v < N) {
-                const int mv = s_mach[v];
-                if (!inc && mv >= 0 && s_pos[v] == s_cnt[mv] - 1) s_tail[mv] = (int16_t)v;
-                if (active) emit_row(v, inc ? ((mv >= 0) ? s_dur[v] * s_psel[v] : s_psel[v]) : ept[it]);
-            }
+            if (v >= 0 && v < N && active) emit_row(v, (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_psel[v]);
         }
         if (inc) {
             if (P.mfea && valid && gl == 0) emit_mach(mc, o_tail);
         } else {
-            __syncwarp();
-            if (P.mfea && gl < M && active) emit_mach(gl, s_tail[gl]);
+            // lane k = machine k: its route is the k-th range of the flat order, the tail its last entry
+            const int c = (gl < M) ? (int)s_cnt[gl] : 0;
+            int incs = c;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const int n_ = __shfl_up_sync(FULL, incs, o, G);
+                if (gl >= o) incs += n_;
+            }
+            if (P.mfea && gl < M && active) emit_mach(gl, c > 0 ? (int)s_ord[incs - 1] : 0);
         }
     }
 }
@@ -1637,7 +1681,13 @@ __global__ void export_kernel(Layout L, const double* __restrict__ sd, const int
     if (mach) mach[gid] = mv;
     if (st) st[gid] = mv >= 0 ? sd[b * L.sd_stride + L.o_st + i] : 0.0;
     if (ft) ft[gid] = mv >= 0 ? sd[b * L.sd_stride + L.o_ft + i] : 0.0;
-    if (routes && mv >= 0) routes[(b * L.M + mv) * L.N + si[b * L.si_stride + L.o_pos + i]] = i;
+    if (routes && i < L.M) {  // thread (b, m): machine m's route is its range of the flat order
+        const int16_t* q = si + b * L.si_stride;
+        int off = 0;
+        for (int k = 0; k < i; k++) off += q[L.o_cnt + k];
+        const int c = q[L.o_cnt + i];
+        for (int k = 0; k < c; k++) routes[(b * L.M + i) * L.N + k] = q[L.o_ord + off + k];
+    }
 }
 
 __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
@@ -1812,10 +1862,11 @@ static int launch_env(mtfjsp_env* h, const Params& P, cudaStream_t s) {
 template <class S, int MODE, typename OutT>
 static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     const Layout& L = h->L;
-    if (L.sd_stride != S::SD || L.si_stride != S::SI || L.xs_stride != S::XS || L.o_sc != S::O_SC || L.o_misc != S::O_MISC)
+    if (L.sd_stride != S::SD || L.si_stride != S::SI || L.xs_stride != S::XS || L.o_sc != S::O_SC || L.o_misc != S::O_MISC ||
+        L.o_eacc != S::O_EACC || L.o_eleaf != S::O_ELEAF || h->pw.nleaves != S::NLEAF)
         return fail(MTFJSP_E_STATE, "specialised kernel layout mismatch");
     static const size_t extra = getenv("MTFJSP_EXTRA_SMEM") ? (size_t)atoi(getenv("MTFJSP_EXTRA_SMEM")) : 0;  // occupancy experiments
-    const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES + ((S::BAR_IN_PAD || S::ALIAS) ? 0 : 16 * ((S::WARPS * 8 + 15) / 16)) + extra;
+    const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES + (S::BAR_IN_PAD ? 0 : 16 * ((S::WARPS * 8 + 15) / 16)) + extra;
     static thread_local int configured_dev = -1;
     if (configured_dev != h->device) {
         CK(cudaFuncSetAttribute(env_kernel_s<S, MODE, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -1966,9 +2017,11 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     const int N = J * M;
     L.B = B; L.J = J; L.M = M; L.N = N; L.E = E; L.left_shift = left_shift ? 1 : 0;
     L.o_st = 0; L.o_ft = N; L.o_dur = 2 * N; L.o_psel = 3 * N; L.o_scal = 4 * N; L.o_macc = 4 * N + 4;
-    L.o_w = L.o_macc + 3 * M; L.o_sc = L.o_w + 3;
+    h->pw.nleaves = 0; h->pw.nprog = 0;
+    build_plan_rec(0, N, h->pw);
+    L.o_w = L.o_macc + 3 * M; L.o_eacc = L.o_w + 3; L.o_eleaf = L.o_eacc + 8 * h->pw.nleaves; L.o_sc = L.o_eleaf + h->pw.nleaves;
     L.sd_stride = align_up(L.o_sc + 13, 2);
-    L.o_mach = 0; L.o_pos = N; L.o_rpred = 2 * N; L.o_cnt = 3 * N; L.o_misc = 3 * N + M;
+    L.o_mach = 0; L.o_ord = N; L.o_rpred = 2 * N; L.o_cnt = 3 * N; L.o_misc = 3 * N + M;
     L.o_nxt = L.o_misc + 3;
     L.si_stride = align_up(L.o_nxt + J, 8);
     L.o_mind = 0; L.o_minpt = N; L.o_tt = 2 * N;
@@ -1988,8 +2041,6 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     while (wpb > 1 && (size_t)wpb * L.smem_per_warp > 200 * 1024) wpb >>= 1;
     if ((size_t)wpb * L.smem_per_warp > 227 * 1024) { delete h; return fail(MTFJSP_E_ARG, "instance too large for shared memory"); }
     L.warps_per_block = wpb;
-    h->pw.nleaves = 0; h->pw.nprog = 0;
-    build_plan_rec(0, N, h->pw);
     h->device = device;
     {
         const char* fg = getenv("MTFJSP_FORCE_GENERIC");  // test hook: run the generic kernel on every size

@@ -137,7 +137,16 @@ class _EnvProxy:
 
 
 class Parallel_env(object):
-    def __init__(self, args, device=None, left_shift=True, return_torch=False):
+    def __init__(self, args, device=None, left_shift=True, return_torch=False, compat="dense"):
+        """compat="dense" (default): the reference's return types exactly -- `adj` is a dense float64 [B,N,N] array.
+        compat="ell": `adj` is the tuple `(adj_w [B,N,2] f32, adj_src [B,N] i16)` of device tensors (compact ELL form,
+        10 bytes per op instead of 8 N), the features are device tensors as well and the step info a [B,6] float64 array;
+        `compat.ell_to_block_sparse` turns the tuple into the block-diagonal sparse matrix the reference networks build
+        from the dense one (INTEGRATION.md has the patch for model/actor_critic.py:134-156).  Nothing but the [B,6] step
+        info leaves the device per step."""
+        if compat not in ("dense", "ell"):
+            raise ValueError("compat must be 'dense' or 'ell'")
+        self.compat = compat
         self.njobs = args["n_job"]
         self.nmachines = args["n_machine"]
         self.ntasks = self.njobs * self.nmachines
@@ -216,6 +225,15 @@ class Parallel_env(object):
         mc = torch.as_tensor(np.ascontiguousarray(acts[:, 1])).to(dev)
         self._env.step_obs(op, mc, MASK_ESA)
         self._invalidate()
+        if self.compat == "ell":
+            e = self._env
+            info = torch.cat((e.reward5[:, :1], e.done.to(torch.float64).unsqueeze(1), e.scaled4), dim=1).cpu().numpy()
+            self.oenv_info = info
+            if bool(e.invalid.any()):
+                print("============= 'DGFJSPEnv_paral_step': invalid (task, machine) for envs",
+                      torch.nonzero(e.invalid).flatten().tolist())
+            adj, mfea, tfea = self._emit_obs()
+            return adj, info, mfea, tfea
         r5 = self._env.reward5.cpu().numpy()
         s4 = self._env.scaled4.cpu().numpy()
         done = self._env.done.cpu().numpy()
@@ -235,6 +253,10 @@ class Parallel_env(object):
 
     # ---- helpers ------------------------------------------------------------------------------------------------
     def _emit_obs(self):
+        if self.compat == "ell":   # device tensors, fresh copies (the env rewrites its own buffers in place every step)
+            e = self._env
+            return ((e.adj_w.clone(), e.adj_src.clone()), e.mach_fea.clone(),
+                    e.task_fea.reshape(self.batch_size * self.ntasks, 12).clone())
         adj = self._env.dense_adj(torch.float64)
         tfea = self._env.task_fea.reshape(self.batch_size * self.ntasks, 12)
         mfea = self._env.mach_fea

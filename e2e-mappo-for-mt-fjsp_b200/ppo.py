@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from torch.distributions import Categorical
 
 from . import encoder as _enc
-from .buffer import gae4
+from .buffer import RolloutBuffer, gae4
 
 
 @dataclass
@@ -54,6 +54,18 @@ class PPOConfig:
     encoder_tf32: bool = False  # every [rows,128] x [128,<=128] product of the update (graph encoders, GAT projections,
                                 # policy heads; > 95 % of its FLOPs) forward + backward on the hand-written tcgen05 TF32
                                 # kernels instead of library FP32 GEMMs under autograd
+
+
+def _obs(bt, name, idx, nxt=False):
+    """Observation field of buffered steps `idx`: through the slot table of a RolloutBuffer (each observation stored
+    once), or from a plain dict of [T, ...] tensors with separate `*_n` copies (tests replaying reference dumps)."""
+    if isinstance(bt, RolloutBuffer):
+        return bt.obs(name, idx, nxt)
+    return bt[name + "_n" if nxt else name].index_select(0, idx)
+
+
+def _steps(bt):
+    return bt["candidate"].shape[0]
 
 
 def _world():
@@ -136,9 +148,16 @@ class MAPPOUpdate:
     def advantages(self, bt):
         c = self.cfg
         with torch.no_grad():
-            multi_v = self._critic_all(bt["task_fea"], bt["adj_w"], bt["adj_src"], bt["mach_fea1"], bt["mach_fea2"])
-            mf1_n = torch.cat((bt["mach_fea1"][1:], bt["mach_fea1"][-1:]), dim=0)                     # :598-603
-            multi_v_n = self._critic_all(bt["task_fea_n"], bt["adj_w_n"], bt["adj_src_n"], mf1_n, bt["mach_fea2_n"])
+            if isinstance(bt, RolloutBuffer):
+                # one critic pass over the observation SLOTS: the value of a step's next state is the value of the slot
+                # after its own (same observation, same candidate-machine features, its own BatchNorm group)
+                sl = bt.slots
+                v_slots = self._critic_all(sl["task_fea"], sl["adj_w"], sl["adj_src"], bt.mach_fea1_of_slots(), sl["mach_fea2"])
+                multi_v, multi_v_n = v_slots.index_select(0, bt.slot), v_slots.index_select(0, bt.slot + 1)
+            else:
+                multi_v = self._critic_all(bt["task_fea"], bt["adj_w"], bt["adj_src"], bt["mach_fea1"], bt["mach_fea2"])
+                mf1_n = torch.cat((bt["mach_fea1"][1:], bt["mach_fea1"][-1:]), dim=0)                 # :598-603
+                multi_v_n = self._critic_all(bt["task_fea_n"], bt["adj_w_n"], bt["adj_src_n"], mf1_n, bt["mach_fea2_n"])
             jv, mv, jvn, mvn = bt["job_v"], bt["mch_v"], bt["job_v_n"], bt["mch_v_n"]
             # streams in the reference's order mk, pt, tt, it: local values = job[0], mch[0], mch[1], job[1] (:449-451)
             v_loc = torch.stack((jv[..., 0], mv[..., 0], mv[..., 1], jv[..., 1]), dim=-1)
@@ -158,8 +177,9 @@ class MAPPOUpdate:
         crosses from item i-1 to item i is re-evaluated for the one step a chunk overlaps its predecessor."""
         c = self.cfg
         S = idx.numel()
-        T, B, N = bt["task_fea"].shape[:3]
+        B = bt["candidate"].shape[1]
         J, M, H = self.job.J, self.job.M, self.job.H
+        N = J * M
         cs = max(1, min(S, self.max_rows // (B * N)))
         take = lambda name, i=idx: bt[name].index_select(0, i)
         mse_sum = lambda a, b: ((a - b) ** 2).sum()
@@ -173,7 +193,7 @@ class MAPPOUpdate:
         # exists at that point, so the actors are not clipped.  Reproduced by not clipping them.
         self.opt_job.zero_grad(set_to_none=True)
         self.opt_mch.zero_grad(set_to_none=True)
-        dev = bt["task_fea"].device
+        dev = bt["candidate"].device
         tot_j = torch.zeros((), device=dev)
         tot_m = torch.zeros((), device=dev)
         chunks = []
@@ -183,14 +203,14 @@ class MAPPOUpdate:
             # machine trunks first: item i's job head consumes item i-1's machine embedding (:739-768)
             p0 = max(s0 - 1, 0)
             ti = idx[p0:s1]
-            nodes_m, pooled_m = self.mch.trunk(take("mach_fea1", ti).reshape(-1, M, 6), take("mach_fea2", ti).reshape(-1, M, 8),
+            nodes_m, pooled_m = self.mch.trunk(take("mach_fea1", ti).reshape(-1, M, 6), _obs(bt, "mach_fea2", ti).reshape(-1, M, 8),
                                                groups=s1 - p0)
             pm = pooled_m.reshape(s1 - p0, B, H)
             gm = (torch.cat((inp, pm[:-1]), dim=0) if s0 == 0 else pm[:-1]).reshape(g * B, H)
             if s0 > 0:
                 nodes_m, pooled_m = nodes_m[B:], pooled_m[B:]
-            tf = take("task_fea", ci).reshape(g * B, N, -1)
-            aw, asrc = take("adj_w", ci).reshape(g * B, N, 2), take("adj_src", ci).reshape(g * B, N)
+            tf = _obs(bt, "task_fea", ci).reshape(g * B, N, -1)
+            aw, asrc = _obs(bt, "adj_w", ci).reshape(g * B, N, 2), _obs(bt, "adj_src", ci).reshape(g * B, N)
             adst = _enc.ell_invert(asrc)
             chunks.append((ci, tf, aw, asrc, adst))
             prob_j, pooled_o, job_v = self.job.evaluate(tf, aw, asrc, take("candidate", ci).reshape(g * B, J), gm,
@@ -234,7 +254,7 @@ class MAPPOUpdate:
         for ci, tf, aw, asrc, adst in chunks:
             g = ci.numel()
             v_s = self.critic.forward(tf, aw, asrc, take("mach_fea1", ci).reshape(g * B, M, 6),
-                                      take("mach_fea2", ci).reshape(g * B, M, 8), groups=g, adj_dst=adst).reshape(g, B, 4)
+                                      _obs(bt, "mach_fea2", ci).reshape(g * B, M, 8), groups=g, adj_dst=adst).reshape(g, B, 4)
             tg = adv["tgt_glob"].index_select(0, ci)
             rw = take("rw", ci)
             w_mk, w_ec, w_tt = rw[..., 0], rw[..., 1], rw[..., 2]
@@ -254,8 +274,8 @@ class MAPPOUpdate:
         permutations of range(T), for replaying the reference's SubsetRandomSampler draws in tests.
         -> (loss_mean [3], loss_std [3]) over the K epochs: job actor, machine actor, global critic (:1080-1124)."""
         c = self.cfg
-        T = bt["task_fea"].shape[0]
-        dev = bt["task_fea"].device
+        T = _steps(bt)
+        dev = bt["candidate"].device
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(c.matmul_tf32)
         try:
@@ -276,18 +296,21 @@ class MAPPOUpdate:
         order: step t's job head receives the machine embedding of step t-1, the first step of an episode the learned
         `_input` vector (Run.py:316-363).  The reference rolls out and updates with one network, so its importance ratio
         starts at exactly 1; a rollout collected by the TF32 inference twin would otherwise start a few percent off."""
-        T, B, N = bt["task_fea"].shape[:3]
+        T, B = bt["candidate"].shape[:2]
         J, M, H = self.job.J, self.job.M, self.job.H
+        N = J * M
         cs = max(1, self.max_rows // (B * N))
         ep0 = bt.get("episode_start")
+        dev = bt["candidate"].device
         with torch.no_grad():
             inp = self.job.w["_input"].detach()[None, None, :].expand(1, B, H)
             prev = None  # pooled machine embedding of the step before the chunk
             for s0 in range(0, T, cs):
                 s1 = min(T, s0 + cs)
                 g = s1 - s0
+                ii = torch.arange(s0, s1, device=dev)
                 nodes_m, pooled_m = self.mch.trunk(bt["mach_fea1"][s0:s1].reshape(-1, M, 6),
-                                                   bt["mach_fea2"][s0:s1].reshape(-1, M, 8), groups=g)
+                                                   _obs(bt, "mach_fea2", ii).reshape(-1, M, 8), groups=g)
                 pm = pooled_m.reshape(g, B, H)
                 gm = torch.cat((inp if prev is None else prev, pm[:-1]), dim=0).clone()
                 for t in range(s0, s1):
@@ -296,8 +319,8 @@ class MAPPOUpdate:
                         gm[t - s0] = inp[0]
                 prev = pm[-1:].clone()
                 prob_j, pooled_o, _ = self.job.evaluate(
-                    bt["task_fea"][s0:s1].reshape(g * B, N, -1), bt["adj_w"][s0:s1].reshape(g * B, N, 2),
-                    bt["adj_src"][s0:s1].reshape(g * B, N), bt["candidate"][s0:s1].reshape(g * B, J), gm.reshape(g * B, H),
+                    _obs(bt, "task_fea", ii).reshape(g * B, N, -1), _obs(bt, "adj_w", ii).reshape(g * B, N, 2),
+                    _obs(bt, "adj_src", ii).reshape(g * B, N), bt["candidate"][s0:s1].reshape(g * B, J), gm.reshape(g * B, H),
                     bt["job_mask"][s0:s1].reshape(g * B, J), groups=g)
                 prob_m, _ = self.mch.heads(nodes_m, pooled_m, pooled_o, bt["mach_mask"][s0:s1].reshape(g * B, M))
                 la = torch.log(prob_j.gather(1, bt["a_job"][s0:s1].reshape(-1, 1).long()).squeeze(-1))
@@ -338,54 +361,25 @@ class MAPPOUpdate:
 
 
 def collect(rollout, weights_per_episode):
-    """Runs len(weights_per_episode) episodes with `rollout` (Run.py:290-545) and returns the update batch: a dict of
-    [T, B, ...] device tensors, T = episodes * N.  `*_n` are the next-state fields (terminal observation included)."""
+    """Runs len(weights_per_episode) episodes with `rollout` (Run.py:290-545) into a `buffer.RolloutBuffer` (each
+    observation stored once; T = episodes * N buffered steps) and returns it: the batch `MAPPOUpdate.update` takes."""
     env = rollout.env
-    B, N, M, J = env.B, env.N, env.M, env.J
+    N = env.N
     job, mch = rollout.job, rollout.mch
-    T = len(weights_per_episode) * N
-    dev = env.device
-    f32 = dict(dtype=torch.float32, device=dev)
-    bt = dict(
-        task_fea=torch.empty((T, B, N, 12), **f32), adj_w=torch.empty((T, B, N, 2), **f32),
-        adj_src=torch.empty((T, B, N), dtype=torch.int16, device=dev),
-        candidate=torch.empty((T, B, J), dtype=torch.int32, device=dev), job_mask=torch.empty((T, B, J), dtype=torch.uint8, device=dev),
-        mach_fea1=torch.empty((T, B, M, 6), **f32), mach_fea2=torch.empty((T, B, M, 8), **f32),
-        mach_mask=torch.empty((T, B, M), dtype=torch.uint8, device=dev),
-        a_job=torch.empty((T, B), dtype=torch.int32, device=dev), a_mach=torch.empty((T, B), dtype=torch.int32, device=dev),
-        log_a=torch.empty((T, B), **f32), m_log_a=torch.empty((T, B), **f32),
-        job_v=torch.empty((T, B, 2), **f32), mch_v=torch.empty((T, B, 2), **f32),
-        job_v_n=torch.empty((T, B, 2), **f32), mch_v_n=torch.empty((T, B, 2), **f32),
-        r4=torch.empty((T, B, 4), **f32), done=torch.empty((T, B), **f32), rw=torch.empty((T, B, 3), **f32),
-        task_fea_n=torch.empty((T, B, N, 12), **f32), adj_w_n=torch.empty((T, B, N, 2), **f32),
-        adj_src_n=torch.empty((T, B, N), dtype=torch.int16, device=dev), mach_fea2_n=torch.empty((T, B, M, 8), **f32),
-    )
-    t = 0
+    buf = RolloutBuffer(len(weights_per_episode), env)
     for w in weights_per_episode:
         rollout.begin_episode(w)
-        wt = torch.as_tensor(w, dtype=torch.float32, device=dev)
+        wt = torch.as_tensor(w, dtype=torch.float32, device=env.device)
         for s in range(N):
-            bt["task_fea"][t].copy_(env.task_fea); bt["adj_w"][t].copy_(env.adj_w); bt["adj_src"][t].copy_(env.adj_src)
-            bt["candidate"][t].copy_(env.candidate); bt["job_mask"][t].copy_(env.job_mask); bt["mach_fea2"][t].copy_(env.mach_fea)
+            buf.store_pre(env, rollout)
             rollout.step()
-            bt["mach_fea1"][t].copy_(env.mfea1_buf); bt["mach_mask"][t].copy_(env.mach_mask)
-            bt["a_job"][t].copy_(torch.div(env.op, M, rounding_mode="floor")); bt["a_mach"][t].copy_(env.mach)
-            bt["log_a"][t].copy_(rollout.log_a); bt["m_log_a"][t].copy_(rollout.m_log_a)
-            bt["job_v"][t].copy_(rollout.job_v); bt["mch_v"][t].copy_(rollout.mch_v)
-            if s > 0:                                                                                # Run.py:448-451
-                bt["job_v_n"][t - 1].copy_(rollout.job_v); bt["mch_v_n"][t - 1].copy_(rollout.mch_v)
-            s4 = env.scaled4                                                                         # env order mk, idle, pt, tt
-            bt["r4"][t, :, 0].copy_(s4[:, 0]); bt["r4"][t, :, 1].copy_(s4[:, 2])
-            bt["r4"][t, :, 2].copy_(s4[:, 3]); bt["r4"][t, :, 3].copy_(s4[:, 1])
-            bt["done"][t].copy_(env.done); bt["rw"][t].copy_(wt)
-            bt["task_fea_n"][t].copy_(env.task_fea); bt["adj_w_n"][t].copy_(env.adj_w); bt["adj_src_n"][t].copy_(env.adj_src)
-            bt["mach_fea2_n"][t].copy_(env.mach_fea)
-            t += 1
+            buf.store_post(env, rollout, wt)
+        t = buf.t
         with torch.no_grad():                                                                        # Run.py:452-475
-            _, h_o, jv = job.evaluate(env.task_fea, env.adj_w, env.adj_src, env.candidate, rollout.h_mch, bt["job_mask"][t - 1])
-            _, _, mv = mch.forward(bt["mach_fea1"][t - 1], env.mach_fea, h_o, bt["mach_mask"][t - 1])
-        bt["job_v_n"][t - 1].copy_(jv); bt["mch_v_n"][t - 1].copy_(mv)
-    return bt
+            _, h_o, jv = job.evaluate(env.task_fea, env.adj_w, env.adj_src, env.candidate, rollout.h_mch, buf["job_mask"][t - 1])
+            _, _, mv = mch.forward(buf["mach_fea1"][t - 1], env.mach_fea, h_o, buf["mach_mask"][t - 1])
+        buf.store_bootstrap(jv, mv)
+    return buf
 
 
 def train_iteration(rollout, updater, weights_per_episode, mini_bs=None):

@@ -144,7 +144,8 @@ class DisjunctiveGraphJspEnv_singleStep:
             self.selected_action_machine.append(m)
             hs = self._host_state()
             pos = int(np.nonzero(hs["routes"][m] == a)[0][0])
-            method = "_insert_at_index_0" if len_before == 0 else "_append_at_the_end" if pos == len_before else "left_shift"
+            # SS:1546-1560: a left-shift insertion in front of the route goes through _insert_at_index_0 and carries its label
+            method = "_insert_at_index_0" if pos == 0 else "_append_at_the_end" if pos == len_before else "left_shift"
             info.update({"start_time": float(hs["st"][a]), "finish_time": float(hs["ft"][a]), "node_id": a + 1,
                          "valid_action": True, "scheduling_method": method, "left_shift": int(method == "left_shift")})
             # idle_this - idle_prev of the step that placed op a, stored into an int64 array (SS:2118-2121: the list of

@@ -56,14 +56,18 @@ def test_rollout_buffer_collects_an_episode():
     job = enc.JobActor(enc.seeded_state_dict(enc.job_actor_keys(128), 11), J, M)
     mch = enc.MachineActor(enc.seeded_state_dict(enc.machine_actor_keys(128), 12), M)
     ro = rom.Rollout(env, job, mch, greedy=False, seed=1)
-    rb = buf.RolloutBuffer(env.N, env)
-    ro.begin_episode(ins.random_weights(0, B, 4))
+    rb = buf.RolloutBuffer(1, env)
+    w = ins.random_weights(0, B, 4)
+    ro.begin_episode(w)
+    wt = torch.as_tensor(w, dtype=torch.float32, device=env.device)
     for s in range(env.N):
         rb.store_pre(env, ro)
         ro.step()
-        rb.store_post(env, ro)
-    assert rb.t == env.N and float(rb.done[-1].sum()) == B and float(rb.done[:-1].sum()) == 0
-    adv = rb.advantages(torch.zeros(B, 4, device=env.device))
+        rb.store_post(env, ro, wt)
+    rb.store_bootstrap(torch.zeros(B, 2, device=env.device), torch.zeros(B, 2, device=env.device))
+    assert rb.t == env.N and float(rb["done"][-1].sum()) == B and float(rb["done"][:-1].sum()) == 0
+    assert torch.equal(rb["job_v_n"][:-1], rb["job_v"][1:])                   # Run.py:448-451
+    adv = rb.advantages()
     assert adv.shape == (env.N, B, 4) and torch.isfinite(adv).all()
     np.testing.assert_allclose(adv.mean(dim=(0, 1)).cpu().numpy(), 0.0, atol=1e-4)
     # 122 GB per dense float64 adjacency copy at B = 65,536 in the reference layout; here, everything per env-step:

@@ -90,3 +90,34 @@ def test_parallel_env_reproduces_reference_dump(name):
             e.reset()
         paral_env.reset_data()
         assert paral_env.paral_env_DG == []
+
+
+@pytest.mark.gpu
+def test_ell_compat_mode_carries_the_same_observation_without_leaving_the_device():
+    """compat="ell": adjacency as (adj_w, adj_src) device tensors; rebuilt block-sparse matrix == the dense mode's."""
+    torch = pytest.importorskip("torch")
+    pe_mod = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.parallel_env")
+    compat = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.compat")
+    g = np.load(os.path.join(GOLD, "replay_j6m6_ls_esa.npz"))
+    J, M, E = int(g["J"]), int(g["M"]), int(g["E"])
+    N, B = J * M, g["t"].shape[0]
+    envs = {}
+    for mode in ("dense", "ell"):
+        pe = pe_mod.Parallel_env(_args(J, M, E, B), compat=mode)
+        pe.get_batch({"t": torch.tensor(g["t"]), "p": torch.tensor(g["p"]), "transT": torch.tensor(g["transT"]),
+                      "edge": torch.tensor(g["edge"])})
+        pe.init_RewardScaling_sameBATCH(shape=4)
+        envs[mode] = (pe, pe.init_DGFJSPEnv_state0(weights=g["weights"][0]))
+    for s in range(N):
+        act = g["actions"][0, s]
+        ja = list(zip(act[:, 0].tolist(), act[:, 1].tolist()))
+        adj_d, info_d, mf_d, tf_d = envs["dense"][0].DGFJSPEnv_paral_step(ja)
+        (aw, asrc), info_e, mf_e, tf_e = envs["ell"][0].DGFJSPEnv_paral_step(ja)
+        assert aw.is_cuda and asrc.is_cuda and mf_e.is_cuda and tf_e.is_cuda
+        eq(np.asarray(info_d, dtype=np.float64), info_e)
+        eq(mf_d, mf_e.cpu().numpy()); eq(tf_d, tf_e.cpu().numpy())
+        blk = compat.ell_to_block_sparse(aw, asrc).to_dense().cpu().numpy()
+        want = np.zeros((B * N, B * N))
+        for b in range(B):
+            want[b * N:(b + 1) * N, b * N:(b + 1) * N] = adj_d[b]
+        eq(blk, want)

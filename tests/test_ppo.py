@@ -240,14 +240,21 @@ def test_collect_feeds_update_consistently():
     ws = [ins.random_weights(0, B, 100 + e) for e in range(2)]
     bt = ppo.collect(ro, ws)
     T = 2 * N
-    assert bt["task_fea"].shape == (T, B, N, 12)
+    buf = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.buffer")
+    assert isinstance(bt, buf.RolloutBuffer) and bt.t == T                       # the tested buffer IS the training path's
+    every = torch.arange(T, device=dev)
+    assert bt.obs("task_fea", every).shape == (T, B, N, 12)
+    assert bt.slots["task_fea"].shape[0] == 2 * (N + 1)                         # each observation stored once
+    assert bt.bytes_per_env_step() < 2800
     done = bt["done"].reshape(2, N, B)
     assert bool((done[:, :-1] == 0).all()) and bool((done[:, -1] == 1).all())
     for e in range(2):                                         # in-episode next values are the next step's values
         sl = slice(e * N, e * N + N - 1)
         assert torch.equal(bt["job_v_n"][sl], bt["job_v"][e * N + 1:e * N + N])
         assert torch.equal(bt["mch_v_n"][sl], bt["mch_v"][e * N + 1:e * N + N])
-        assert torch.equal(bt["task_fea_n"][sl], bt["task_fea"][e * N + 1:e * N + N])
+        assert torch.equal(bt.obs("task_fea", every[sl], nxt=True), bt.obs("task_fea", every[e * N + 1:e * N + N]))
+    # the terminal observation of episode 0 is its own slot, not the first observation of episode 1
+    assert not torch.equal(bt.obs("task_fea", every[N - 1:N], nxt=True), bt.obs("task_fea", every[N:N + 1]))
     assert bool((bt["a_job"] >= 0).all()) and bool((bt["a_job"] < J).all())
 
     up = ppo.MAPPOUpdate(job, mch, crit, ppo.PPOConfig(k_epochs=1))
