@@ -20,10 +20,12 @@
 //
 // HBM layout (per handle, B environments; every record is 16-byte aligned):
 //   sd  [B][sd_stride] f64   dynamic doubles: st[N] ft[N] dur[N] psel[N] | mk_prev e_prev trans idle_prev |
-//                            macc[M][3] | w[3] | eacc[L][8] eleaf[L] | scaler R[4] mean[4] S[4] n
+//                            macc[M][3] | w[3] | eacc[L][8] eleaf[L] ipre[C] | scaler R[4] mean[4] S[4] n
 //                            (for an unscheduled op st/ft hold the current estimate, dur = 0, psel = min energy;
 //                            eacc / eleaf cache numpy's pairwise summation of the energy estimate: the 8 accumulators
-//                            and the result of each of its L leaves, so a step re-adds one accumulator chain only)
+//                            and the result of each of its L leaves, so a step re-adds one accumulator chain only;
+//                            ipre (N > 128 only, C = ceil(N/32)) caches the running idle-time sum in front of every
+//                            32nd term of the flat order: a step re-adds from the chunk it inserted into)
 //   si  [B][si_stride] i16   dynamic ints:    mach[N] ord[N] rpred[N] cnt[M] | removed_head fresh_co nsched | nxt[J]
 //                            (ord = the scheduled ops in (machine, route position) order: machine m's route is
 //                            ord[off_m, off_m + cnt[m]) with off_m = cnt[0] + ... + cnt[m-1]; rpred = route predecessor)
@@ -50,7 +52,7 @@ namespace {
 struct Layout {
     int B, J, M, N, E, left_shift;
     int sd_stride, si_stride, xs_stride;
-    int o_st, o_ft, o_dur, o_psel, o_scal, o_macc, o_w, o_eacc, o_eleaf, o_sc;  // sd offsets (doubles)
+    int o_st, o_ft, o_dur, o_psel, o_scal, o_macc, o_w, o_eacc, o_eleaf, o_ipre, nich, o_sc;  // sd offsets (doubles)
     int o_mach, o_ord, o_rpred, o_cnt, o_misc, o_nxt;          // si offsets (int16)
     int o_mind, o_minpt, o_tt;                                 // xs offsets (doubles)
     int sm_sd, sm_xs, sm_pt, sm_v, sm_leaf, sm_si, sm_off, sm_nxt, sm_tail;  // smem byte offsets per warp
@@ -178,7 +180,7 @@ __device__ double pairwise_sum(const double* a, const PwPlan& pw, double* s_leaf
         double res = r;  // n < 8 (only when N < 8): r is 0 and the loop below is the plain sum
         if (k == 0)
             for (int i = nb; i < n; i++) res += a[off + i];
-        if (act && k == 0) { s_leaf[Lx] = res; eleaf[Lx] = res; }
+        if (act && k == 0) { s_leaf[Lx] = res; if (pw.nleaves > 1) eleaf[Lx] = res; }
     }
     __syncwarp();
     if (pw.nleaves == 1) return s_leaf[0];
@@ -396,8 +398,15 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
                 s_pt[g] = term * 1.0;
             }
             __syncwarp();
+            if (L.nich) {  // large instances: running sum in front of every 32nd term (the specialised kernel restarts there)
+                for (int g = 0; g <= nsched; g++) {
+                    if ((g & 31) == 0 && (g >> 5) < L.nich && lane == 0) s_sd[L.o_ipre + (g >> 5)] = idle;
+                    if (g < nsched) idle = idle + s_pt[g];
+                }
+            } else {
 #pragma unroll 4
-            for (int g = 0; g < nsched; g++) idle = idle + s_pt[g];
+                for (int g = 0; g < nsched; g++) idle = idle + s_pt[g];
+            }
             __syncwarp();
             nt = first ? 0.0 : s_tt[s_mach[a - 1] * M + m];  // SS:872-877
             trans = s_scal[2] + nt;
@@ -678,22 +687,39 @@ __device__ __forceinline__ double pw_combine(const double* leaf) {
     }
 }
 
-template <int J_, int M_, int G_, int WARPS_>
+// COLD_: dur / psel are not staged into shared memory (a step reads them at a handful of ops: the re-added accumulator
+// chain of the energy sum and the rewritten observation rows) and the idle terms pass through a two-chunk buffer instead
+// of an N-term array -- shared memory per env drops by (2N + N) doubles, which is what bounds the resident warps.
+template <int J_, int M_, int G_, int WARPS_, bool COLD_ = false>
 struct Spec {
     static constexpr int J = J_, M = M_, G = G_, N = J_ * M_, EPW = 32 / G_, WARPS = WARPS_;
+    static constexpr bool COLD = COLD_;
+    // NOTT (one env per warp, COLD): the M x M transport table is not staged either.  A step needs column m of it (lane k
+    // keeps tt[k][m] in a register, read through shuffles) and a few single entries for rewritten observation rows.
+    static constexpr bool NOTT = COLD_ && G_ == 32;
     static_assert(J_ <= G_ && M_ <= G_, "one lane per job and per machine");
-    static_assert(3 * M_ <= J_ * M_, "the random-step mode parks three compacted machine rows in the op scratch");
     static constexpr int NLEAF = pw_nleaf(N), CHAIN = pw_maxchain(N);
     static_assert(N >= 8 && CHAIN <= G_, "one lane per term of an accumulator chain");
-    static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 9 * NLEAF + 13, 2);
+    static constexpr int NELEAF = NLEAF > 1 ? NLEAF : 0;  // a single leaf's result is the total: nothing to cache
+    static constexpr int NICH = N > 128 ? (N + 31) / 32 : 0;  // cached idle-sum prefixes (one per 32 terms of the flat order)
+    static_assert(NICH == 0 || G_ == 32, "idle-sum chunks are one warp wide");
+    static constexpr int SD = calign(4 * N + 4 + 3 * M + 3 + 8 * NLEAF + NELEAF + NICH + 13, 2);
     static constexpr int SI = calign(3 * N + M + 3 + J, 8);
     static constexpr int XS = calign(2 * N + M * M, 2);
     static constexpr int TT = calign(M * M, 2);  // only the transport table is staged from xs
     static constexpr int O_ST = 0, O_FT = N, O_DUR = 2 * N, O_PSEL = 3 * N, O_SCAL = 4 * N, O_MACC = 4 * N + 4,
-                         O_W = O_MACC + 3 * M, O_EACC = O_W + 3, O_ELEAF = O_EACC + 8 * NLEAF, O_SC = O_ELEAF + NLEAF;
+                         O_W = O_MACC + 3 * M, O_EACC = O_W + 3, O_ELEAF = O_EACC + 8 * NLEAF, O_IPRE = O_ELEAF + NELEAF,
+                         O_SC = O_IPRE + NICH;
+    // shared-memory image of sd: st ft [dur psel] | scal macc w eacc eleaf sc (COLD drops the bracket)
+    static constexpr int HOT = COLD ? 2 * N : 4 * N, TAILBLK = SD - 4 * N, SM_SD = HOT + TAILBLK;
+    static constexpr int SM_SCAL = HOT, SM_MACC = HOT + 4, SM_W = SM_MACC + 3 * M, SM_EACC = SM_W + 3,
+                         SM_ELEAF = SM_EACC + 8 * NLEAF, SM_IPRE = SM_ELEAF + NELEAF, SM_SC = SM_IPRE + NICH;
     static constexpr int O_MACH = 0, O_ORD = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
     static constexpr int O_MIND = 0, O_TT = 2 * N;
-    static constexpr int B_SD = SD * 8, B_TT = TT * 8, B_PT = calign(N, 4) * 8, B_SI = SI * 2;
+    // idle-term scratch: two G-term chunks (at least the three machine rows the policy mode parks there), or all N terms
+    static constexpr int NPT = COLD ? (2 * G > calign(3 * M, 4) ? 2 * G : calign(3 * M, 4)) : calign(N, 4);
+    static_assert(NPT >= 3 * M, "the random-step mode parks three compacted machine rows in the idle-term scratch");
+    static constexpr int B_SD = SM_SD * 8, B_TT = NOTT ? 0 : TT * 8, B_PT = NPT * 8, B_SI = SI * 2;
     static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_SI, 16);
     // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
     static constexpr int ENV_BYTES = (G_ == 8) ? (RAW + ((64 - RAW % 128) + 128) % 128) : RAW;
@@ -805,12 +831,14 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     bool sel = false;  // MODE_POLICY, lane j: job j selectable
     int cj = 0;        //              lane j: candidate op of job j
     int nsel_step = 0; //              ops scheduled so far = the step counter of the random stream
+    int eid = 0;       //              lane k: edge group of machine k (candidate-machine feature 5), independent of the action
     if constexpr ((MODE & MODE_POLICY) != 0) {
         const uint8_t* jsrc = (P.mask_mode == MTFJSP_MASK_ESA ? P.jm_esa : P.jm_fin) + (size_t)bc * J;
         if (gl < J) {
             sel = jsrc[gl] == 0;
             cj = P.cand_int[(size_t)bc * J + gl];
         }
+        if (gl < M && P.mfea1 != nullptr) eid = __ldg(P.edge_id + (size_t)bc * M + gl);
         nsel_step = g_si[S::O_MISC + 2];
     } else if (MODE & MODE_STEP) {
         if (P.act2) { const int2 am = __ldg(P.act2 + bc); a = am.x; m = am.y; }
@@ -829,13 +857,18 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"((uint32_t)(EPW * (S::SD * 8 + S::TT * 8 + S::SI * 2)))
+                     "r"((uint32_t)(EPW * (S::SM_SD * 8 + S::B_TT + S::SI * 2)))
                      : "memory");
     }
     __syncwarp();
     if (gl == 0) {
-        bulk_g2s(s_sd, g_sd, S::SD * 8, bar);
-        bulk_g2s(base + S::B_SD, g_xs + S::O_TT, S::TT * 8, bar);
+        if constexpr (S::COLD) {
+            bulk_g2s(s_sd, g_sd, S::HOT * 8, bar);
+            bulk_g2s(s_sd + S::HOT, g_sd + 4 * N, S::TAILBLK * 8, bar);
+        } else {
+            bulk_g2s(s_sd, g_sd, S::SD * 8, bar);
+        }
+        if constexpr (!S::NOTT) bulk_g2s(base + S::B_SD, g_xs + S::O_TT, S::TT * 8, bar);
         bulk_g2s(s_si, g_si, S::SI * 2, bar);
     }
     double tr = 0.0, pr = 0.0;  // MODE_POLICY, lane k < M: t[op][k], p[op][k]
@@ -875,6 +908,35 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         pa = __ldg(P.p + ((size_t)bc * N + ac) * M + mc);
         if (gl < M) mind_r = __ldg(g_xs + S::O_MIND + ja * M + gl);  // lane c: min duration of op (ja, c)
     }
+    double ttcol = 0.0;  // NOTT, lane k < M: tt[k][m]
+    if constexpr (S::NOTT && (MODE & MODE_STEP) != 0) {
+        if (gl < M) ttcol = __ldg(g_xs + S::O_TT + gl * M + mc);
+    }
+    if constexpr (S::COLD && (MODE & MODE_STEP) != 0) {
+        // the few dur / psel words this step reads from HBM, requested now (the action is known) so that they are in L1
+        // when the energy chain and the observation rows get to them: accumulator chain and tail of the op's leaf, the
+        // rows of the stepped job
+        int lf = 0, loff = 0, ln = N;
+        if constexpr (S::NLEAF > 1) {
+#pragma unroll
+            for (int q = 1; q < S::NLEAF; q++)
+                if (ac >= P.pw.leaf_off[q]) lf = q;
+            loff = P.pw.leaf_off[lf];
+            ln = P.pw.leaf_len[lf];
+        }
+        const int nb = ln - (ln & 7), x = ac - loff;
+        int v1 = -1;
+        if (x < nb && gl < (nb >> 3)) v1 = loff + (x & 7) + 8 * gl;
+        else if (gl >= 16 && gl - 16 < (ln & 7)) v1 = loff + nb + gl - 16;
+        if (v1 >= 0) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g_sd + S::O_DUR + v1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g_sd + S::O_PSEL + v1));
+        }
+        if (gl < M && (MODE & MODE_OBS)) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g_sd + S::O_PSEL + ja * M + gl));
+            if (gl == 0 && apos > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(g_sd + S::O_DUR + ac - 1));
+        }
+    }
     {
         uint32_t ok;
         do {
@@ -891,12 +953,25 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
 
     double* __restrict__ s_st = s_sd + S::O_ST;
     double* __restrict__ s_ft = s_sd + S::O_FT;
-    double* __restrict__ s_dur = s_sd + S::O_DUR;
-    double* __restrict__ s_psel = s_sd + S::O_PSEL;
-    double* __restrict__ s_scal = s_sd + S::O_SCAL;
-    double* __restrict__ s_macc = s_sd + S::O_MACC;
-    const double* __restrict__ s_w = s_sd + S::O_W;
-    double* __restrict__ s_sc = s_sd + S::O_SC;
+    double* __restrict__ s_scal = s_sd + S::SM_SCAL;
+    double* __restrict__ s_macc = s_sd + S::SM_MACC;
+    const double* __restrict__ s_w = s_sd + S::SM_W;
+    double* __restrict__ s_sc = s_sd + S::SM_SC;
+    // duration / selected power of op v: shared memory, or (COLD) straight from the state record in HBM.  The stepped
+    // op's own values are in registers (d, pa): its HBM words are written by this very launch.
+    auto TT = [&](const int i, const int j) -> double {
+        if constexpr (S::NOTT) return __ldg(g_xs + S::O_TT + i * M + j);
+        else return s_tt[i * M + j];
+    };
+    bool stepped = false;  // set once the action is known to be valid
+    auto DUR = [&](const int v) -> double {
+        if constexpr (S::COLD) return (stepped && v == ac) ? d : g_sd[S::O_DUR + v];
+        else return s_sd[S::O_DUR + v];
+    };
+    auto PSEL = [&](const int v) -> double {
+        if constexpr (S::COLD) return (stepped && v == ac) ? pa : g_sd[S::O_PSEL + v];
+        else return s_sd[S::O_PSEL + v];
+    };
     int16_t* __restrict__ s_mach = s_si + S::O_MACH;
     int16_t* __restrict__ s_ord = s_si + S::O_ORD;
     int16_t* __restrict__ s_rpred = s_si + S::O_RPRED;
@@ -904,6 +979,10 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     int16_t* __restrict__ s_misc = s_si + S::O_MISC;
     int16_t* __restrict__ s_nxt = s_si + S::O_NXT;
 
+    // NOTT: feature 2 of the candidate-machine row is a transport-table entry that comes straight from HBM; its pair is
+    // stored after the placement scan so that the load's latency is not waited for here
+    double mf_f2 = 0.0, mf_f3 = 0.0;
+    bool mf_pending = false;
     if constexpr ((MODE & MODE_POLICY) != 0) {
         // candidate-machine features of the drawn op (trainer/parallel_env.py:152-214), lane k = machine k; the means
         // run over the positive entries in machine order = numpy's sum of the compacted row (np_sum_small)
@@ -932,21 +1011,22 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 }
                 const int infeasible = !(tr >= 0);
                 const double f0 = tr > 0 ? tr : mean_t, f1 = ptl > 0 ? ptl : mean_pt;
-                const double f2 = (a % M == 0) ? 0.0 : s_tt[pm_row * M + gl];
+                const double f2 = (a % M == 0) ? 0.0 : TT(pm_row, gl);
                 const double f3 = (double)(1 - infeasible), f4 = pr > 0 ? pr : mean_p;
-                const double f5 = (double)P.edge_id[(size_t)b * M + gl];
+                const double f5 = (double)eid;
                 OutT* o = reinterpret_cast<OutT*>(P.mfea1) + ((size_t)b * M + gl) * 6;
                 if constexpr (sizeof(OutT) == 4) {
                     float2* o2 = reinterpret_cast<float2*>(o);
                     o2[0] = make_float2((float)f0, (float)f1);
-                    o2[1] = make_float2((float)f2, (float)f3);
+                    if constexpr (!S::NOTT) o2[1] = make_float2((float)f2, (float)f3);
                     o2[2] = make_float2((float)f4, (float)f5);
                 } else {
                     double2* o2 = reinterpret_cast<double2*>(o);
                     o2[0] = make_double2(f0, f1);
-                    o2[1] = make_double2(f2, f3);
+                    if constexpr (!S::NOTT) o2[1] = make_double2(f2, f3);
                     o2[2] = make_double2(f4, f5);
                 }
+                if constexpr (S::NOTT) { mf_f2 = f2; mf_f3 = f3; mf_pending = true; }
                 if (P.mmask) P.mmask[(size_t)b * M + gl] = (uint8_t)infeasible;
             }
             __syncwarp();  // s_pt is reused by the idle terms
@@ -966,11 +1046,19 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const bool first = apos == 0;
         const int aprev = first ? ac : ac - 1;
         valid = valid && nsched0 < N && (s_mach[ac] < 0) && (first || s_mach[aprev] >= 0) && !(d < 0);
+        stepped = valid;
         int mp = s_mach[aprev];
         mp = (first || mp < 0) ? 0 : mp;
-        const double arr_a = first ? 0.0 : s_ft[aprev] + s_tt[mp * M + mc];  // DGenv_func.py:46-66
+        double tt_pa, ttmm;  // tt[machine of the job predecessor][m], tt[m][m]
+        if constexpr (S::NOTT) {
+            tt_pa = __shfl_sync(FULL, ttcol, mp);
+            ttmm = __shfl_sync(FULL, ttcol, mc);
+        } else {
+            tt_pa = s_tt[mp * M + mc];
+            ttmm = s_tt[mc * M + mc];
+        }
+        const double arr_a = first ? 0.0 : s_ft[aprev] + tt_pa;  // DGenv_func.py:46-66
         const int len = s_cnt[mc];
-        const double ttmm = s_tt[mc * M + mc];
         const double lbft = arr_a + d;
         // machine k's route is ord[off_k, off_k + cnt[k]): exclusive scan of the route lengths over the group's lanes
         int offm;
@@ -988,26 +1076,41 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         unsigned best = 0xffffffffu;
         const int lastop = len > 0 ? (int)s_ord[offm + len - 1] : -1;
         if (P.L.left_shift) {
-            for (int k = gl; k < len; k += G) {
-                const int v = s_ord[offm + k];
+            // NOTT: tt[.][m] comes from a shuffle, so every lane walks ceil(len / G) chunks (one env per warp: uniform)
+            const int kend = S::NOTT ? ((len + G - 1) / G) * G : len;
+            for (int k = gl; k < kend; k += G) {
+                const bool in = k < len;
+                const int v = in ? (int)s_ord[offm + k] : 0;
                 const bool vfirst = (v % M) == 0;
                 const int vp = vfirst ? v : v - 1;
                 int mvp = s_mach[vp];
                 mvp = mvp < 0 ? 0 : mvp;
-                double nst = vfirst ? 0.0 : s_ft[vp] + s_tt[mvp * M + mc];
-                bool ok;
-                if (k == 0) {
-                    ok = (lbft <= nst);  // SS:1548
-                } else {
-                    const int rp = s_ord[offm + k - 1];
-                    const double val = s_ft[rp] + ((rp / M == v / M) ? ttmm : 0.0);
-                    nst = fmax(nst, val);
-                    ok = !(lbft > nst) && !((nst - s_ft[rp]) < d);  // SS:1597-1601
+                double ttv;
+                if constexpr (S::NOTT) ttv = __shfl_sync(FULL, ttcol, mvp);
+                else ttv = s_tt[mvp * M + mc];
+                if (in) {
+                    double nst = vfirst ? 0.0 : s_ft[vp] + ttv;
+                    bool ok;
+                    if (k == 0) {
+                        ok = (lbft <= nst);  // SS:1548
+                    } else {
+                        const int rp = s_ord[offm + k - 1];
+                        const double val = s_ft[rp] + ((rp / M == v / M) ? ttmm : 0.0);
+                        nst = fmax(nst, val);
+                        ok = !(lbft > nst) && !((nst - s_ft[rp]) < d);  // SS:1597-1601
+                    }
+                    if (ok) best = min(best, ((unsigned)k << 16) | (unsigned)v);
                 }
-                if (ok) best = min(best, ((unsigned)k << 16) | (unsigned)v);
             }
         }
         best = gmin_u(best, gmask);
+        if constexpr (S::NOTT && (MODE & MODE_POLICY) != 0) {
+            if (mf_pending) {
+                OutT* o = reinterpret_cast<OutT*>(P.mfea1) + ((size_t)b * M + gl) * 6;
+                if constexpr (sizeof(OutT) == 4) reinterpret_cast<float2*>(o)[1] = make_float2((float)mf_f2, (float)mf_f3);
+                else reinterpret_cast<double2*>(o)[1] = make_double2(mf_f2, mf_f3);
+            }
+        }
         double st = arr_a;
         int where = 0, prev = -1, next = -1, rem_head = -1, fresh = -1;
         if (len > 0) {
@@ -1030,6 +1133,14 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         }
         o_next = next;
         o_tail = (where == len || lastop < 0) ? ac : lastop;
+        if constexpr (S::COLD && (MODE & MODE_OBS) != 0) {  // rows of the follower and of last step's transients: dur / psel
+            const int pv = gl == 0 ? next : gl == 1 ? rem_prev : gl == 2 ? fresh_prev : gl == 3 ? next - 1 : gl == 4 ? rem_prev - 1
+                                                                                                  : gl == 5 ? fresh_prev - 1 : -1;
+            if (pv >= 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g_sd + S::O_DUR + pv));
+                if (gl < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(g_sd + S::O_PSEL + pv));
+            }
+        }
         // estimator chain of the job's remaining ops (SS:1964-1995): lane c ends up with op (ja, c)
         double my_st = 0.0, my_ft = 0.0;
         {
@@ -1071,7 +1182,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             s_cnt[mc] = (int16_t)(len + 1);
             s_misc[0] = (int16_t)rem_head; s_misc[1] = (int16_t)fresh; s_misc[2] = (int16_t)(nsched0 + 1);
             s_nxt[ja] = (int16_t)(apos + 1);
-            s_st[ac] = st; s_ft[ac] = st + d; s_dur[ac] = d; s_psel[ac] = pa;
+            s_st[ac] = st; s_ft[ac] = st + d;
+            if constexpr (!S::COLD) { s_sd[S::O_DUR + ac] = d; s_sd[S::O_PSEL + ac] = pa; }
             g_si[S::O_MACH + ac] = (int16_t)mc; g_si[S::O_ORD + p] = (int16_t)ac; g_si[S::O_RPRED + ac] = (int16_t)prev;
             if (next >= 0) g_si[S::O_RPRED + next] = (int16_t)ac;
             g_si[S::O_CNT + mc] = (int16_t)(len + 1);
@@ -1084,7 +1196,46 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const int nsched = nsched0 + (valid ? 1 : 0);
         done = (nsched == N);
         // ---- idle time: sequential sum in (machine, route) order, DGenv_func.py:144-170 ----
-        {
+        if constexpr (S::COLD) {
+            // terms in (machine, route) order = flat order, G at a time through a two-chunk buffer: chunk i is summed
+            // (a chain of dependent additions in the reference's order, on every lane) while chunk i + 1 is being written
+            const int nchunk = (__reduce_max_sync(FULL, nsched) + G - 1) / G;
+            // the terms in front of the chunk the op went into are the previous step's: restart from the cached running
+            // sum there (terms behind the slot moved up by one, the follower's changed) and refresh the cache on the way
+            int c0 = 0;
+            if constexpr (S::NICH > 0) {
+                c0 = valid ? (p >> 5) : 0;
+                idle = s_sd[S::SM_IPRE + c0];
+            }
+            for (int it = c0; it < nchunk; it++) {
+                if constexpr (S::NICH > 0) {
+                    if (valid && it > c0 && gl == 0) { s_sd[S::SM_IPRE + it] = idle; g_sd[S::O_IPRE + it] = idle; }
+                }
+                const int g = gl + it * G;
+                double term = 0.0;   // x + 0.0 == x exactly (gaps are never -0.0): slots past the env's term count add nothing
+                if (g < nsched) {
+                    const int v = s_ord[g], rp = s_rpred[v];
+                    term = (rp < 0) ? (s_st[v] - 0.0) : (s_st[v] - s_ft[rp]);
+                }
+                double* buf = s_pt + (it & 1) * G;
+                buf[gl] = term * 1.0;
+                __syncwarp();
+                const double2* t2 = reinterpret_cast<const double2*>(buf);
+#pragma unroll
+                for (int q = 0; q < G / 2; q += 2) {
+                    const double2 ta = t2[q], tb = t2[q + 1];
+                    idle = idle + ta.x;
+                    idle = idle + ta.y;
+                    idle = idle + tb.x;
+                    idle = idle + tb.y;
+                }
+            }
+            if constexpr (S::NICH > 0) {  // a full last chunk: the next op may open chunk `nchunk`
+                if (valid && gl == 0 && nchunk * G == nsched && nchunk < S::NICH && nchunk > c0) {
+                    s_sd[S::SM_IPRE + nchunk] = idle; g_sd[S::O_IPRE + nchunk] = idle;
+                }
+            }
+        } else {
             // terms in (machine, route) order = flat order; a route head's term is its start time
 #pragma unroll
             for (int it = 0; it < ITER; it++) {
@@ -1099,7 +1250,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             // -0.0), so the slots between this env's term count and the warp's trip count are zero-filled and the loop
             // needs no per-term predicates: two 16-byte loads and four additions per four terms
             const int nmax4 = (__reduce_max_sync(FULL, nsched) + 3) & ~3;
-            static_assert(S::B_PT >= ((N + 3) & ~3) * 8, "the padded idle sum reads whole groups of four terms");
+            static_assert(S::COLD || S::B_PT >= ((N + 3) & ~3) * 8, "the padded idle sum reads whole groups of four terms");
             for (int g = nsched + gl; g < nmax4; g += G) s_pt[g] = 0.0;
             __syncwarp();
             const double2* t2 = reinterpret_cast<const double2*>(s_pt);
@@ -1111,7 +1262,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 idle = idle + tb.y;
             }
         }
-        nt = first ? 0.0 : s_tt[mp * M + mc];  // SS:872-877
+        nt = first ? 0.0 : tt_pa;  // SS:872-877
         trans = s_scal[2] + nt;
         ec = pa * d;
         __syncwarp();
@@ -1137,8 +1288,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         // a full recomputation (which the generic kernel does, and the parity suite compares).
         double en;
         {
-            double* __restrict__ s_eacc = s_sd + S::O_EACC;
-            double* __restrict__ s_eleaf = s_sd + S::O_ELEAF;
+            double* __restrict__ s_eacc = s_sd + S::SM_EACC;
+            double* __restrict__ s_eleaf = s_sd + S::SM_ELEAF;
             int lf = 0, loff = 0, ln = N;
             if constexpr (S::NLEAF > 1) {
 #pragma unroll
@@ -1148,7 +1299,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 ln = P.pw.leaf_len[lf];
             }
             const int nb = ln - (ln & 7), x = ac - loff, k = x & 7;
-            auto ept_of = [&](const int v) { return (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_psel[v]; };
+            constexpr int TAILMAX = S::NLEAF > 1 ? 7 : (N & 7);  // a single leaf: the tail length is known at compile time
+            auto ept_of = [&](const int v) { return (s_mach[v] >= 0) ? DUR(v) * PSEL(v) : PSEL(v); };
             // accumulator chain k: lane i fetches term i, the additions run in order on every lane of the group
             const int nterm = (x < nb) ? (nb >> 3) : 0;
             const double term = (gl < nterm) ? ept_of(loff + k + 8 * gl) : 0.0;
@@ -1168,7 +1320,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             const int ntail = ln & 7;
             const double tl = (gl < ntail) ? ept_of(loff + nb + gl) : 0.0;
 #pragma unroll
-            for (int i = 0; i < 7; i++) {
+            for (int i = 0; i < TAILMAX; i++) {
                 const double t_ = __shfl_sync(FULL, tl, i, G);
                 if (i < ntail) leaf = leaf + t_;
             }
@@ -1177,7 +1329,6 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 __syncwarp();
                 en = pw_combine<N>(s_eleaf);
             } else {
-                if (valid && gl == 0) g_sd[S::O_ELEAF] = leaf;
                 en = leaf;
             }
         }
@@ -1284,21 +1435,21 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             const bool has_job = !vfirst && v != rem_head;
             const bool co = has_job && rp == v - 1;
             const bool has_m = rp >= 0 && !co;
-            const double stv = s_st[v], ftv = s_ft[v], durv = s_dur[v];
+            const double stv = s_st[v], ftv = s_ft[v], durv = DUR(v);
             if (tf) {
                 const int indeg = (vfirst ? 1 : 0) + (has_job ? 1 : 0) + (has_m ? 1 : 0);
                 OutT* row = tf + ((size_t)b * N + v) * 12;
                 if constexpr (sizeof(OutT) == 4) {
                     float4* r4 = reinterpret_cast<float4*>(row);
                     r4[0] = make_float4((float)stv, (float)ftv, (float)eptv, sch ? 1.f : 0.f);
-                    r4[1] = make_float4((float)indeg, (float)(mv + 1), (float)durv, sch ? (float)s_psel[v] : 0.f);
+                    r4[1] = make_float4((float)indeg, (float)(mv + 1), (float)durv, sch ? (float)PSEL(v) : 0.f);
                     r4[2] = make_float4((float)(v / M + 1), w0, w1, w2);
                 } else {
                     double2* r2 = reinterpret_cast<double2*>(row);
                     r2[0] = make_double2(stv, ftv);
                     r2[1] = make_double2(eptv, sch ? 1.0 : 0.0);
                     r2[2] = make_double2((double)indeg, (double)(mv + 1));
-                    r2[3] = make_double2(durv, sch ? s_psel[v] : 0.0);
+                    r2[3] = make_double2(durv, sch ? PSEL(v) : 0.0);
                     r2[4] = make_double2((double)(v / M + 1), w0);
                     r2[5] = make_double2(w1, w2);
                 }
@@ -1308,16 +1459,16 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 int src = -1;
                 if (has_job) {
                     const int u = v - 1, mu = s_mach[u];
-                    const double du = s_dur[u];
+                    const double du = DUR(u);
                     double w;
-                    if (fresh == v) w = du + s_tt[mu * M + mv] + (stv - s_ft[u]);                 // SS:1764 / 1644
-                    else if (du != 0.0) w = du + ((mu >= 0 && sch) ? s_tt[mu * M + mv] : 0.0);   // SS:1392-1422
+                    if (fresh == v) w = du + TT(mu, mv) + (stv - s_ft[u]);                 // SS:1764 / 1644
+                    else if (du != 0.0) w = du + ((mu >= 0 && sch) ? TT(mu, mv) : 0.0);   // SS:1392-1422
                     else w = 1.0;                                                                  // SS:625,642
                     wj = adj_val_t(w, mu >= 0, du);
                 }
                 if (has_m) {
-                    const double dr = s_dur[rp];
-                    const double w = dr + ((rp / M == v / M) ? s_tt[mv * M + mv] : 0.0) + (stv - s_ft[rp]);
+                    const double dr = DUR(rp);
+                    const double w = dr + ((rp / M == v / M) ? TT(mv, mv) : 0.0) + (stv - s_ft[rp]);
                     wm = adj_val_t(w, true, dr);
                     if (wm != 0.0) src = rp;
                 }
@@ -1350,7 +1501,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         for (int it = 0; it < ITER; it++) {
             if (inc && it >= 2) break;
             const int v = inc ? (it == 0 ? row0 : row1) : gl + it * G;
-            if (v >= 0 && v < N && active) emit_row(v, (s_mach[v] >= 0) ? s_dur[v] * s_psel[v] : s_psel[v]);
+            if (v >= 0 && v < N && active) emit_row(v, (s_mach[v] >= 0) ? DUR(v) * PSEL(v) : PSEL(v));
         }
         if (inc) {
             if (P.mfea && valid && gl == 0) emit_mach(mc, o_tail);
@@ -1863,7 +2014,7 @@ template <class S, int MODE, typename OutT>
 static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     const Layout& L = h->L;
     if (L.sd_stride != S::SD || L.si_stride != S::SI || L.xs_stride != S::XS || L.o_sc != S::O_SC || L.o_misc != S::O_MISC ||
-        L.o_eacc != S::O_EACC || L.o_eleaf != S::O_ELEAF || h->pw.nleaves != S::NLEAF)
+        L.o_eacc != S::O_EACC || L.o_eleaf != S::O_ELEAF || L.o_ipre != S::O_IPRE || L.nich != S::NICH || h->pw.nleaves != S::NLEAF)
         return fail(MTFJSP_E_STATE, "specialised kernel layout mismatch");
     static const size_t extra = getenv("MTFJSP_EXTRA_SMEM") ? (size_t)atoi(getenv("MTFJSP_EXTRA_SMEM")) : 0;  // occupancy experiments
     const size_t smem = (size_t)S::WARPS * S::EPW * S::ENV_BYTES + (S::BAR_IN_PAD ? 0 : 16 * ((S::WARPS * 8 + 15) / 16)) + extra;
@@ -1893,10 +2044,11 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
 // generic one-warp-per-env kernel.  X(J, M, lanes per env, warps per block): lanes >= max(J, M), 32 when N > 128; warps per block = what
 // keeps the most envs resident (shared memory per env is the limiter).
 #define MTFJSP_SPEC_SIZES(X) \
-    X(6, 6, 8, 4) X(10, 6, 16, 1) X(20, 6, 32, 1) X(10, 10, 16, 1) X(15, 10, 32, 1) X(20, 10, 32, 1) X(30, 20, 32, 1)
+    X(6, 6, 8, 4, false) X(10, 6, 16, 1, false) X(20, 6, 32, 1, false) X(10, 10, 16, 1, false) X(15, 10, 32, 1, true) \
+    X(20, 10, 32, 1, true) X(30, 20, 32, 1, true)
 
 static bool has_spec(int J, int M) {
-#define X(JJ, MM, GG, WW) if (J == JJ && M == MM) return true;
+#define X(JJ, MM, GG, WW, CC) if (J == JJ && M == MM) return true;
     MTFJSP_SPEC_SIZES(X)
 #undef X
     return false;
@@ -1906,7 +2058,7 @@ template <int MODE, typename OutT>
 static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     if (!(MODE & MODE_RESET) && !h->force_generic) {
         const int J = h->L.J, M = h->L.M;
-#define X(JJ, MM, GG, WW) if (J == JJ && M == MM) return launch_spec<Spec<JJ, MM, GG, WW>, MODE, OutT>(h, P, s);
+#define X(JJ, MM, GG, WW, CC) if (J == JJ && M == MM) return launch_spec<Spec<JJ, MM, GG, WW, CC>, MODE, OutT>(h, P, s);
         MTFJSP_SPEC_SIZES(X)
 #undef X
     }
@@ -1920,9 +2072,9 @@ static int launch_random_fused(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     if (h->force_generic || !h->fuse_policy) return 0;
     constexpr int MD = MODE_STEP | MODE_OBS | MODE_POLICY;
     const int J = h->L.J, M = h->L.M;
-#define X(JJ, MM, GG, WW)                                                        \
+#define X(JJ, MM, GG, WW, CC)                                                    \
     if (J == JJ && M == MM) {                                                    \
-        const int rc = launch_spec<Spec<JJ, MM, GG, WW>, MD, OutT>(h, P, s);     \
+        const int rc = launch_spec<Spec<JJ, MM, GG, WW, CC>, MD, OutT>(h, P, s); \
         return rc == MTFJSP_OK ? 1 : rc;                                         \
     }
     MTFJSP_SPEC_SIZES(X)
@@ -2019,7 +2171,10 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     L.o_st = 0; L.o_ft = N; L.o_dur = 2 * N; L.o_psel = 3 * N; L.o_scal = 4 * N; L.o_macc = 4 * N + 4;
     h->pw.nleaves = 0; h->pw.nprog = 0;
     build_plan_rec(0, N, h->pw);
-    L.o_w = L.o_macc + 3 * M; L.o_eacc = L.o_w + 3; L.o_eleaf = L.o_eacc + 8 * h->pw.nleaves; L.o_sc = L.o_eleaf + h->pw.nleaves;
+    L.o_w = L.o_macc + 3 * M; L.o_eacc = L.o_w + 3; L.o_eleaf = L.o_eacc + 8 * h->pw.nleaves;
+    L.o_ipre = L.o_eleaf + (h->pw.nleaves > 1 ? h->pw.nleaves : 0);  // a single leaf's result is the total: not cached
+    L.nich = N > 128 ? (N + 31) / 32 : 0;
+    L.o_sc = L.o_ipre + L.nich;
     L.sd_stride = align_up(L.o_sc + 13, 2);
     L.o_mach = 0; L.o_ord = N; L.o_rpred = 2 * N; L.o_cnt = 3 * N; L.o_misc = 3 * N + M;
     L.o_nxt = L.o_misc + 3;

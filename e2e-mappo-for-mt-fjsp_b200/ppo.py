@@ -31,6 +31,7 @@ from torch.distributions import Categorical
 
 from . import encoder as _enc
 from .buffer import RolloutBuffer, gae4
+from .rollout import nvtx_range
 
 
 @dataclass
@@ -330,7 +331,8 @@ class MAPPOUpdate:
 
     def _update(self, bt, mini_bs, orders, generator, T, dev):
         c = self.cfg
-        adv = self.advantages(bt)
+        with nvtx_range("mtfjsp/ppo_advantages"):
+            adv = self.advantages(bt)
         per_epoch = []
         for k in range(c.k_epochs):
             if orders is not None:
@@ -341,7 +343,8 @@ class MAPPOUpdate:
                 perm = torch.randperm(T, generator=generator, device=generator.device).to(dev)
             lj, lm, lc = [], [], []
             for s0 in range(0, T, mini_bs):                                                          # BatchSampler(..., drop_last=False)
-                a, b, cc = self._minibatch(bt, adv, perm[s0:s0 + mini_bs])
+                with nvtx_range("mtfjsp/ppo_minibatch"):
+                    a, b, cc = self._minibatch(bt, adv, perm[s0:s0 + mini_bs])
                 lj.append(a); lm.append(b); lc.append(cc)
             per_epoch.append(torch.stack((torch.stack(lj).mean(), torch.stack(lm).mean(), torch.stack(lc).mean())))
         if c.use_lr_decay:

@@ -7,9 +7,21 @@ episode (the reference crosses the host/device boundary four times per step).  T
 CUDA graph and replayed (`Rollout(..., use_cuda_graph=True)`)."""
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 from .env import BatchedMTFJSPEnv, MASK_ESA
+
+# MTFJSP_NVTX=1: NVTX ranges around the phases of a rollout step (job encoder + head, candidate-machine features, machine
+# actor, env step + observation) for nsys / ncu --nvtx timelines (SURVEY.md 5.1).  Off by default: a range push / pop
+# pair costs about a microsecond of host time per phase.
+_NVTX = os.environ.get("MTFJSP_NVTX", "0") == "1"
+
+
+def nvtx_range(name):
+    return torch.cuda.nvtx.range(name) if _NVTX else contextlib.nullcontext()
 
 
 class Rollout:
@@ -47,11 +59,14 @@ class Rollout:
         env = self.env
         with torch.no_grad():
             h_in = None if first else self.h_mch
-            ti, ai, la, prob, h_o, jv = self.job.forward(env.task_fea, env.adj_w, env.adj_src, env.candidate, h_in,
-                                                         env.job_mask, greedy=self.greedy, generator=self._g())
-            env.op.copy_(ti.to(torch.int32))
-            m1, mmask = env.mfea1(env.op)
-            mp, h_m, mv = self.mch.forward(m1, env.mach_fea, h_o, mmask)
+            with nvtx_range("mtfjsp/job_actor"):
+                ti, ai, la, prob, h_o, jv = self.job.forward(env.task_fea, env.adj_w, env.adj_src, env.candidate, h_in,
+                                                             env.job_mask, greedy=self.greedy, generator=self._g())
+                env.op.copy_(ti.to(torch.int32))
+            with nvtx_range("mtfjsp/mfea1"):
+                m1, mmask = env.mfea1(env.op)
+            with nvtx_range("mtfjsp/machine_actor"):
+                mp, h_m, mv = self.mch.forward(m1, env.mach_fea, h_o, mmask)
             if self.greedy:
                 ma = mp.argmax(dim=-1)
             else:
@@ -62,7 +77,8 @@ class Rollout:
             self.m_log_a.copy_(torch.log(mp.gather(1, ma.unsqueeze(-1)).squeeze(-1)))
             self.job_v.copy_(jv)
             self.mch_v.copy_(mv)
-            env.step_obs(env.op, env.mach, MASK_ESA)
+            with nvtx_range("mtfjsp/env_step_obs"):
+                env.step_obs(env.op, env.mach, MASK_ESA)
 
     def step(self):
         """Advances every env by one operation.  Results: env.reward5 / scaled4 / done / invalid and the new obs."""

@@ -19,7 +19,7 @@ HDR = {}
 def sass_lines(so, pattern):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-    cub = [f for f in os.listdir(tmp) if "mtfjsp_env" in f and f.endswith(".cubin")][0]
+    cub = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))  # the env kernels
     txt = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
     out, on, line = [], False, 0
     for ln in txt:
@@ -31,7 +31,7 @@ def sass_lines(so, pattern):
         m = re.search(r'//## File "(.*)", line (\d+)', ln)
         if m:
             # lines of other files (CUDA headers: shuffles, math) are folded into negative pseudo-lines per header
-            line = int(m.group(2)) if m.group(1).endswith("mtfjsp_env.cu") else -(abs(hash(os.path.basename(m.group(1)))) % 1000 + 1)
+            line = int(m.group(2)) if m.group(1).endswith(".cu") else -(abs(hash(os.path.basename(m.group(1)))) % 1000 + 1)
             if line < 0:
                 HDR[line] = os.path.basename(m.group(1))
             continue
@@ -82,17 +82,33 @@ def main():
               src[line - 1].strip()[:90] if 0 < line <= len(src) else HDR.get(line, "")))
     # phases: contiguous line ranges
     print("\ncumulative by line range")
-    ranges = [(762, 826, "prologue: action, staging issue"), (826, 875, "policy draw + dependent loads + barrier wait"),
-              (876, 940, "mfea1 (policy)"), (941, 1009, "placement scan"), (1010, 1059, "chain + apply"),
-              (1060, 1101, "idle sum"), (1102, 1123, "ept + per-job"), (1124, 1207, "energy sum + reward + scaler + writeback"),
-              (1208, 1236, "job mask"), (1237, 1328, "observation rows")]
+    # phases of env_kernel_s, located by marker strings in the source (line numbers move with the code)
+    marks = [("prologue: action, staging issue", "__global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s"),
+             ("policy draw, dependent loads, barrier wait", "    if constexpr ((MODE & MODE_POLICY) != 0) {\n        // uniform random selectable job"),
+             ("mfea1 (policy)", "        // candidate-machine features of the drawn op (trainer/parallel_env.py:152-214), lane k = machine k"),
+             ("placement scan", "    if (MODE & MODE_STEP) {\n        const int nsched0 = s_misc[2];"),
+             ("estimator chain + apply", "        // estimator chain of the job's remaining ops (SS:1964-1995): lane c ends up with op (ja, c)"),
+             ("idle sum", "        // ---- idle time: sequential sum in (machine, route) order, DGenv_func.py:144-170 ----"),
+             ("per-job state", "    // per job (lane j): ops scheduled so far, ESA key"),
+             ("energy sum (incremental)", "        // ---- energy estimate (SS:896): np.sum over all ops"),
+             ("reward + scaler + write-back", "        // ---- reward (SS:1066-1132) and reward scaling"),
+             ("job mask", "    // ---- job mask + candidates (ppo_algorithm.py:202-317) ----"),
+             ("observation rows", "        // feature row (SS:2246-2277) and compact ELL adjacency row (SS:2019-2073) of op v; eptv = its estimated energy"),
+             ("(end)", "// ---- static tables: min feasible duration / energy per op")]
+    text = "\n".join(src)
+    starts = []
+    for nm, mk in marks:
+        k = text.rfind(mk)
+        starts.append((nm, text.count("\n", 0, k) + 1 if k >= 0 else None))
+    ranges = [(starts[i][1], starts[i + 1][1] - 1, starts[i][0]) for i in range(len(starts) - 1) if starts[i][1] and starts[i + 1][1]]
+    kstart = starts[0][1] or 0
     for a, b, nm in ranges:
         s = sum(d["samples"] for l, d in by.items() if a <= l <= b)
         x = sum(d["inst"] for l, d in by.items() if a <= l <= b)
         print("  %4d-%4d %-45s samples %5.1f%%  inst %5.1f%%" % (a, b, nm, 100.0 * s / max(tot_s, 1), 100.0 * x / max(tot_x, 1)))
-    s = sum(d["samples"] for l, d in by.items() if 0 <= l < 762)
-    x = sum(d["inst"] for l, d in by.items() if 0 <= l < 762)
-    print("  helpers (<762: reductions, adj_val_t, rand, INFO6_PUT)       samples %5.1f%%  inst %5.1f%%" % (100.0 * s / max(tot_s, 1), 100.0 * x / max(tot_x, 1)))
+    s = sum(d["samples"] for l, d in by.items() if 0 <= l < kstart)
+    x = sum(d["inst"] for l, d in by.items() if 0 <= l < kstart)
+    print("  helpers (above the kernel: reductions, adj_val_t, rand)       samples %5.1f%%  inst %5.1f%%" % (100.0 * s / max(tot_s, 1), 100.0 * x / max(tot_x, 1)))
     s = sum(d["samples"] for l, d in by.items() if l < 0)
     x = sum(d["inst"] for l, d in by.items() if l < 0)
     print("  CUDA headers (shuffles, ballots, math intrinsics)            samples %5.1f%%  inst %5.1f%%" % (100.0 * s / max(tot_s, 1), 100.0 * x / max(tot_x, 1)))
