@@ -68,6 +68,7 @@ SIGNATURES = {
     "mtfjsp_mfea1": ([_VP, _VP, _VP, _VP, _I, _VP], _I),
     "mtfjsp_dense_adj": ([_VP, _VP, _I, _VP], _I),
     "mtfjsp_raw_adj": ([_VP, _VP, _VP], _I),
+    "mtfjsp_generate_instances": ([_I, _I, _I, _I, _U64, _U64, _VP, _VP, _VP, _VP, _I, _VP], _I),
     "mtfjsp_costs": ([_VP, _VP, _VP, _VP], _I),
     "mtfjsp_export_state": ([_VP] + [_VP] * 4 + [_VP], _I),
     "mtfjsp_export_scaler": ([_VP] + [_VP] * 4 + [_VP], _I),

@@ -1556,6 +1556,68 @@ __global__ void load_kernel(Layout L, const double* __restrict__ t, const double
     }
 }
 
+// Synthetic instances on the device (reference distributions: instance/generate_allsize_mofjsp_dataset.py:161-273 with
+// instance/config_ins.json's ranges): per op a mean time U(1,99) and mean power U(1,20), per (op, machine) multiplicative
+// noise U(0.8,1.2); k ~ randint(0, M) machines of the op chosen without replacement (partial Fisher-Yates) are made
+// infeasible by negating t and p; tt symmetric, zero diagonal, U(1,10) inside an edge group and U(10 d, 20 d) across
+// groups at distance d; machines split contiguously into E groups (last group takes the remainder, padded with -1).
+// Counter-based: every draw is a function of (seed, global env index, op / machine pair, draw number), so any slice of a
+// batch can be generated on any rank.  One thread per (env, op) for t / p; the first M * M threads of an env also fill tt
+// and the first E * W the edge table.
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t env, uint64_t item, uint64_t k) {
+    const uint64_t x = splitmix64(seed ^ splitmix64(env * 0x100000001B3ULL + item * 0x9E3779B97F4A7C15ULL + k * 0xD1B54A32D192ED03ULL));
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);  // 53 bits -> [0, 1)
+}
+
+__global__ void instance_gen_kernel(int B, int J, int M, int E, int W, uint64_t seed, uint64_t env_offset, double* t, double* p,
+                                    double* tt, int32_t* edge) {
+    const int N = J * M;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * N) return;
+    const size_t b = gid / N;
+    const int i = (int)(gid % N);
+    const uint64_t env = env_offset + b;
+    {
+        const double avg_t = 1.0 + 98.0 * u01(seed, env, i, 0), avg_p = 1.0 + 19.0 * u01(seed, env, i, 1);
+        int k = (int)(u01(seed, env, i, 2) * M);  // 0 .. M-1 infeasible machines: at least one stays feasible
+        if (k > M - 1) k = M - 1;
+        unsigned char perm[64];
+        for (int m = 0; m < M; m++) perm[m] = (unsigned char)m;
+        uint64_t neg = 0;
+        for (int q = 0; q < k; q++) {  // choose k of M without replacement
+            int r = q + (int)(u01(seed, env, i, 3 + q) * (M - q));
+            if (r > M - 1) r = M - 1;
+            const unsigned char tmp = perm[q]; perm[q] = perm[r]; perm[r] = tmp;
+            neg |= 1ull << perm[q];
+        }
+        for (int m = 0; m < M; m++) {
+            double tv = avg_t * (0.8 + 0.4 * u01(seed, env, i, 100 + m));
+            double pv = avg_p * (0.8 + 0.4 * u01(seed, env, i, 200 + m));
+            if ((neg >> m) & 1) { tv = -tv; pv = -pv; }
+            t[gid * M + m] = tv;
+            p[gid * M + m] = pv;
+        }
+    }
+    const int avg = M / E;
+    auto group_of = [&](int m) { const int g = m / (avg > 0 ? avg : 1); return g < E - 1 ? g : E - 1; };
+    if (i < M * M) {
+        const int r = i / M, c = i % M;
+        double v = 0.0;
+        if (r != c) {
+            const int lo = r < c ? r : c, hi = r < c ? c : r;  // one draw per unordered pair: symmetric
+            const int dgrp = abs(group_of(lo) - group_of(hi));
+            const double u = u01(seed, env, (uint64_t)N + (uint64_t)lo * M + hi, 0);
+            v = dgrp == 0 ? 1.0 + 9.0 * u : 10.0 * dgrp + 10.0 * dgrp * u;
+        }
+        tt[(b * M + r) * M + c] = v;
+    }
+    if (i < E * W) {
+        const int g = i / W, k2 = i % W;
+        const int start = g * avg, size = g < E - 1 ? avg : M - avg * (E - 1);
+        edge[(b * E + g) * W + k2] = k2 < size ? start + k2 : -1;
+    }
+}
+
 __global__ void scaler_kernel(Layout L, double* sd, int full) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int per = full ? 13 : 4;
@@ -1952,6 +2014,12 @@ struct mtfjsp_env {
     int host_chunks, fuse_policy;  // tuning knobs read from the environment at create time (tests compare the settings)
     int alternate_order, flip;     // MTFJSP_ALTERNATE_ORDER (default on): successive step launches walk the batch in
                                    // opposite directions for L2 reuse
+    // MTFJSP_L2_PERSIST (default on): the small records every launch starts from -- job masks, candidates, the si record
+    // (route order, counters) -- live in one slab that step launches mark as an L2-persisting access window, so the loads
+    // at the head of a warp's dependent chain hit L2 instead of DRAM although the batch's working set is larger than L2
+    unsigned char* slab;
+    size_t slab_bytes, window_bytes;
+    int l2_persist;
     int64_t launches;
     struct HostPipe* pipe;  // host-step pipeline (streams, events, instantiated graphs), created on first use
 };
@@ -2026,13 +2094,29 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
     }
     const int per_block = S::WARPS * S::EPW;
     const int blocks = (P.b1 - P.b0 + per_block - 1) / per_block;
+    Params Q = P;
     if (h->alternate_order && (MODE & MODE_STEP)) {  // eager step launches alternate direction (see Params::rev)
-        Params Q = P;
         Q.rev = h->flip;
         h->flip ^= 1;
-        env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(Q);
+    }
+    if (h->window_bytes && (MODE & MODE_STEP)) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(S::WARPS * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[0].val.accessPolicyWindow.base_ptr = h->slab;
+        at[0].val.accessPolicyWindow.num_bytes = h->window_bytes;
+        at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, env_kernel_s<S, MODE, OutT>, Q), "env_kernel_s launch");
     } else {
-        env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(P);
+        env_kernel_s<S, MODE, OutT><<<blocks, S::WARPS * 32, smem, s>>>(Q);
     }
     h->launches++;
     CK(cudaGetLastError(), "env_kernel_s launch");
@@ -2214,14 +2298,35 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
         cudaMemset((ptr), 0, (bytes));                                         \
     } while (0)
     ALLOC(h->sd, Bs * L.sd_stride * 8);
-    ALLOC(h->si, Bs * L.si_stride * 2);
-    ALLOC(h->xs, Bs * L.xs_stride * 8);
+    {
+        auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+        const size_t b_si = up(Bs * L.si_stride * 2), b_jm = up(Bs * J), b_cd = up(Bs * J * 4), b_xs = up(Bs * L.xs_stride * 8);
+        h->slab_bytes = b_si + 2 * b_jm + b_cd + b_xs;
+        ALLOC(h->slab, h->slab_bytes);
+        h->jm_fin = h->slab;
+        h->jm_esa = h->slab + b_jm;
+        h->cand = reinterpret_cast<int32_t*>(h->slab + 2 * b_jm);
+        h->si = reinterpret_cast<int16_t*>(h->slab + 2 * b_jm + b_cd);
+        h->xs = reinterpret_cast<double*>(h->slab + 2 * b_jm + b_cd + b_si);  // static tables (transport table, min durations)
+        h->window_bytes = 0;
+        h->l2_persist = getenv("MTFJSP_L2_PERSIST") ? atoi(getenv("MTFJSP_L2_PERSIST")) : 1;  // 2: the static tables as well
+        if (h->l2_persist) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                size_t want = h->l2_persist >= 2 ? h->slab_bytes : h->slab_bytes - b_xs;
+                if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
+                size_t carve = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+                size_t cur = 0;
+                cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+                if (cur < carve) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+                h->window_bytes = want;
+            }
+            cudaGetLastError();
+        }
+    }
     ALLOC(h->t, Bs * N * M * 8);
     ALLOC(h->p, Bs * N * M * 8);
     ALLOC(h->edge_id, Bs * M);
-    ALLOC(h->jm_fin, Bs * J);
-    ALLOC(h->jm_esa, Bs * J);
-    ALLOC(h->cand, Bs * J * 4);
     ALLOC(h->a_op, Bs * 4);
     ALLOC(h->a_mach, Bs * 4);
     ALLOC(h->r5, Bs * 5 * 8);
@@ -2244,7 +2349,7 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
 int mtfjsp_destroy(mtfjsp_env* h) {
     if (!h) return MTFJSP_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->sd, h->si, h->xs, h->t, h->p, h->edge_id, h->jm_fin, h->jm_esa, h->cand, h->a_op, h->a_mach,
+    void* ptrs[] = {h->sd, h->slab, h->t, h->p, h->edge_id, h->a_op, h->a_mach,
                     h->r5, h->s4, h->info6, h->dn, h->inv, h->tmp_adj_w, h->tmp_adj_src, h->act2, h->rec, h->sd0, h->si0};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -2430,6 +2535,20 @@ int mtfjsp_raw_adj(mtfjsp_env* h, int32_t* adj, void* stream) {
     raw_adj_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, h->sd, h->si, h->xs, adj);
     h->launches++;
     CK(cudaGetLastError(), "raw_adj_kernel");
+    return MTFJSP_OK;
+}
+
+int mtfjsp_generate_instances(int B, int J, int M, int E, uint64_t seed, uint64_t env_offset, double* t, double* p, double* tt,
+                              int32_t* edge, int W, void* stream) {
+    if (B < 1 || J < 1 || M < 2 || M > 64 || E < 1 || E > M || !t || !p || !tt || !edge)
+        return fail(MTFJSP_E_ARG, "mtfjsp_generate_instances: bad argument");
+    const int avg = M / E, wmin = M - avg * (E - 1);
+    if (W < wmin || W < avg || (long long)E * W > (long long)J * M || (long long)M * M > (long long)J * M * 64)
+        return fail(MTFJSP_E_ARG, "mtfjsp_generate_instances: edge table width too small (need W >= largest group) or sizes out of range");
+    if ((long long)M * M > (long long)J * M) return fail(MTFJSP_E_ARG, "mtfjsp_generate_instances: needs J >= M");
+    const size_t n = (size_t)B * J * M;
+    instance_gen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, J, M, E, W, seed, env_offset, t, p, tt, edge);
+    CK(cudaGetLastError(), "instance_gen_kernel");
     return MTFJSP_OK;
 }
 

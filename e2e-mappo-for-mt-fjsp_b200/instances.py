@@ -176,3 +176,29 @@ def random_weights(first_env: int, count: int, seed: int, episode: int = 0) -> n
         pos += s1 - s0
         b0 += _BLOCK
     return out
+
+
+def device_instances(first_env: int, count: int, n_job: int, n_machine: int, n_edge: int, seed: int, device=None) -> dict:
+    """Envs [first_env, first_env + count) of the device-generated synthetic batch `seed`: the reference's distributions
+    drawn by `mtfjsp_generate_instances` (csrc/mtfjsp_env.cu `instance_gen_kernel`) straight into device tensors -- a
+    65,536-env J6M6 batch is 226 MB of tables that never cross PCIe.  Counter-based like `synthetic_instances` (a slice
+    equals the same rows of the whole batch) but a different stream: the two generators are not interchangeable."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    N, M, E = n_job * n_machine, n_machine, n_edge
+    W = edge_groups(M, E).shape[1]
+    t = torch.empty((count, N, M), dtype=torch.float64, device=dev)
+    p = torch.empty_like(t)
+    tt = torch.empty((count, M, M), dtype=torch.float64, device=dev)
+    edge = torch.empty((count, E, W), dtype=torch.int32, device=dev)
+    ptr = lambda x: C.c_void_p(x.data_ptr())
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mtfjsp_generate_instances(count, n_job, M, E, seed & 0xFFFFFFFFFFFFFFFF, first_env, ptr(t), ptr(p),
+                                                        ptr(tt), ptr(edge), W, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "mtfjsp_generate_instances")
+    return dict(t=t, p=p, transT=tt, edge=edge)

@@ -104,6 +104,14 @@ int mtfjsp_mfea1(mtfjsp_env* h, const int32_t* op, void* mfea1, uint8_t* mach_ma
 /* compatibility view: dense adjacency adj[b,dst,src], diagonal 1 (SS:2019-2073), element type dtype. */
 int mtfjsp_dense_adj(mtfjsp_env* h, void* adj, int dtype, void* stream);
 
+/* replaces: Instance_Dataset's sample generation (instance/generate_allsize_mofjsp_dataset.py:161-273) for synthetic
+ * batches -- the same distributions drawn on the device from a counter-based generator keyed by (seed, env_offset + b),
+ * so a rank generates its own slice without touching the host.  t, p [B,N,M] f64; tt [B,M,M] f64; edge [B,E,W] i32
+ * (machine ids of each edge group, padded with -1; W >= largest group).  Needs J >= M.  No handle: the arrays are the
+ * caller's and go to mtfjsp_load. */
+int mtfjsp_generate_instances(int B, int J, int M, int E, uint64_t seed, uint64_t env_offset, double* t, double* p, double* tt,
+                              int32_t* edge, int W, void* stream);
+
 /* compatibility view of the single-env class: raw arc weights between real ops, adj[b,u,v] = trunc(weight of u -> v),
  * int32 [B,N,N] -- nx.to_numpy_array(G)[1:-1,1:-1].astype(int) of SS:2019, the matrix the reference's gym `state`
  * vector (first element of the reset 9-tuple / step 14-tuple, SS:2075-2130, 2515) is built from. */

@@ -68,3 +68,41 @@ def test_synthetic_slices_agree_with_whole_batch():
     assert ((t >= 0).sum(-1) >= 1).all() and ((t < 0) == (p < 0)).all()   # at least one feasible machine per op
     tt = whole["transT"]
     assert (tt == np.transpose(tt, (0, 2, 1))).all() and (np.diagonal(tt, axis1=1, axis2=2) == 0).all()
+
+
+@pytest.mark.gpu
+def test_device_generator_draws_the_reference_distributions():
+    """mtfjsp_generate_instances: ranges and structure of generate_allsize_mofjsp_dataset.py:161-273,
+    slices equal the whole batch, and the env steps on what it produced."""
+    torch = pytest.importorskip("torch")
+    J, M, E, B = 10, 10, 3, 4096
+    d = ins.device_instances(0, B, J, M, E, seed=11)
+    t, p, tt, edge = (d[k].cpu().numpy() for k in ("t", "p", "transT", "edge"))
+    assert ((t < 0) == (p < 0)).all() and ((t >= 0).sum(-1) >= 1).all()
+    at, ap = np.abs(t), np.abs(p)
+    assert at.min() >= 0.8 * 1 and at.max() <= 1.2 * 99 and ap.min() >= 0.8 and ap.max() <= 1.2 * 20
+    assert 49.0 < at.mean() < 51.0 and 10.2 < ap.mean() < 10.8                    # E[U(1,99)] = 50, E[U(1,20)] = 10.5
+    frac_neg = (t < 0).mean()
+    assert abs(frac_neg - (M - 1) / (2 * M)) < 0.01                                # k ~ randint(0, M): mean (M-1)/2 of M
+    k = (t < 0).sum(-1)
+    assert k.min() == 0 and k.max() == M - 1 and len(np.unique(k)) == M
+    assert (tt == np.transpose(tt, (0, 2, 1))).all() and (np.diagonal(tt, axis1=1, axis2=2) == 0).all()
+    np.testing.assert_array_equal(edge[0], ins.edge_groups(M, E))
+    gid = ins.edge_of_machine(edge[0], M)
+    dist = np.abs(gid[:, None] - gid[None, :])
+    off = ~np.eye(M, dtype=bool)
+    lo = np.where(dist == 0, 1.0, 10.0 * dist); hi = np.where(dist == 0, 10.0, 20.0 * dist)
+    assert (tt[:, off] >= lo[off]).all() and (tt[:, off] <= hi[off]).all()
+    part = ins.device_instances(1000, 300, J, M, E, seed=11)
+    for kname in ("t", "p", "transT", "edge"):
+        assert torch.equal(part[kname], d[kname][1000:1300])
+    other = ins.device_instances(0, 64, J, M, E, seed=12)
+    assert not torch.equal(other["t"], d["t"][:64])
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    env.reset(ins.random_weights(0, B, 11))
+    for _ in range(J * M):
+        env.random_step(seed=3)
+    assert bool(env.done.all()) and not bool(env.invalid.any())
