@@ -80,3 +80,39 @@ def test_allreduce_mean_grads_is_a_no_op_without_a_process_group():
     w = torch.ones(3, requires_grad=True)
     (w * 2).sum().backward()
     assert ppo.allreduce_mean_grads([w]) == 0 and torch.equal(w.grad, torch.full((3,), 2.0))
+
+
+def _weighted_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ppo = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.ppo")
+    B = (3, 1)[rank]                                   # 4 envs over 2 ranks, unequal shards (sharding.shard_range)
+    up = object.__new__(ppo.MAPPOUpdate)
+    up._shard_weight = {}
+    wgt = up._grad_weight(B, torch.device("cpu"))      # B_local * world / B_total
+    w = torch.ones(5, requires_grad=True)
+    (w * float(rank + 1)).sum().backward()             # this rank's mean-over-its-envs gradient: (rank + 1) everywhere
+    ppo.allreduce_mean_grads([w], weight=wgt)
+    q.put((rank, wgt, w.grad.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_unequal_shards_weight_the_gradient_by_env_count():
+    """each rank's loss is a mean over ITS envs; with 3 + 1 envs the global mean gradient is
+    (3 * g0 + 1 * g1) / 4, not (g0 + g1) / 2."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_weighted_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert res[0][1] == 1.5 and res[1][1] == 0.5
+    for _, _, g in res:
+        np.testing.assert_allclose(g, np.full(5, (3 * 1.0 + 1 * 2.0) / 4), rtol=0, atol=1e-7)
