@@ -399,6 +399,33 @@ def measure_env(wl, B, K, W, repeats, rank, world, dev, barrier, sh, envm, torch
                              "records (f64 info6, i16 candidates, u8 job mask) out; observation tensors stay on the device)",
                       "steps": Ke, "repeats": repeats, "us_per_step": e2e_s * 1e6 / Ke}
         assert float(rec_view["info6"][:, 1].sum()) in (0.0, float(B))
+        # the same call returning ONLY the reference's step info (`oenv_info` rows, 48 B per env): candidates and job mask
+        # stay on the device, where the actors that consume them run (mtfjsp_step_host with NULL mask / candidate buffers)
+        h_op = [rec_op[s].cpu().pin_memory() for s in range(N)]
+        h_mc = [rec_mc[s].cpu().pin_memory() for s in range(N)]
+        h_info = torch.zeros((B, 6), dtype=torch.float64).pin_memory()
+
+        def info_steps(n):
+            for _ in range(n):
+                if es["s"] == N:
+                    env.reset(w); env.scaler_reset(); es["s"] = 0
+                env.step_host(h_op[es["s"]], h_mc[es["s"]], h_info, None, None)
+                es["s"] += 1
+
+        es["s"] = N
+        info_steps(N + 3)
+        it = []
+        for _ in range(max(3, repeats // 3)):
+            barrier()
+            t0 = time.perf_counter()
+            info_steps(Ke)
+            torch.cuda.synchronize()
+            it.append(sh.max_over_ranks(time.perf_counter() - t0, dev))
+        out["e2e"]["step_info_only"] = {"value": B * world * Ke / median(it), "unit": UNIT, "h2d_bytes_per_step": B * 8,
+                                        "d2h_bytes_per_step": B * 48, "us_per_step": median(it) * 1e6 / Ke,
+                                        "api": "mtfjsp_step_host (op / machine arrays in, the [B,6] float64 step info of "
+                                               "trainer/parallel_env.py:260 out; candidates, job mask and observation stay "
+                                               "on the device)"}
     return out
 
 

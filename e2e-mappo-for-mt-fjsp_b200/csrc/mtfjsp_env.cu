@@ -2024,14 +2024,16 @@ struct mtfjsp_env {
     struct HostPipe* pipe;  // host-step pipeline (streams, events, instantiated graphs), created on first use
 };
 
-// Host-step pipeline: the batch is cut into chunks; chunk c's (H2D actions -> fused kernel -> D2H step info) runs
-// on its own stream, so that chunk c's copy-out overlaps chunk c+1's kernel.  The whole fan-out is captured once per
-// set of buffer addresses into a CUDA graph and replayed with a single launch call per step (the eager form of the
-// same pipeline lost to its 9 API calls per chunk, profiles/README.md).
+// Host-step pipeline: the batch is cut into chunks; the copies in, the kernels and the copies out run on three
+// streams -- copy-in c -> kernel c -> copy-out c, kernels in chunk order on ONE stream -- so that chunk c's copy-out
+// overlaps chunk c+1's kernel.  (Round 1 gave every chunk its own stream: the block scheduler then interleaves the blocks
+// of all chunk kernels, every chunk finishes near the end and no copy-out can start early: 161 us per 65,536-env step
+// against 174 us unchunked.  `MTFJSP_HOST_PIPE=0` restores that form.)  The whole fan-out is captured once per set of
+// buffer addresses into a CUDA graph and replayed with a single launch call per step.
 struct HostPipe {
     static constexpr int MAXC = 8;
     cudaStream_t ms, cs[MAXC];
-    cudaEvent_t fork, join[MAXC];
+    cudaEvent_t fork, join[MAXC], hev[MAXC], kev[MAXC];
     struct Entry {
         const void* key[11];
         int mask_mode, dtype, chunks, kernels, inc;
@@ -2130,6 +2132,18 @@ static int launch_spec(mtfjsp_env* h, const Params& P, cudaStream_t s) {
 #define MTFJSP_SPEC_SIZES(X) \
     X(6, 6, 8, 4, false) X(10, 6, 16, 1, false) X(20, 6, 32, 1, false) X(10, 10, 16, 1, false) X(15, 10, 32, 1, true) \
     X(20, 10, 32, 1, true) X(30, 20, 32, 1, true)
+
+// envs that ONE wave of resident blocks of the size's specialised kernel covers on this device (0: no specialisation).
+// The host-step pipeline cuts the batch into whole waves: a chunk of 1.15 waves costs two block lifetimes, one wave one.
+static int envs_per_wave(int J, int M, int device) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 0;
+#define X(JJ, MM, GG, WW, CC) \
+    if (J == JJ && M == MM) return sms * Spec<JJ, MM, GG, WW, CC>::MINB * WW * Spec<JJ, MM, GG, WW, CC>::EPW;
+    MTFJSP_SPEC_SIZES(X)
+#undef X
+    return 0;
+}
 
 static bool has_spec(int J, int M) {
 #define X(JJ, MM, GG, WW, CC) if (J == JJ && M == MM) return true;
@@ -2357,7 +2371,10 @@ int mtfjsp_destroy(mtfjsp_env* h) {
         for (auto& e : h->pipe->cache) cudaGraphExecDestroy(e.exec);
         cudaStreamDestroy(h->pipe->ms);
         cudaEventDestroy(h->pipe->fork);
-        for (int c = 0; c < HostPipe::MAXC; c++) { cudaStreamDestroy(h->pipe->cs[c]); cudaEventDestroy(h->pipe->join[c]); }
+        for (int c = 0; c < HostPipe::MAXC; c++) {
+            cudaStreamDestroy(h->pipe->cs[c]); cudaEventDestroy(h->pipe->join[c]);
+            cudaEventDestroy(h->pipe->hev[c]); cudaEventDestroy(h->pipe->kev[c]);
+        }
         delete h->pipe;
     }
     delete h;
@@ -2663,8 +2680,8 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
     const int inc = obs_inc_now(h, task_fea, mach_fea, adj_w, adj_src, dtype);  // one decision for all chunks of the step
     const uint8_t* jm_dev = mask_mode == MTFJSP_MASK_ESA ? h->jm_esa : h->jm_fin;
     const size_t rs = (size_t)h->rec_stride;
-    // everything one chunk [b0, b1) does, in order, on stream q
-    auto chunk = [&](int b0, int b1, cudaStream_t q) -> int {
+    // the three parts of one chunk [b0, b1): copy-in, kernel, copy-out
+    auto copy_in = [&](int b0, int b1, cudaStream_t q) -> int {
         const size_t n = (size_t)(b1 - b0);
         if (packed) {
             CK(cudaMemcpyAsync(h->act2 + b0, io.act + (size_t)b0 * 2, n * 8, cudaMemcpyHostToDevice, q), "H2D actions");
@@ -2672,10 +2689,15 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
             CK(cudaMemcpyAsync(h->a_op + b0, io.op + b0, n * 4, cudaMemcpyHostToDevice, q), "H2D op");
             CK(cudaMemcpyAsync(h->a_mach + b0, io.mach + b0, n * 4, cudaMemcpyHostToDevice, q), "H2D mach");
         }
-        int rc = step_obs_range(h, h->a_op, h->a_mach, nullptr, nullptr, h->dn, h->inv, io.info6 ? h->info6 : nullptr,
-                                task_fea, mach_fea, adj_w, adj_src, nullptr, nullptr, mask_mode, dtype, b0, b1, q,
-                                packed ? h->act2 : nullptr, io.rec ? h->rec : nullptr, inc);
-        if (rc) return rc;
+        return MTFJSP_OK;
+    };
+    auto kernel = [&](int b0, int b1, cudaStream_t q) -> int {
+        return step_obs_range(h, h->a_op, h->a_mach, nullptr, nullptr, h->dn, h->inv, io.info6 ? h->info6 : nullptr,
+                              task_fea, mach_fea, adj_w, adj_src, nullptr, nullptr, mask_mode, dtype, b0, b1, q,
+                              packed ? h->act2 : nullptr, io.rec ? h->rec : nullptr, inc);
+    };
+    auto copy_out = [&](int b0, int b1, cudaStream_t q) -> int {
+        const size_t n = (size_t)(b1 - b0);
         if (io.rec) CK(cudaMemcpyAsync(io.rec + b0 * rs, h->rec + b0 * rs, n * rs, cudaMemcpyDeviceToHost, q), "D2H records");
         if (io.info6)
             CK(cudaMemcpyAsync(io.info6 + (size_t)b0 * 6, h->info6 + (size_t)b0 * 6, n * 48, cudaMemcpyDeviceToHost, q), "D2H info6");
@@ -2685,6 +2707,12 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
             CK(cudaMemcpyAsync(io.cand + (size_t)b0 * L.J, h->cand + (size_t)b0 * L.J, n * L.J * 4, cudaMemcpyDeviceToHost, q),
                "D2H candidate");
         return MTFJSP_OK;
+    };
+    auto chunk = [&](int b0, int b1, cudaStream_t q) -> int {  // everything one chunk does, in order, on stream q
+        int rc = copy_in(b0, b1, q);
+        if (rc == MTFJSP_OK) rc = kernel(b0, b1, q);
+        if (rc == MTFJSP_OK) rc = copy_out(b0, b1, q);
+        return rc;
     };
     const int want_chunks = h->host_chunks;  // MTFJSP_HOST_CHUNKS, 0: no graph
     const bool pinned = is_pinned(io.op) && is_pinned(io.mach) && is_pinned(io.act) && is_pinned(io.info6) &&
@@ -2705,6 +2733,8 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
         for (int c = 0; c < HostPipe::MAXC; c++) {
             CK(cudaStreamCreateWithFlags(&hp->cs[c], cudaStreamNonBlocking), "cudaStreamCreate");
             CK(cudaEventCreateWithFlags(&hp->join[c], cudaEventDisableTiming), "cudaEventCreate");
+            CK(cudaEventCreateWithFlags(&hp->hev[c], cudaEventDisableTiming), "cudaEventCreate");
+            CK(cudaEventCreateWithFlags(&hp->kev[c], cudaEventDisableTiming), "cudaEventCreate");
         }
         h->pipe = hp;
     }
@@ -2712,6 +2742,22 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
     // chunks of whole 256-env groups, at least 4,096 envs each (below that one launch does not fill the GPU)
     int chunks = want_chunks > HostPipe::MAXC ? HostPipe::MAXC : want_chunks;
     while (chunks > 1 && L.B / chunks < 4096) chunks--;
+    int per = ((L.B + chunks - 1) / chunks + 255) / 256 * 256;
+    static const int ordered = getenv("MTFJSP_HOST_PIPE") ? atoi(getenv("MTFJSP_HOST_PIPE")) : 1;
+    if (ordered && !h->force_generic && chunks > 1) {  // whole waves per chunk (the chunk kernels run one after the other)
+        static thread_local int wave_J = -1, wave_M = -1, wave_dev = -1, wave = 0;
+        if (wave_J != L.J || wave_M != L.M || wave_dev != h->device) {
+            wave = envs_per_wave(L.J, L.M, h->device);
+            wave_J = L.J; wave_M = L.M; wave_dev = h->device;
+        }
+        if (wave > 0 && L.B > wave) {
+            int k = (L.B / chunks + wave / 2) / wave;
+            if (k < 1) k = 1;
+            while ((L.B + k * wave - 1) / (k * wave) > HostPipe::MAXC) k++;
+            per = k * wave;
+            chunks = (L.B + per - 1) / per;
+        }
+    }
     const void* key[11] = {io.op, io.mach, io.act, io.info6, io.jm, io.cand, io.rec, task_fea, mach_fea, adj_w, adj_src};
     HostPipe::Entry* ent = nullptr;
     for (auto& e : hp->cache)
@@ -2721,22 +2767,48 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
             for (auto& e : hp->cache) cudaGraphExecDestroy(e.exec);
             hp->cache.clear();
         }
-        const int per = ((L.B + chunks - 1) / chunks + 255) / 256 * 256;
+
         const int64_t l0 = h->launches;
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(hp->ms, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
         int rc = MTFJSP_OK;
         cudaError_t ce = cudaEventRecord(hp->fork, hp->ms);
-        for (int c = 0; c < chunks && rc == MTFJSP_OK && ce == cudaSuccess; c++) {
-            const int b0 = c * per, b1 = (c + 1) * per < L.B ? (c + 1) * per : L.B;
-            if (b0 >= b1) break;
-            cudaStream_t q = hp->cs[c];
-            ce = cudaStreamWaitEvent(q, hp->fork, 0);
-            if (ce != cudaSuccess) break;
-            rc = chunk(b0, b1, q);
-            if (rc) break;
-            ce = cudaEventRecord(hp->join[c], q);
-            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(hp->ms, hp->join[c], 0);
+        if (ordered) {
+            cudaStream_t qi = hp->cs[0], qk = hp->cs[1], qo = hp->cs[2];  // copies in, kernels (in chunk order), copies out
+            for (int k = 0; k < 3 && ce == cudaSuccess; k++) ce = cudaStreamWaitEvent(hp->cs[k], hp->fork, 0);
+            auto range = [&](int c, int& b0, int& b1) { b0 = c * per; b1 = (c + 1) * per < L.B ? (c + 1) * per : L.B; return b0 < b1; };
+            int b0, b1;
+            for (int c = 0; c < chunks && rc == MTFJSP_OK && ce == cudaSuccess && range(c, b0, b1); c++) {
+                rc = copy_in(b0, b1, qi);
+                if (rc == MTFJSP_OK) ce = cudaEventRecord(hp->hev[c], qi);
+            }
+            for (int c = 0; c < chunks && rc == MTFJSP_OK && ce == cudaSuccess && range(c, b0, b1); c++) {
+                ce = cudaStreamWaitEvent(qk, hp->hev[c], 0);
+                if (ce != cudaSuccess) break;
+                rc = kernel(b0, b1, qk);
+                if (rc == MTFJSP_OK) ce = cudaEventRecord(hp->kev[c], qk);
+            }
+            for (int c = 0; c < chunks && rc == MTFJSP_OK && ce == cudaSuccess && range(c, b0, b1); c++) {
+                ce = cudaStreamWaitEvent(qo, hp->kev[c], 0);
+                if (ce != cudaSuccess) break;
+                rc = copy_out(b0, b1, qo);
+            }
+            for (int k = 0; k < 3 && rc == MTFJSP_OK && ce == cudaSuccess; k++) {
+                ce = cudaEventRecord(hp->join[k], hp->cs[k]);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(hp->ms, hp->join[k], 0);
+            }
+        } else {
+            for (int c = 0; c < chunks && rc == MTFJSP_OK && ce == cudaSuccess; c++) {
+                const int b0 = c * per, b1 = (c + 1) * per < L.B ? (c + 1) * per : L.B;
+                if (b0 >= b1) break;
+                cudaStream_t q = hp->cs[c];
+                ce = cudaStreamWaitEvent(q, hp->fork, 0);
+                if (ce != cudaSuccess) break;
+                rc = chunk(b0, b1, q);
+                if (rc) break;
+                ce = cudaEventRecord(hp->join[c], q);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(hp->ms, hp->join[c], 0);
+            }
         }
         cudaError_t ee = cudaStreamEndCapture(hp->ms, &g);
         const int kernels = (int)(h->launches - l0);
