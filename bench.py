@@ -367,7 +367,9 @@ def measure_env(wl, B, K, W, repeats, rank, world, dev, barrier, sh, envm, torch
     out["kern"], out["peak"], out["peak_src"], out["rows"] = kern, peak, peak_src, rows
 
     # ---- e2e: host-buffer C-ABI call per step (pinned H2D action pairs, D2H packed step records = step info + job
-    # mask + candidates; mtfjsp_step_host_packed cuts the batch into chunks whose copies overlap the other chunks' kernels) ----
+    # mask + candidates; mtfjsp_step_host_packed: one launch whose warps write their records straight into the mapped pinned
+    # host buffer and read the action pairs from it -- the bytes below cross PCIe inside the timed region, by SM loads /
+    # stores instead of the copy engine) ----
     if want_e2e:
         h_act = torch.stack([rec_op.cpu(), rec_mc.cpu()], dim=2).contiguous().pin_memory()  # [N,B,2] (op, machine)
         _, h_rec = env.host_buffers()
@@ -396,7 +398,8 @@ def measure_env(wl, B, K, W, repeats, rank, world, dev, barrier, sh, envm, torch
         out["e2e"] = {"value": B * world * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 8,
                       "d2h_bytes_per_step": B * h_rec.shape[1],
                       "api": "mtfjsp_step_host_packed (C ABI, pinned host buffers: [B,2] i32 action pairs in, [B] packed "
-                             "records (f64 info6, i16 candidates, u8 job mask) out; observation tensors stay on the device)",
+                             "records (f64 info6, i16 candidates, u8 job mask) out, written by the step kernel itself over "
+                             "PCIe (mapped host memory); observation tensors stay on the device)",
                       "steps": Ke, "repeats": repeats, "us_per_step": e2e_s * 1e6 / Ke}
         assert float(rec_view["info6"][:, 1].sum()) in (0.0, float(B))
         # the same call returning ONLY the reference's step info (`oenv_info` rows, 48 B per env): candidates and job mask

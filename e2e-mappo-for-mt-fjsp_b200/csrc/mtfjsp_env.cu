@@ -114,7 +114,8 @@ struct Params {
     int32_t* cand_int;
 };
 
-enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4, MODE_POLICY = 8 };
+enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4, MODE_POLICY = 8,
+       MODE_HOST = 16 };  // size-specialised kernels: step info / packed records leave as whole-warp runs (host-step calls)
 
 // step info (r, done, mk_s, idle_s, pt_s, tt_s) goes to the contiguous [B,6] array and / or the packed host record
 #define INFO6_PUT(b_, k_, v_)                                                                               \
@@ -821,6 +822,21 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     const double* __restrict__ s_tt = reinterpret_cast<const double*>(base + S::B_SD);
     double* __restrict__ s_pt = reinterpret_cast<double*>(base + S::B_SD + S::B_TT);
     int16_t* __restrict__ s_si = reinterpret_cast<int16_t*>(base + S::B_SD + S::B_TT + S::B_PT);
+    // packed host-step record (P.rec): assembled in the idle-term scratch once the idle sum is done with it, then written
+    // by the whole warp as one contiguous run of 8-byte words -- the buffer may be mapped host memory, where piecewise
+    // stores would each become a PCIe write of their own
+    constexpr int RECW = (48 + 3 * J + 7) / 8;
+    static_assert(RECW <= S::NPT, "the record is staged in the idle-term scratch");
+    unsigned char* const s_rec = reinterpret_cast<unsigned char*>(s_pt);
+    constexpr bool REC_STAGED = (MODE & MODE_HOST) != 0;  // the host-step kernel
+#define INFO6_S(k_, v_)                                                                      \
+    do {                                                                                     \
+        if constexpr (REC_STAGED) {                                                          \
+            if (P.rec || P.info6) reinterpret_cast<double*>(s_rec)[(k_)] = (v_);             \
+        } else {                                                                             \
+            INFO6_PUT(b, (k_), (v_));                                                        \
+        }                                                                                    \
+    } while (0)
 
     double* g_sd = P.sd + (size_t)bc * S::SD;
     int16_t* g_si = P.si + (size_t)bc * S::SI;
@@ -1354,11 +1370,12 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const double mean = firstn ? R : mean1, Sn = firstn ? S0 : S1, sdv = firstn ? fabs(R) : sd1;
         const double scaled = x / (sdv + 1e-8);
         __syncwarp();
+        if (REC_STAGED && P.rec && gl == 5) reinterpret_cast<uint64_t*>(s_rec)[RECW - 1] = 0;  // padding behind the mask bytes
         if (valid) {
             if (gl < 4) {
                 s_sc[gl] = R; s_sc[4 + gl] = mean; s_sc[8 + gl] = Sn;
                 if (P.scaled4) P.scaled4[(size_t)b * 4 + gl] = scaled;
-                INFO6_PUT(b, 2 + gl, scaled);
+                INFO6_S(2 + gl, scaled);
             }
             if (gl == 0) {
                 s_sc[12] = nn;
@@ -1372,16 +1389,16 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 }
                 if (P.done) P.done[b] = done ? 1 : 0;
                 if (P.invalid) P.invalid[b] = 0;
-                INFO6_PUT(b, 0, total); INFO6_PUT(b, 1, done ? 1.0 : 0.0);
+                INFO6_S(0, total); INFO6_S(1, done ? 1.0 : 0.0);
             }
         } else if (active) {
             if (gl < 5 && P.reward5) P.reward5[(size_t)b * 5 + gl] = 0.0;
             if (gl < 4 && P.scaled4) P.scaled4[(size_t)b * 4 + gl] = 0.0;
-            if (gl < 6 && gl != 1) INFO6_PUT(b, gl, 0.0);
+            if (gl < 6 && gl != 1) INFO6_S(gl, 0.0);
             if (gl == 0) {
                 if (P.done) P.done[b] = (s_misc[2] == N) ? 1 : 0;
                 if (P.invalid) P.invalid[b] = 1;
-                INFO6_PUT(b, 1, (s_misc[2] == N) ? 1.0 : 0.0);
+                INFO6_S(1, (s_misc[2] == N) ? 1.0 : 0.0);
             }
         }
         __syncwarp();
@@ -1415,9 +1432,45 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 if (P.jmask) P.jmask[(size_t)b * J + gl] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
                 if (P.cand) P.cand[(size_t)b * J + gl] = c;
                 if (P.rec) {
-                    unsigned char* r = P.rec + (size_t)b * P.rec_stride;
+                    unsigned char* r = REC_STAGED ? s_rec : P.rec + (size_t)b * P.rec_stride;
                     reinterpret_cast<int16_t*>(r + 48)[gl] = (int16_t)c;
                     r[48 + 2 * J + gl] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+                }
+            }
+        }
+        if constexpr (REC_STAGED) {
+            const unsigned char* const wbase = smem_raw + (size_t)(warp * EPW) * S::ENV_BYTES + S::B_SD + S::B_TT;
+            if (P.rec || P.info6) __syncwarp();
+            if (P.info6) {  // [B,6] step info: the warp's EPW rows are contiguous, 16 bytes per lane
+                double2* const out = reinterpret_cast<double2*>(P.info6 + (size_t)wb0 * 6);
+#pragma unroll
+                for (int i0 = 0; i0 < EPW * 3; i0 += 32) {
+                    const int i = i0 + lane, e = i / 3, w = i - e * 3;
+                    if (i < EPW * 3 && wb0 + e < B)
+                        out[i] = *reinterpret_cast<const double2*>(wbase + (size_t)e * S::ENV_BYTES + w * 16);
+                }
+            }
+            if (P.rec) {  // the warp's EPW records are contiguous in the output
+                auto word = [&](const int i) {  // 8-byte word i of the warp's run
+                    const int e = i / RECW, w = i - e * RECW;
+                    return *reinterpret_cast<const double*>(wbase + (size_t)e * S::ENV_BYTES + w * 8);
+                };
+                if constexpr ((EPW * RECW) % 2 == 0) {
+                    // 16 bytes per lane: over PCIe 47.5 GB/s against 43.7 with 8-byte lanes (profiles/micro/hostwrite.cu)
+                    double2* const out = reinterpret_cast<double2*>(P.rec + (size_t)wb0 * (RECW * 8));
+#pragma unroll
+                    for (int i0 = 0; i0 < EPW * RECW / 2; i0 += 32) {
+                        const int i = i0 + lane;
+                        if (i < EPW * RECW / 2 && wb0 + (2 * i + 1) / RECW < B) out[i] = make_double2(word(2 * i), word(2 * i + 1));
+                        else if (i < EPW * RECW / 2 && wb0 + (2 * i) / RECW < B) reinterpret_cast<double*>(out)[2 * i] = word(2 * i);
+                    }
+                } else {
+                    double* const out = reinterpret_cast<double*>(P.rec + (size_t)wb0 * (RECW * 8));
+#pragma unroll
+                    for (int i0 = 0; i0 < EPW * RECW; i0 += 32) {
+                        const int i = i0 + lane;
+                        if (i < EPW * RECW && wb0 + i / RECW < B) out[i] = word(i);
+                    }
                 }
             }
         }
@@ -2011,6 +2064,7 @@ struct mtfjsp_env {
     bool obs_inc_enabled, obs_inc_allowed, obs_synced;
     const void* obs_ptrs[4];
     int obs_dtype;
+    int host_zerocopy;             // MTFJSP_HOST_ZEROCOPY: packed host step writes records straight to mapped host memory
     int host_chunks, fuse_policy;  // tuning knobs read from the environment at create time (tests compare the settings)
     int alternate_order, flip;     // MTFJSP_ALTERNATE_ORDER (default on): successive step launches walk the batch in
                                    // opposite directions for L2 reuse
@@ -2160,7 +2214,7 @@ static int launch_env_auto(mtfjsp_env* h, const Params& P, cudaStream_t s) {
         MTFJSP_SPEC_SIZES(X)
 #undef X
     }
-    return launch_env<MODE, OutT>(h, P, s);
+    return launch_env<MODE & ~MODE_HOST, OutT>(h, P, s);
 }
 
 // random-rollout step in one launch (policy + candidate-machine features + step + observation): sizes with a
@@ -2245,6 +2299,9 @@ static int step_obs_range(mtfjsp_env* h, const int32_t* op, const int32_t* mach,
     P.obs_inc = obs_inc;
     int rc = fill_obs(h, P, task_fea, mach_fea, adj_w, adj_src, job_mask, candidate, mask_mode, dtype);
     if (rc) return rc;
+    if (rec || info6)  // host-step calls: the variant that stages these outputs and writes them as whole-warp runs
+        return dtype == MTFJSP_F64 ? launch_env_auto<MODE_STEP | MODE_OBS | MODE_HOST, double>(h, P, s)
+                                   : launch_env_auto<MODE_STEP | MODE_OBS | MODE_HOST, float>(h, P, s);
     return dtype == MTFJSP_F64 ? launch_env_auto<MODE_STEP | MODE_OBS, double>(h, P, s)
                                : launch_env_auto<MODE_STEP | MODE_OBS, float>(h, P, s);
 }
@@ -2299,6 +2356,8 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
         const char* fg = getenv("MTFJSP_FORCE_GENERIC");  // test hook: run the generic kernel on every size
         h->force_generic = fg && fg[0] == '1';
         h->host_chunks = getenv("MTFJSP_HOST_CHUNKS") ? atoi(getenv("MTFJSP_HOST_CHUNKS")) : 4;
+        // default: records zero-copy; the actions too from 16,384 envs up (below that the explicit copy is as fast)
+        h->host_zerocopy = getenv("MTFJSP_HOST_ZEROCOPY") ? atoi(getenv("MTFJSP_HOST_ZEROCOPY")) : (B >= 16384 ? 2 : 1);
         h->fuse_policy = getenv("MTFJSP_FUSE_POLICY") ? atoi(getenv("MTFJSP_FUSE_POLICY")) : 1;
         h->alternate_order = getenv("MTFJSP_ALTERNATE_ORDER") ? atoi(getenv("MTFJSP_ALTERNATE_ORDER")) : 1;
         h->obs_inc_allowed = !(getenv("MTFJSP_OBS_INCREMENTAL") && atoi(getenv("MTFJSP_OBS_INCREMENTAL")) == 0);  // test hook
@@ -2724,6 +2783,47 @@ static int host_step_impl(mtfjsp_env* h, const HostIO& io, void* task_fea, void*
         obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
         CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
         return MTFJSP_OK;
+    }
+    // Zero-copy form (packed records in pinned, device-mapped host memory; MTFJSP_HOST_ZEROCOPY, default on): ONE launch over
+    // the whole batch whose warps write their finished records straight into the caller's buffer, so the PCIe writes of
+    // the first blocks run under the rest of the kernel -- no staging buffer, no copy engine, no cross-stream dependencies.
+    // Level 2 also reads the packed actions from the caller's buffer instead of copying them in first.
+    if (packed && h->host_zerocopy > 0 && !h->force_generic && has_spec(L.J, L.M)) {
+        void* drec = nullptr;
+        void* dact = nullptr;
+        if (cudaHostGetDevicePointer(&drec, io.rec, 0) == cudaSuccess && drec &&
+            (h->host_zerocopy < 2 || (cudaHostGetDevicePointer(&dact, const_cast<int32_t*>(io.act), 0) == cudaSuccess && dact))) {
+            if (!dact) CK(cudaMemcpyAsync(h->act2, io.act, (size_t)L.B * 8, cudaMemcpyHostToDevice, s), "H2D actions");
+            int rc = step_obs_range(h, h->a_op, h->a_mach, nullptr, nullptr, h->dn, h->inv, nullptr, task_fea, mach_fea, adj_w,
+                                    adj_src, nullptr, nullptr, mask_mode, dtype, 0, L.B, s,
+                                    dact ? reinterpret_cast<const int2*>(dact) : h->act2, reinterpret_cast<unsigned char*>(drec), inc);
+            if (rc) return rc;
+            obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
+            CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+            return MTFJSP_OK;
+        }
+        cudaGetLastError();  // not mapped for this device: the copy pipeline below
+    }
+    // the split form when only the [B,6] step info comes back (job mask / candidates stay on the device): same idea
+    if (!packed && io.info6 && !io.jm && !io.cand && h->host_zerocopy > 0 && !h->force_generic && has_spec(L.J, L.M)) {
+        void *dinfo = nullptr, *dop = nullptr, *dmach = nullptr;
+        if (cudaHostGetDevicePointer(&dinfo, io.info6, 0) == cudaSuccess && dinfo &&
+            (h->host_zerocopy < 2 || (cudaHostGetDevicePointer(&dop, const_cast<int32_t*>(io.op), 0) == cudaSuccess && dop &&
+                                      cudaHostGetDevicePointer(&dmach, const_cast<int32_t*>(io.mach), 0) == cudaSuccess && dmach))) {
+            if (!dop) {
+                CK(cudaMemcpyAsync(h->a_op, io.op, (size_t)L.B * 4, cudaMemcpyHostToDevice, s), "H2D op");
+                CK(cudaMemcpyAsync(h->a_mach, io.mach, (size_t)L.B * 4, cudaMemcpyHostToDevice, s), "H2D mach");
+            }
+            int rc = step_obs_range(h, dop ? reinterpret_cast<const int32_t*>(dop) : h->a_op,
+                                    dop ? reinterpret_cast<const int32_t*>(dmach) : h->a_mach, nullptr, nullptr, h->dn, h->inv,
+                                    reinterpret_cast<double*>(dinfo), task_fea, mach_fea, adj_w, adj_src, nullptr, nullptr, mask_mode,
+                                    dtype, 0, L.B, s, nullptr, nullptr, inc);
+            if (rc) return rc;
+            obs_mark(h, task_fea, mach_fea, adj_w, adj_src, dtype);
+            CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+            return MTFJSP_OK;
+        }
+        cudaGetLastError();
     }
     if (!h->pipe) {
         HostPipe* hp = new (std::nothrow) HostPipe();

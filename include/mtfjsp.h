@@ -165,9 +165,15 @@ int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_
  *     f64 info6[6] = (r, done, mk_s, idle_s, pt_s, tt_s)   trainer/parallel_env.py:260
  *     i16 candidate[J]                                      algorithm/ppo_algorithm.py:202-317
  *     u8  job_mask[J]   (1 = not selectable), then padding
- * With pinned buffers the batch is cut into MTFJSP_HOST_CHUNKS (default 4) chunks whose copy-in -> kernel -> copy-out
- * chains run on separate streams, replayed as one CUDA graph per step, so that the copy-out of chunk c overlaps the
- * kernel of chunk c+1; pageable buffers take the plain in-order path.  Synchronises `stream` before returning. */
+ * With pinned buffers (cudaHostAlloc / cudaHostRegister'd, hence mapped into the device's address space) and a
+ * size-specialised kernel, the step is ONE launch whose warps write their finished records straight into
+ * `records_host` over PCIe while the rest of the batch is still being stepped -- no staging buffer, no copy engine
+ * (MTFJSP_HOST_ZEROCOPY: 1 = records, 2 = the actions are read from `actions_host` in place as well; default 2 from
+ * 16,384 envs up, else 1; 0 = the staged form).  Staged form: the batch is cut into MTFJSP_HOST_CHUNKS (default 4) chunks
+ * whose copy-in -> kernel -> copy-out chains run on three streams, replayed as one CUDA graph per step, so that the
+ * copy-out of chunk c overlaps the kernel of chunk c+1; pageable buffers take the plain in-order path.  mtfjsp_step_host
+ * with NULL job_mask_host / candidate_host writes its [B,6] step info the same zero-copy way.  Synchronises `stream`
+ * before returning: the host buffers are complete when the call returns. */
 int mtfjsp_step_host_packed(mtfjsp_env* h, const int32_t* actions_host, void* records_host, void* task_fea, void* mach_fea,
                             float* adj_w, int16_t* adj_src, int mask_mode, int dtype, void* stream);
 int mtfjsp_host_record_bytes(const mtfjsp_env* h);

@@ -229,13 +229,18 @@ def test_step_before_reset_is_a_state_error():
 
 
 @pytest.mark.parametrize("B", [4096 + 77, 3 * 4096 + 77])
-@pytest.mark.parametrize("pinned", [True, False])
-def test_host_step_equals_device_step(pinned, B, kernel_path):
+@pytest.mark.parametrize("pinned", [True, False, "copy", "zerocopy_actions"])
+def test_host_step_equals_device_step(pinned, B, kernel_path, monkeypatch):
     """mtfjsp_step_host with pinned (graph-replayed chunk pipeline; 1 chunk and 3 ragged chunks) and with pageable
     host buffers (in-order copies) must equal the device-pointer call bit for bit, including the all-invalid step
-    after the episode has ended."""
+    after the episode has ended.  The packed form with pinned buffers writes its records straight into the mapped host
+    buffer (default); "copy" = the staged copy pipeline instead (MTFJSP_HOST_ZEROCOPY=0), "zerocopy_actions" = the actions
+    are read from the mapped host buffer as well (=2)."""
     if kernel_path == "unfused":
         pytest.skip("no random_step here, 'auto' covers it")
+    if pinned in ("copy", "zerocopy_actions"):
+        monkeypatch.setenv("MTFJSP_HOST_ZEROCOPY", "0" if pinned == "copy" else "2")  # read by mtfjsp_create
+        pinned = True
     envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
     J, M, E = 6, 6, 2
     N = J * M
@@ -253,6 +258,10 @@ def test_host_step_equals_device_step(pinned, B, kernel_path):
     pk_env.load(d["t"], d["p"], d["transT"], d["edge"])
     pk_env.scaler_init()
     pk_env.reset(w)
+    io_env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)  # step info only comes back
+    io_env.load(d["t"], d["p"], d["transT"], d["edge"])
+    io_env.scaler_init()
+    io_env.reset(w)
     pk_act, pk_rec = pk_env.host_buffers()
     if not pinned:
         pk_act, pk_rec = pk_act.clone(), pk_rec.clone()
@@ -262,6 +271,7 @@ def test_host_step_equals_device_step(pinned, B, kernel_path):
     info6 = pin(torch.full((B, 6), -7.0, dtype=torch.float64))
     h_jm = pin(torch.full((B, J), 9, dtype=torch.uint8))
     h_cd = pin(torch.full((B, J), -1, dtype=torch.int32))
+    info6_only = pin(torch.full((B, 6), -9.0, dtype=torch.float64))
     for s in range(N + 1):  # one step past the end: every action is invalid and must be reported as such
         op, mach = dev_env.policy_random(seed=5)
         if s == N:
@@ -274,6 +284,8 @@ def test_host_step_equals_device_step(pinned, B, kernel_path):
         eq(info6[:, 2:].numpy(), dev_env.scaled4.cpu().numpy())
         eq(h_jm.numpy(), dev_env.job_mask.cpu().numpy())
         eq(h_cd.numpy(), dev_env.candidate.cpu().numpy())
+        io_env.step_host(h_op, h_mc, info6_only, None, None)
+        eq(info6_only.numpy(), info6.numpy())
         pk_act[:, 0].copy_(op.cpu()); pk_act[:, 1].copy_(mach.cpu())
         if s % 2:   # the prepared-call form and the general method are interchangeable
             pk_env.host_stepper(pk_rec)(pk_act.data_ptr())
@@ -285,6 +297,7 @@ def test_host_step_equals_device_step(pinned, B, kernel_path):
         for name in ("task_fea", "mach_fea", "adj_w", "adj_src"):
             assert torch.equal(getattr(host_env, name), getattr(dev_env, name)), (name, s)
             assert torch.equal(getattr(pk_env, name), getattr(dev_env, name)), (name, s)
+            assert torch.equal(getattr(io_env, name), getattr(dev_env, name)), (name, s)
         assert int(dev_env.invalid.sum()) == (B if s == N else 0)
     assert bool(dev_env.done.all()) and float(info6[:, 1].sum()) == B
     eq(host_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
