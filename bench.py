@@ -398,10 +398,10 @@ def measure_env(wl, B, K, W, repeats, rank, world, dev, barrier, sh, envm, torch
         out["e2e"] = {"value": B * world * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 8,
                       "d2h_bytes_per_step": B * h_rec.shape[1],
                       "api": "mtfjsp_step_host_packed (C ABI, pinned host buffers: [B,2] i32 action pairs in, [B] packed "
-                             "records (f64 info6, i16 candidates, u8 job mask) out, written by the step kernel itself over "
+                             "records (f64 r, f64 scaled[4], u8 done, job-mask bits, u8 next op per job) out, written by the step kernel itself over "
                              "PCIe (mapped host memory); observation tensors stay on the device)",
                       "steps": Ke, "repeats": repeats, "us_per_step": e2e_s * 1e6 / Ke}
-        assert float(rec_view["info6"][:, 1].sum()) in (0.0, float(B))
+        assert float(rec_view["done"].sum()) in (0.0, float(B))
         # the same call returning ONLY the reference's step info (`oenv_info` rows, 48 B per env): candidates and job mask
         # stay on the device, where the actors that consume them run (mtfjsp_step_host with NULL mask / candidate buffers)
         h_op = [rec_op[s].cpu().pin_memory() for s in range(N)]

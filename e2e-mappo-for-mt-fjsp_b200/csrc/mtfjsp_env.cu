@@ -93,7 +93,8 @@ struct Params {
     int32_t* mach_out;
     void* mfea1;     // [B,M,6] OutT or NULL
     uint8_t* mmask;  // [B,M] or NULL
-    unsigned char* rec;    // optional packed step records, rec_stride bytes per env: f64 info6[6] | i16 cand[J] | u8 mask[J]
+    unsigned char* rec;    // optional packed step records, rec_stride bytes per env (include/mtfjsp.h, mtfjsp_step_host_packed):
+                           // f64 r | f64 scaled[4] | u8 done | u8 mask_bits[ceil(J/8)] | u8 next_op[J] | padding to 8
     int rec_stride;
     int b0, b1;     // env range [b0, b1) of this launch (host-step pipeline launches sub-ranges)
     int rev;        // blocks walk the env range from its END (alternate launches: what the previous launch touched last is
@@ -121,8 +122,15 @@ enum { MODE_STEP = 1, MODE_OBS = 2, MODE_RESET = 4, MODE_POLICY = 8,
 #define INFO6_PUT(b_, k_, v_)                                                                               \
     do {                                                                                                    \
         if (P.info6) P.info6[(size_t)(b_) * 6 + (k_)] = (v_);                                               \
-        if (P.rec) reinterpret_cast<double*>(P.rec + (size_t)(b_) * P.rec_stride)[(k_)] = (v_);             \
+        if (P.rec) {                                                                                        \
+            unsigned char* r_ = P.rec + (size_t)(b_) * P.rec_stride;                                        \
+            if ((k_) == 1) r_[REC_DONE] = (v_) != 0.0 ? 1 : 0;                                              \
+            else reinterpret_cast<double*>(r_)[(k_) == 0 ? 0 : (k_) - 1] = (v_);                            \
+        }                                                                                                   \
     } while (0)
+// packed record: f64 r @0, f64 scaled[4] @8, u8 done @40, u8 mask_bits[ceil(J/8)] @41, u8 next_op[J] behind them
+constexpr int REC_DONE = 40, REC_BITS = 41;
+__host__ __device__ constexpr int rec_bytes(int J) { return (REC_BITS + (J + 7) / 8 + J + 7) / 8 * 8; }
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -548,26 +556,34 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ Params
         double mn = INFINITY;
         for (int j = lane; j < J; j += 32) mn = fmin(mn, s_v[j]);
         mn = warp_min(mn);
-        for (int j = lane; j < J; j += 32) {
-            int nx = s_nxt[j];
-            uint8_t fin = (nx == M) ? 1 : 0;
-            uint8_t esa = fin;
-            if (first_missing) esa = (nx >= 1) ? 1 : 0;
-            else if (unfinished) esa = (s_v[j] != mn) ? 1 : 0;
-            int c = j * M + (nx < M - 1 ? nx : M - 1);
-            P.jm_fin[(size_t)b * J + j] = fin;
-            P.jm_esa[(size_t)b * J + j] = esa;
-            P.cand_int[(size_t)b * J + j] = c;
-            if (MODE & MODE_OBS) {
-                if (P.jmask) P.jmask[(size_t)b * J + j] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
-                if (P.cand) P.cand[(size_t)b * J + j] = c;
-                if (P.rec) {
-                    unsigned char* r = P.rec + (size_t)b * P.rec_stride;
-                    reinterpret_cast<int16_t*>(r + 48)[j] = (int16_t)c;
-                    r[48 + 2 * J + j] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+        for (int j0 = 0; j0 < J; j0 += 32) {
+            const int j = j0 + lane;
+            uint8_t out_mask = 0;
+            if (j < J) {
+                int nx = s_nxt[j];
+                uint8_t fin = (nx == M) ? 1 : 0;
+                uint8_t esa = fin;
+                if (first_missing) esa = (nx >= 1) ? 1 : 0;
+                else if (unfinished) esa = (s_v[j] != mn) ? 1 : 0;
+                int c = j * M + (nx < M - 1 ? nx : M - 1);
+                P.jm_fin[(size_t)b * J + j] = fin;
+                P.jm_esa[(size_t)b * J + j] = esa;
+                P.cand_int[(size_t)b * J + j] = c;
+                out_mask = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+                if (MODE & MODE_OBS) {
+                    if (P.jmask) P.jmask[(size_t)b * J + j] = out_mask;
+                    if (P.cand) P.cand[(size_t)b * J + j] = c;
+                    if (P.rec) P.rec[(size_t)b * P.rec_stride + REC_BITS + (J + 7) / 8 + j] = (uint8_t)(nx < M - 1 ? nx : M - 1);
                 }
             }
+            if (MODE & MODE_OBS) {
+                const unsigned bits = __ballot_sync(FULL, out_mask != 0);
+                if (P.rec && lane < 4 && j0 + 8 * lane < J)
+                    P.rec[(size_t)b * P.rec_stride + REC_BITS + j0 / 8 + lane] = (uint8_t)(bits >> (8 * lane));
+            }
         }
+        if ((MODE & MODE_OBS) && P.rec)  // padding
+            for (int i = REC_BITS + (J + 7) / 8 + J + lane; i < P.rec_stride; i += 32) P.rec[(size_t)b * P.rec_stride + i] = 0;
     }
 
     if (MODE & MODE_OBS) {
@@ -825,14 +841,19 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     // packed host-step record (P.rec): assembled in the idle-term scratch once the idle sum is done with it, then written
     // by the whole warp as one contiguous run of 8-byte words -- the buffer may be mapped host memory, where piecewise
     // stores would each become a PCIe write of their own
-    constexpr int RECW = (48 + 3 * J + 7) / 8;
-    static_assert(RECW <= S::NPT, "the record is staged in the idle-term scratch");
-    unsigned char* const s_rec = reinterpret_cast<unsigned char*>(s_pt);
+    // Staging: words 0..5 of the scratch = the six step-info doubles, behind them the record's bytes from `done` on.
+    constexpr int RECW = rec_bytes(J) / 8, MBYTES = (J + 7) / 8;
+    static_assert(6 + RECW - 5 <= S::NPT, "step info and record tail are staged in the idle-term scratch");
+    unsigned char* const s_rec = reinterpret_cast<unsigned char*>(s_pt + 6) - REC_DONE;  // record byte i >= 40 at s_rec[i]
     constexpr bool REC_STAGED = (MODE & MODE_HOST) != 0;  // the host-step kernel
 #define INFO6_S(k_, v_)                                                                      \
     do {                                                                                     \
         if constexpr (REC_STAGED) {                                                          \
-            if (P.rec || P.info6) reinterpret_cast<double*>(s_rec)[(k_)] = (v_);             \
+            if (P.rec || P.info6) s_pt[(k_)] = (v_);                                         \
+            if ((k_) == 1 && P.rec) {  /* the lane that knows `done` clears the tail first */ \
+                for (int i_ = 0; i_ < RECW - 5; i_++) reinterpret_cast<uint64_t*>(s_pt + 6)[i_] = 0; \
+                s_rec[REC_DONE] = (v_) != 0.0 ? 1 : 0;                                       \
+            }                                                                                \
         } else {                                                                             \
             INFO6_PUT(b, (k_), (v_));                                                        \
         }                                                                                    \
@@ -1370,7 +1391,6 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const double mean = firstn ? R : mean1, Sn = firstn ? S0 : S1, sdv = firstn ? fabs(R) : sd1;
         const double scaled = x / (sdv + 1e-8);
         __syncwarp();
-        if (REC_STAGED && P.rec && gl == 5) reinterpret_cast<uint64_t*>(s_rec)[RECW - 1] = 0;  // padding behind the mask bytes
         if (valid) {
             if (gl < 4) {
                 s_sc[gl] = R; s_sc[4 + gl] = mean; s_sc[8 + gl] = Sn;
@@ -1419,6 +1439,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const bool first_missing = ((bal0 >> (ge * G)) & S::GMASK) != 0;
         const bool unfinished = ((bal1 >> (ge * G)) & S::GMASK) != 0;
         const double mn = gmin_d<G>(vj);
+        uint8_t out_mask = 0;
         if (gl < J && active) {
             const uint8_t fin = (nx == M) ? 1 : 0;
             uint8_t esa = fin;
@@ -1428,14 +1449,20 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             P.jm_fin[(size_t)b * J + gl] = fin;
             P.jm_esa[(size_t)b * J + gl] = esa;
             P.cand_int[(size_t)b * J + gl] = c;
+            out_mask = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
             if (MODE & MODE_OBS) {
-                if (P.jmask) P.jmask[(size_t)b * J + gl] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
+                if (P.jmask) P.jmask[(size_t)b * J + gl] = out_mask;
                 if (P.cand) P.cand[(size_t)b * J + gl] = c;
-                if (P.rec) {
-                    unsigned char* r = REC_STAGED ? s_rec : P.rec + (size_t)b * P.rec_stride;
-                    reinterpret_cast<int16_t*>(r + 48)[gl] = (int16_t)c;
-                    r[48 + 2 * J + gl] = (P.mask_mode == MTFJSP_MASK_ESA) ? esa : fin;
-                }
+            }
+        }
+        if ((MODE & MODE_OBS) && P.rec) {  // mask bits and next-op bytes of the packed record
+            const unsigned bits = (__ballot_sync(FULL, out_mask != 0) >> (ge * G)) & S::GMASK;
+            unsigned char* const r = REC_STAGED ? s_rec : P.rec + (size_t)b * P.rec_stride;
+            if (active) {
+                if (gl < MBYTES) r[REC_BITS + gl] = (uint8_t)(bits >> (8 * gl));
+                if (gl < J) r[REC_BITS + MBYTES + gl] = (uint8_t)(nx < M - 1 ? nx : M - 1);
+                if (!REC_STAGED)
+                    for (int i = REC_BITS + MBYTES + J + gl; i < RECW * 8; i += G) r[i] = 0;
             }
         }
         if constexpr (REC_STAGED) {
@@ -1451,9 +1478,9 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 }
             }
             if (P.rec) {  // the warp's EPW records are contiguous in the output
-                auto word = [&](const int i) {  // 8-byte word i of the warp's run
+                auto word = [&](const int i) {  // 8-byte word i of the warp's run: r | scaled[4] | tail words
                     const int e = i / RECW, w = i - e * RECW;
-                    return *reinterpret_cast<const double*>(wbase + (size_t)e * S::ENV_BYTES + w * 8);
+                    return *reinterpret_cast<const double*>(wbase + (size_t)e * S::ENV_BYTES + (w == 0 ? 0 : w + 1) * 8);
                 };
                 if constexpr ((EPW * RECW) % 2 == 0) {
                     // 16 bytes per lane: over PCIe 47.5 GB/s against 43.7 with 8-byte lanes (profiles/micro/hostwrite.cu)
@@ -2405,7 +2432,7 @@ int mtfjsp_create(mtfjsp_env** out, int B, int J, int M, int E, int left_shift, 
     ALLOC(h->r5, Bs * 5 * 8);
     ALLOC(h->s4, Bs * 4 * 8);
     ALLOC(h->info6, Bs * 6 * 8);
-    h->rec_stride = (48 + 3 * J + 7) / 8 * 8;
+    h->rec_stride = rec_bytes(J);
     ALLOC(h->act2, Bs * 8);
     ALLOC(h->rec, Bs * h->rec_stride);
     ALLOC(h->dn, Bs);

@@ -169,10 +169,25 @@ class BatchedMTFJSPEnv:
                                          _ptr(self.adj_src), mm, self._dt, _stream()), "mtfjsp_step_host")
 
     def host_record_dtype(self):
-        """numpy structured dtype of one packed host-step record (include/mtfjsp.h: mtfjsp_step_host_packed)."""
+        """numpy structured dtype of one packed host-step record (include/mtfjsp.h: mtfjsp_step_host_packed):
+        r, scaled4 = (mk_s, idle_s, pt_s, tt_s), done, mask_bits (bit j & 7 of byte j >> 3: job j not selectable),
+        next_op (candidate op of job j = j * M + next_op[j])."""
         nbytes = int(self._lib.mtfjsp_host_record_bytes(self._h))
-        return np.dtype({"names": ["info6", "candidate", "job_mask"], "formats": [("<f8", 6), ("<i2", self.J), ("u1", self.J)],
-                         "offsets": [0, 48, 48 + 2 * self.J], "itemsize": nbytes})
+        mb = (self.J + 7) // 8
+        return np.dtype({"names": ["r", "scaled4", "done", "mask_bits", "next_op"],
+                         "formats": ["<f8", ("<f8", 4), "u1", ("u1", mb), ("u1", self.J)],
+                         "offsets": [0, 8, 40, 41, 41 + mb], "itemsize": nbytes})
+
+    def decode_records(self, records_host):
+        """Packed host-step records -> the arrays of the split call: info6 [B,6] f64 = (r, done, mk_s, idle_s, pt_s, tt_s)
+        (trainer/parallel_env.py:260), candidate [B,J] int32, job_mask [B,J] uint8."""
+        rec = records_host.numpy() if isinstance(records_host, torch.Tensor) else np.asarray(records_host)
+        rec = rec.view(self.host_record_dtype())[:, 0]
+        info6 = np.empty((rec.shape[0], 6), dtype=np.float64)
+        info6[:, 0] = rec["r"]; info6[:, 1] = rec["done"]; info6[:, 2:] = rec["scaled4"]
+        candidate = np.arange(self.J, dtype=np.int32)[None, :] * self.M + rec["next_op"].astype(np.int32)
+        job_mask = np.unpackbits(rec["mask_bits"], axis=1, bitorder="little")[:, :self.J]
+        return info6, candidate, job_mask
 
     def host_buffers(self):
         """Pinned host buffers for step_host_packed: actions [B,2] int32 and records [B, record_bytes] uint8

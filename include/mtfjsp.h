@@ -162,9 +162,11 @@ int mtfjsp_step_host(mtfjsp_env* h, const int32_t* op_host, const int32_t* mach_
 /* Packed form of mtfjsp_step_host, one copy each way: `actions_host` [B,2] i32 is the reference's joint-action list
  * [(task_idx, machine_idx), ...] (trainer/parallel_env.py:217-232) as an array; `records_host` receives B records of
  * mtfjsp_host_record_bytes(h) bytes each (8-byte aligned):
- *     f64 info6[6] = (r, done, mk_s, idle_s, pt_s, tt_s)   trainer/parallel_env.py:260
- *     i16 candidate[J]                                      algorithm/ppo_algorithm.py:202-317
- *     u8  job_mask[J]   (1 = not selectable), then padding
+ *     f64 r, f64 scaled[4] = (mk_s, idle_s, pt_s, tt_s)     trainer/parallel_env.py:260 (oenv_info columns 0, 2..5)
+ *     u8  done                                              (oenv_info column 1)
+ *     u8  mask_bits[(J+7)/8]   bit (j & 7) of byte (j >> 3) set = job j not selectable   algorithm/ppo_algorithm.py:202-317
+ *     u8  next_op[J]           candidate op of job j = j * M + next_op[j]; then zero padding to a multiple of 8
+ * (48 bytes at J = 6: the step's D2H traffic is what bounds the call).
  * With pinned buffers (cudaHostAlloc / cudaHostRegister'd, hence mapped into the device's address space) and a
  * size-specialised kernel, the step is ONE launch whose warps write their finished records straight into
  * `records_host` over PCIe while the rest of the batch is still being stepped -- no staging buffer, no copy engine

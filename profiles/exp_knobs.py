@@ -100,7 +100,7 @@ for rep in range(reps):
 torch.cuda.synchronize()
 p_us = (time.perf_counter() - t0) * 1e6 / (reps * N)
 recv = p_rec.numpy().view(env.host_record_dtype())[:, 0]
-assert float(recv["info6"][:, 1].sum()) == B and torch.equal(env.costs(), costs_ref)
+assert float(recv["done"].sum()) == B and torch.equal(env.costs(), costs_ref)
 bytes_step = env.bytes_per_step()
 print(json.dumps({"workload": sys.argv[1] if len(sys.argv) > 1 else "A",
                   "knobs": {k: v for k, v in os.environ.items() if k.startswith("MTFJSP_")},

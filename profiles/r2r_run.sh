@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_cuda_parity.py -m gpu -x -q -k "host_step" > gpurun_out/r2r_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2r_pytest.log
+timeout 900 python -m pytest tests/test_cuda_parity.py -m gpu -x -q -k "host_step or packed_host" > gpurun_out/r2r_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2r_pytest.log
 timeout 600 python profiles/prof_zerocopy.py A > gpurun_out/r2r_zc_A.log 2>&1; cat gpurun_out/r2r_zc_A.log | tail -8
 timeout 600 python profiles/prof_zerocopy.py C > gpurun_out/r2r_zc_C.log 2>&1; cat gpurun_out/r2r_zc_C.log | tail -8
 timeout 600 python bench.py --steps 72 --warmup 5 --repeats 5 --no-policy --no-train --no-dropin --no-cpu-baseline --no-workloads > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err; python - <<'PY'

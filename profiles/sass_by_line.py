@@ -19,8 +19,11 @@ HDR = {}
 def sass_lines(so, pattern):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-    cub = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))  # the env kernels
-    txt = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
+    txt = []
+    for cub in sorted((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: -os.path.getsize(os.path.join(tmp, f))):
+        txt = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
+        if any(ln.startswith("//--------------------- .text.") and pattern in ln for ln in txt):
+            break  # the cubin (one per .cu file) that holds the kernel
     out, on, line = [], False, 0
     for ln in txt:
         if ln.startswith("//--------------------- .text."):

@@ -266,7 +266,6 @@ def test_host_step_equals_device_step(pinned, B, kernel_path, monkeypatch):
     if not pinned:
         pk_act, pk_rec = pk_act.clone(), pk_rec.clone()
     pk_rec.fill_(0xAB)
-    rec = pk_rec.numpy().view(pk_env.host_record_dtype())[:, 0]
     pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
     info6 = pin(torch.full((B, 6), -7.0, dtype=torch.float64))
     h_jm = pin(torch.full((B, J), 9, dtype=torch.uint8))
@@ -291,9 +290,13 @@ def test_host_step_equals_device_step(pinned, B, kernel_path, monkeypatch):
             pk_env.host_stepper(pk_rec)(pk_act.data_ptr())
         else:
             pk_env.step_host_packed(pk_act, pk_rec)
-        eq(rec["info6"], info6.numpy())
-        eq(rec["candidate"].astype(np.int32), h_cd.numpy())
-        eq(rec["job_mask"], h_jm.numpy())
+        r_info6, r_cand, r_mask = pk_env.decode_records(pk_rec)
+        eq(r_info6, info6.numpy())
+        eq(r_cand, h_cd.numpy())
+        eq(r_mask, h_jm.numpy())
+        raw = pk_rec.numpy()
+        used = 41 + (J + 7) // 8 + J
+        assert not raw[:, used:].any()   # padding is written (zero), never left over
         for name in ("task_fea", "mach_fea", "adj_w", "adj_src"):
             assert torch.equal(getattr(host_env, name), getattr(dev_env, name)), (name, s)
             assert torch.equal(getattr(pk_env, name), getattr(dev_env, name)), (name, s)
@@ -302,6 +305,46 @@ def test_host_step_equals_device_step(pinned, B, kernel_path, monkeypatch):
     assert bool(dev_env.done.all()) and float(info6[:, 1].sum()) == B
     eq(host_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
     eq(pk_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
+
+
+@pytest.mark.parametrize("size", [(10, 10, 3), (20, 6, 3), (15, 10, 2), (30, 20, 5), (3, 4, 2), (9, 5, 1)])
+def test_packed_host_records_other_sizes(size):
+    """Packed host-step records at sizes with odd record word counts, more than 8 jobs (several mask bytes), the COLD /
+    NOTT kernels, and sizes without a specialised kernel: decoded records equal the device-pointer call's outputs."""
+    J, M, E = size
+    N, B = J * M, 333
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    d = ins.synthetic_instances(0, B, J, M, E, 91)
+    w = ins.random_weights(0, B, 91)
+    envs = []
+    for _ in range(2):
+        env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)
+        env.load(d["t"], d["p"], d["transT"], d["edge"])
+        env.scaler_init()
+        env.reset(w)
+        envs.append(env)
+    dev_env, pk_env = envs
+    pk_act, pk_rec = pk_env.host_buffers()
+    assert pk_rec.shape[1] == (41 + (J + 7) // 8 + J + 7) // 8 * 8
+    pk_rec.fill_(0xCD)
+    steps = list(range(N)) if N <= 150 else list(range(40)) + list(range(N - 3, N))
+    for s in range(N):
+        op, mach = dev_env.policy_random(seed=17)
+        dev_env.step_obs(op, mach)
+        pk_act[:, 0].copy_(op.cpu()); pk_act[:, 1].copy_(mach.cpu())
+        pk_env.step_host_packed(pk_act, pk_rec)
+        if s not in steps:
+            continue
+        info6, cand, mask = pk_env.decode_records(pk_rec)
+        eq(info6[:, 0], dev_env.reward5[:, 0].cpu().numpy())
+        eq(info6[:, 1], dev_env.done.cpu().numpy().astype(np.float64))
+        eq(info6[:, 2:], dev_env.scaled4.cpu().numpy())
+        eq(cand, dev_env.candidate.cpu().numpy())
+        eq(mask, dev_env.job_mask.cpu().numpy())
+        assert not pk_rec.numpy()[:, 41 + (J + 7) // 8 + J:].any()
+        for name in ("task_fea", "mach_fea", "adj_w", "adj_src"):
+            assert torch.equal(getattr(pk_env, name), getattr(dev_env, name)), (name, s)
+    assert bool(dev_env.done.all())
 
 
 @pytest.mark.parametrize("cfg", [(65536, 6, 6, 2), (16384, 10, 10, 3), (4096, 30, 20, 5)])
