@@ -541,6 +541,174 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ parts, const float
     }
 }
 
+
+// =====================================================================================================================
+// Policy head in ONE kernel (model/gcn_mlp.py:258-320 MLPActor over cat(per-row, per-env, per-env) features,
+// actor_critic.py:244-268 and :455-470):
+//     out[r] = tanh( tanh( act(X[src(r)]) Wa^T + bias_env[r / rpe] ) W1^T + b1 ) . w2 + b2
+// Nothing in this chain couples rows, so a 128-row tile goes through both products without leaving the SM: the rows are
+// gathered (candidate op of each job, or the row itself), the producing layer's BatchNorm + ReLU is applied, the tile is
+// staged as the A operand; `tcgen05.mma` -> TMEM; the first epilogue adds the per-env bias (the per-env column blocks of
+// the first weight matrix, applied once per env by the caller), takes tanh and writes the result back INTO the A buffer
+// (the first product has finished reading it) as the second product's operand; the second epilogue takes tanh, dots the
+// row with w2 and writes one float per row.  Replaces gather + 2 GEMM launches + bias_tanh + tanh_dot: five passes over
+// [rows,128] tensors become one gathered read.  Both weight matrices stay in shared memory (2 x 64 KB), one CTA per SM.
+constexpr int HEAD_WARPS = 16;
+
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
+    const float* __restrict__ X, const int32_t* __restrict__ cand, long long rows, int rpe, int nodes_per_env,
+    const float* __restrict__ in_scale, const float* __restrict__ in_shift, const float* __restrict__ Wa,
+    const float* __restrict__ bias_env, long long bias_rows, const float* __restrict__ W1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out, long long num_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr size_t WBYTES = (size_t)TILE_N * 128 * 4;
+    float* sWa = reinterpret_cast<float*>(smem);
+    float* sW1 = reinterpret_cast<float*>(smem + WBYTES);
+    float* sA = reinterpret_cast<float*>(smem + 2 * WBYTES);
+    float* s_part = reinterpret_cast<float*>(smem + 3 * WBYTES);  // [4][128] partial dots of the second epilogue
+    float* s_b1 = s_part + 4 * 128;
+    float* s_w2 = s_b1 + 128;
+    float* s_scale = s_w2 + 128;
+    float* s_shift = s_scale + 128;
+    int* s_row = reinterpret_cast<int*>(s_shift + 128);  // [2][128] source row of each tile row (-1 past the end)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_row + 256);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool affine = in_scale != nullptr;
+    if (tid < 128) {
+        s_b1[tid] = b1 ? b1[tid] : 0.f;
+        s_w2[tid] = w2[tid];
+        s_scale[tid] = affine ? in_scale[tid] : 1.f;
+        s_shift[tid] = affine ? in_shift[tid] : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar + 0), 1);
+        mbar_init(smem_u32(s_bar + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    stage_block<false, HEAD_WARPS>(sWa, Wa, 0, TILE_N, 128, 128, 128, nullptr, nullptr, false, warp, lane);
+    stage_block<false, HEAD_WARPS>(sW1, W1, 0, TILE_N, 128, 128, 128, nullptr, nullptr, false, warp, lane);
+    auto fill_rows = [&](long long tile, int slot) {  // threads 0..127
+        const long long r = tile * TILE_M + tid;
+        int src = -1;
+        if (tile < num_tiles && r < rows) src = cand ? (int)((r / rpe) * nodes_per_env + __ldg(cand + r)) : (int)r;
+        s_row[slot * 128 + tid] = src;
+    };
+    if (tid < 128) fill_rows(blockIdx.x, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t bar0 = smem_u32(s_bar), bar1 = smem_u32(s_bar + 1);
+    const float b2v = b2 ? __ldg(b2) : 0.f;
+
+    // tile rows -> registers: iteration it = warp + 16 u covers rows 8 (it / 8) .., columns 16 (it % 8) ..; lane = (row % 8,
+    // 16-byte piece): the mapping of stage_block (conflict-free 512-byte shared-memory runs per warp)
+    const int r8 = lane & 7, c4 = lane >> 3;
+    float4 v[8];
+    auto gather = [&](int slot) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int it = warp + u * HEAD_WARPS, grp = it >> 3, q = it & 7;
+            const int src = s_row[slot * 128 + grp * 8 + r8];
+            v[u] = src >= 0 ? __ldg(reinterpret_cast<const float4*>(X + (size_t)src * 128 + q * 16 + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_a = [&](int slot) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int it = warp + u * HEAD_WARPS, grp = it >> 3, q = it & 7, k = q * 16 + c4 * 4;
+            float4 x = v[u];
+            if (affine && s_row[slot * 128 + grp * 8 + r8] >= 0) {
+                x.x = fmaxf(x.x * s_scale[k] + s_shift[k], 0.f); x.y = fmaxf(x.y * s_scale[k + 1] + s_shift[k + 1], 0.f);
+                x.z = fmaxf(x.z * s_scale[k + 2] + s_shift[k + 2], 0.f); x.w = fmaxf(x.w * s_scale[k + 3] + s_shift[k + 3], 0.f);
+            }
+            x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
+            *reinterpret_cast<float4*>(reinterpret_cast<char*>(sA) + grp * 4096 + (q * 4 + c4) * 128 + r8 * 16) = x;
+        }
+    };
+    auto mma_tile = [&](const float* sW, uint32_t dcol) {  // one elected thread: D[dcol..] = A W^T over K = 128
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            umma_tf32(tmem_base + dcol, make_desc(aA + k * 256, 128, 4096), make_desc(aW + k * 256, 128, 4096), k > 0 ? 1u : 0u);
+    };
+
+    const int quad = warp & 3, cg = warp >> 2;  // this warp's TMEM lanes 32 quad .., columns 32 cg ..
+    const int trow = quad * 32 + lane;          // its thread's tile row
+    gather(0);
+    long long i = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+        const int slot = (int)(i & 1);
+        const uint32_t par = (uint32_t)(i & 1);
+        store_a(slot);
+        if (tid < 128) fill_rows(tile + gridDim.x, slot ^ 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            mma_tile(sWa, 0);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0) : "memory");
+        }
+        gather(slot ^ 1);  // the next tile's rows travel while this tile is multiplied
+        mbar_wait(bar0, par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long grow = tile * TILE_M + trow;
+        const bool rok = grow < rows;
+        {   // first epilogue: + per-env bias, tanh, back into the A buffer as the second product's operand
+            uint32_t r[32];
+            TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32), r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const long long brow = bias_rows == 1 ? 0 : (rok ? grow / rpe : 0);
+            const float4* bp = reinterpret_cast<const float4*>(bias_env + brow * 128 + cg * 32);
+            char* dst = reinterpret_cast<char*>(sA) + (trow >> 3) * 4096 + (cg * 8) * 128 + (trow & 7) * 16;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 bb = __ldg(bp + j);
+                float4 x;
+                x.x = to_tf32(tanhf(__uint_as_float(r[4 * j]) + bb.x)); x.y = to_tf32(tanhf(__uint_as_float(r[4 * j + 1]) + bb.y));
+                x.z = to_tf32(tanhf(__uint_as_float(r[4 * j + 2]) + bb.z)); x.w = to_tf32(tanhf(__uint_as_float(r[4 * j + 3]) + bb.w));
+                if (!rok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(dst + j * 128) = x;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            mma_tile(sW1, TILE_N);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar1) : "memory");
+        }
+        mbar_wait(bar1, par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {   // second epilogue: + b1, tanh, dot with w2 over this warp's 32 columns
+            uint32_t r[32];
+            TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TILE_N + cg * 32), r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc = fmaf(tanhf(__uint_as_float(r[j]) + s_b1[cg * 32 + j]), s_w2[cg * 32 + j], acc);
+            s_part[cg * 128 + trow] = acc;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 128) {
+            const long long orow = tile * TILE_M + tid;
+            if (orow < rows) out[orow] = ((s_part[tid] + s_part[128 + tid]) + (s_part[256 + tid] + s_part[384 + tid])) + b2v;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+}
+
 }  // namespace
 
 template <int KP>
@@ -581,6 +749,34 @@ int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, 
     if (K <= 32) return launch_linear<32>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
     if (K <= 64) return launch_linear<64>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
     return launch_linear<128>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
+}
+
+int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int rows_per_env, int nodes_per_env,
+                         const float* in_scale, const float* in_shift, const float* Wa, const float* bias_env,
+                         int64_t bias_rows, const float* W1, const float* b1, const float* w2, const float* b2, float* out,
+                         void* stream) {
+    if (!X || !Wa || !bias_env || !W1 || !w2 || !out || B < 1 || rows_per_env < 1) return MTFJSP_E_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
+    if (bias_rows != 1 && bias_rows != B) return MTFJSP_E_ARG;
+    if (cand && (nodes_per_env < 1 || (long long)B * nodes_per_env > 0x7fffffffLL)) return MTFJSP_E_ARG;
+    const long long rows = (long long)B * rows_per_env;
+    if (rows > 0x7fffffffLL) return MTFJSP_E_ARG;
+    const size_t smem = 3 * (size_t)TILE_N * 128 * 4 + (4 * 128 + 4 * 128) * 4 + 256 * 4 + 2 * 8 + 16;
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(head_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MTFJSP_E_CUDA;
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (rows + TILE_M - 1) / TILE_M;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    head_tf32_kernel<<<grid, HEAD_WARPS * 32, smem, (cudaStream_t)stream>>>(X, cand, rows, rows_per_env, nodes_per_env, in_scale,
+                                                                          in_shift, Wa, bias_env, bias_rows, W1, b1, w2, b2, out,
+                                                                          tiles);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 
 int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,

@@ -24,8 +24,14 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+import os
+
 from . import _lib
 from ._lib import check
+
+# MTFJSP_FUSED_HEAD=0: the policy heads of the rollout path as separate launches (gather, GEMM, bias + tanh, GEMM,
+# tanh + dot) instead of the one-launch head kernel -- kept for A/B measurements
+_FUSED_HEAD = os.environ.get("MTFJSP_FUSED_HEAD", "1") != "0"
 
 
 def _ptr(t):
@@ -96,6 +102,16 @@ class _GraphMeanFn(torch.autograd.Function):
     def backward(ctx, g):
         inv = torch.tensor(1.0 / ctx.N, dtype=torch.float32).item()
         return (g * inv).unsqueeze(1).expand(-1, ctx.N, -1)
+
+
+def head_tf32(x, cand, B, rows_per_env, nodes_per_env, in_scale, in_shift, Wa, bias_env, W1, b1, w2, b2):
+    """mtfjsp_enc_head_tf32: a whole policy head (gather, BatchNorm + ReLU of the producing layer, Linear, per-env bias,
+    tanh, Linear, tanh, Linear(128, 1)) in one launch -> scores [B, rows_per_env]."""
+    out = torch.empty((B, rows_per_env), dtype=torch.float32, device=x.device)
+    check(_lib.lib().mtfjsp_enc_head_tf32(_ptr(x), _optr(cand), B, rows_per_env, nodes_per_env, _optr(in_scale), _optr(in_shift),
+                                          _ptr(Wa), _ptr(bias_env), bias_env.shape[0], _ptr(W1), _optr(b1), _ptr(w2), _optr(b2),
+                                          _ptr(out), _stream()), "mtfjsp_enc_head_tf32")
+    return out
 
 
 def _graph_mean_raw(h, in_scale=None, in_shift=None, relu=False):
@@ -533,22 +549,31 @@ class _Twin:
         for t, fn in self.__dict__.get("_dcache", {}).values():
             t.copy_(fn())
 
-    def _head_tf32(self, prefix, per_row, env_terms, rows_per_env, in_scale=None, in_shift=None):
+    def _head_tf32(self, prefix, per_row, env_terms, rows_per_env, in_scale=None, in_shift=None, cand=None):
         """First two layers of a 3-layer tanh MLP whose input is cat(per_row [B*r,H], env_term_0 [B,H], env_term_1 [B,H]):
         the per-env blocks of the first weight matrix are applied once per env and added as a bias, the per-row block
         and the second layer run on the tcgen05 kernel -- no [B*r, 3H] concatenation, a third of the GEMM work."""
         w, H = self.w, self.H
         W0 = w[prefix + "linears.0.weight"]
         Wa = self._derived(prefix + "W0a", lambda: W0[:, :H])
-        z = linear_tf32(per_row, Wa, None, in_scale, in_shift, relu=in_scale is not None)
         bias = w[prefix + "linears.0.bias"]
         for k, e in enumerate(env_terms):
             Wk = self._derived(prefix + "W0%d" % (k + 1), lambda k=k: W0[:, (k + 1) * H:(k + 2) * H])
             bias = bias + linear_tf32(e.contiguous(), Wk, None)
-        B = per_row.shape[0] // rows_per_env
-        bias_tanh_(z, (bias if bias.dim() == 2 else bias.unsqueeze(0)).contiguous(), rows_per_env)
-        z = linear_tf32(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"])
+        bias = (bias if bias.dim() == 2 else bias.unsqueeze(0)).contiguous()
         w2 = self._derived(prefix + "w2", lambda: w[prefix + "linears.2.weight"].reshape(-1))
+        if cand is not None:  # per_row = the node embeddings [B, nodes, H]; the kernel gathers the candidate rows itself
+            B, nodes = per_row.shape[0], per_row.shape[1]
+        else:
+            B, nodes = per_row.shape[0] // rows_per_env, 0
+        if _FUSED_HEAD:
+            return head_tf32(per_row, cand, B, rows_per_env, nodes, in_scale, in_shift, Wa, bias,
+                             w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"], w2, w[prefix + "linears.2.bias"])
+        if cand is not None:
+            per_row = torch.gather(per_row, 1, cand.long().unsqueeze(-1).expand(-1, rows_per_env, H)).reshape(-1, H)
+        z = linear_tf32(per_row, Wa, None, in_scale, in_shift, relu=in_scale is not None)
+        bias_tanh_(z, bias, rows_per_env)
+        z = linear_tf32(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"])
         return tanh_dot(z, w2, w[prefix + "linears.2.bias"]).view(B, rows_per_env)
 
 
@@ -594,10 +619,9 @@ class JobActor(_GraphEncoder, _Twin):
         w = self.w
         pooled, nodes = self.encode(task_fea, adj_w, adj_src, groups, adj_dst)
         if self.precision == "tf32":
-            cf = torch.gather(nodes, 1, candidate.long().unsqueeze(-1).expand(-1, self.J, self.H)).reshape(-1, self.H)
             sc, sh = self._pending
             gmv = w["_input"].unsqueeze(0) if h_g_m_pooled is None else h_g_m_pooled
-            s = self._head_tf32("o_policy.", cf, (pooled, gmv), self.J, sc, sh)
+            s = self._head_tf32("o_policy.", nodes, (pooled, gmv), self.J, sc, sh, cand=candidate.to(torch.int32).contiguous())
         elif getattr(self, "train_tf32", False):
             cf = self.candidate_features(nodes, candidate)
             gmv = w["_input"].unsqueeze(0) if h_g_m_pooled is None else h_g_m_pooled

@@ -228,6 +228,18 @@ int mtfjsp_enc_gat_attend_bwd(const float* t, const float* a_src, const float* a
 int mtfjsp_enc_gat_attend_bwd_blocks(int64_t R);
 int mtfjsp_enc_bias_tanh(float* z, const float* bias, int64_t rows, int rows_per_env, int64_t bias_rows, void* stream);
 int mtfjsp_enc_tanh_dot(const float* z, const float* w, const float* b, float* out, int64_t rows, void* stream);
+/* A whole policy head (MLPActor, model/gcn_mlp.py:258-320, on the concatenated features of actor_critic.py:244-268 and
+ * :455-470) in one launch, hidden = 128, both products on tcgen05.mma kind::tf32 with the intermediate kept on the SM:
+ *   out[r] = tanh( tanh( act(X[src(r)]) Wa^T + bias_env[r / rows_per_env] ) W1^T + b1 ) . w2 + b2,   r < B * rows_per_env
+ * src(r) = (r / rows_per_env) * nodes_per_env + cand[r] when cand != NULL (the candidate op of each job gathered from the
+ * node embeddings), else r; act = ReLU(x * in_scale + in_shift) when in_scale != NULL (the producing layer's BatchNorm),
+ * else identity; bias_env [bias_rows,128] with bias_rows = B or 1 = the first layer's bias plus its per-env column blocks
+ * applied to the per-env inputs; b1 / b2 may be NULL.  Replaces torch.gather + mtfjsp_enc_linear_tf32 +
+ * mtfjsp_enc_bias_tanh + mtfjsp_enc_linear_tf32 + mtfjsp_enc_tanh_dot. */
+int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int rows_per_env, int nodes_per_env,
+                         const float* in_scale, const float* in_shift, const float* Wa, const float* bias_env,
+                         int64_t bias_rows, const float* W1, const float* b1, const float* w2, const float* b2, float* out,
+                         void* stream);
 /* replaces: one Linear (+ the BatchNorm statistics pass, + the previous BatchNorm/ReLU apply pass) of
  * gcn_mlp.py:238-249 on the tensor cores (tcgen05.mma kind::tf32, FP32 accumulate in TMEM):
  * Z[rows,128] = act(X[rows,K]*in_scale+in_shift) @ W[128,K]^T + bias; stats[0:128] += column sums of Z,

@@ -137,6 +137,56 @@ def test_tcgen05_linear_matches_fp32_matmul(K, rows, affine):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,rpe,nodes,affine,per_env_bias", [(7, 6, 36, True, True), (1000, 6, 36, True, True),
+                                                            (148 * 128 * 2 // 6 + 3, 6, 0, False, True), (333, 10, 100, True, False),
+                                                            (50, 20, 0, False, False)])
+def test_fused_policy_head_matches_the_separate_launches(B, rpe, nodes, affine, per_env_bias):
+    """mtfjsp_enc_head_tf32 (gather + BatchNorm/ReLU prologue + Linear + per-env bias + tanh + Linear + tanh + dot, one
+    launch, intermediate kept on the SM) against an FP64 evaluation with TF32-rounded GEMM operands (tight) and against
+    plain FP32 (TF32 tolerance)."""
+    torch = pytest.importorskip("torch")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + rpe)
+    H = 128
+    rows = B * rpe
+    if nodes:
+        x = torch.randn(B, nodes, H, device="cuda", generator=g)
+        cand = torch.randint(0, nodes, (B, rpe), device="cuda", generator=g, dtype=torch.int32)
+        per_row = torch.gather(x, 1, cand.long().unsqueeze(-1).expand(-1, rpe, H)).reshape(rows, H)
+    else:
+        x = torch.randn(rows, H, device="cuda", generator=g)
+        cand = None
+        per_row = x
+    sc = sh = None
+    if affine:
+        sc = torch.rand(H, device="cuda", generator=g) + 0.5
+        sh = torch.randn(H, device="cuda", generator=g) * 0.3
+        per_row = torch.relu((per_row.double() * sc.double() + sh.double()).float())
+    Wa = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
+    W1 = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
+    b1 = torch.randn(H, device="cuda", generator=g) * 0.2
+    w2 = torch.randn(H, device="cuda", generator=g) / H ** 0.5
+    b2 = torch.randn(1, device="cuda", generator=g)
+    bias = torch.randn(B if per_env_bias else 1, H, device="cuda", generator=g) * 0.5
+    out = enc.head_tf32(x, cand, B, rpe, nodes, sc, sh, Wa, bias, W1, b1, w2, b2)
+    torch.cuda.synchronize()
+
+    def tf32(t):
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    brow = bias.double().repeat_interleave(rpe, dim=0) if per_env_bias else bias.double()
+
+    def chain(rnd):
+        z = torch.tanh((rnd(per_row).double() @ rnd(Wa).double().T + brow).float())
+        z = torch.tanh((rnd(z).double() @ rnd(W1).double().T + b1.double()).float())
+        return (z.double() @ w2.double() + b2.double()).view(B, rpe)
+
+    np.testing.assert_allclose(out.double().cpu().numpy(), chain(tf32).cpu().numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(out.double().cpu().numpy(), chain(lambda t: t).cpu().numpy(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("K,rows", [(128, 64), (128, 1000), (12, 333), (12, 64 * 200 + 17), (128, 64 * 148 * 3 + 5),
                                     (64, 777), (32, 4096)])
 def test_tcgen05_weight_gradient_matches_fp64_product(K, rows):
