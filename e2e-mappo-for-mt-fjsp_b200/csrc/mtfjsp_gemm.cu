@@ -553,6 +553,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ parts, const float
 // (the first product has finished reading it) as the second product's operand; the second epilogue takes tanh, dots the
 // row with w2 and writes one float per row.  Replaces gather + 2 GEMM launches + bias_tanh + tanh_dot: five passes over
 // [rows,128] tensors become one gathered read.  Both weight matrices stay in shared memory (2 x 64 KB), one CTA per SM.
+// tanh / ELU for operands that are rounded to TF32 next (or summed into a score next to TF32 products): one ex2.approx
+// and one fast division instead of the ~25-instruction accurate routines; absolute error < 3e-7
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float t = __expf(2.f * fminf(x, 44.f));
+    return 1.f - __fdividef(2.f, t + 1.f);
+}
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
 constexpr int HEAD_WARPS = 16;
 
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
@@ -673,8 +681,8 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
             for (int j = 0; j < 8; j++) {
                 const float4 bb = __ldg(bp + j);
                 float4 x;
-                x.x = to_tf32(tanhf(__uint_as_float(r[4 * j]) + bb.x)); x.y = to_tf32(tanhf(__uint_as_float(r[4 * j + 1]) + bb.y));
-                x.z = to_tf32(tanhf(__uint_as_float(r[4 * j + 2]) + bb.z)); x.w = to_tf32(tanhf(__uint_as_float(r[4 * j + 3]) + bb.w));
+                x.x = to_tf32(tanh_fast(__uint_as_float(r[4 * j]) + bb.x)); x.y = to_tf32(tanh_fast(__uint_as_float(r[4 * j + 1]) + bb.y));
+                x.z = to_tf32(tanh_fast(__uint_as_float(r[4 * j + 2]) + bb.z)); x.w = to_tf32(tanh_fast(__uint_as_float(r[4 * j + 3]) + bb.w));
                 if (!rok) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(dst + j * 128) = x;
             }
@@ -694,7 +702,14 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j++) acc = fmaf(tanhf(__uint_as_float(r[j]) + s_b1[cg * 32 + j]), s_w2[cg * 32 + j], acc);
+            for (int j = 0; j < 8; j++) {
+                const float4 bb = *reinterpret_cast<const float4*>(s_b1 + cg * 32 + 4 * j);
+                const float4 ww = *reinterpret_cast<const float4*>(s_w2 + cg * 32 + 4 * j);
+                acc = fmaf(tanh_fast(__uint_as_float(r[4 * j]) + bb.x), ww.x, acc);
+                acc = fmaf(tanh_fast(__uint_as_float(r[4 * j + 1]) + bb.y), ww.y, acc);
+                acc = fmaf(tanh_fast(__uint_as_float(r[4 * j + 2]) + bb.z), ww.z, acc);
+                acc = fmaf(tanh_fast(__uint_as_float(r[4 * j + 3]) + bb.w), ww.w, acc);
+            }
             s_part[cg * 128 + trow] = acc;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -707,6 +722,183 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+}
+
+
+// =====================================================================================================================
+// Machine-node trunk in ONE kernel (model/actor_critic.py:381-420: m_fea_1_fcl, m_fea_2_fcl, three applications of the
+// GAT layer model/gat.py:82-159 on the fixed 2-node graph with ELU between them, mean over the two node sets):
+//     h1 = f1 W1p^T, h2 = f2 W2p^T;   3 x { t = [h1; h2] W;  att = softmax(lrelu(t1.a_src + t1.a_dst), lrelu(t1.a_src + t2.a_dst));
+//                                          h1 = att0 t1 + att1 t2, h2 = t2;  (ELU on both between layers) };   out = (h1 + h2) / 2
+// Nothing couples machines before the BatchNorm that follows, so 64 machines (tile rows 0..63 = their node-1 rows,
+// 64..127 = their node-2 rows) run through all three layers on one SM: the input projections (K = 6 / 8) on the CUDA
+// cores straight into the A operand, each layer's product on `tcgen05.mma` into TMEM, the attention / combination / ELU in
+// the epilogue, written back into the A buffer for the next layer.  Replaces mach_proj + 3 x (GEMM launch + gat_attend):
+// thirteen passes over [2R,128] tensors become one [R,128] write.
+constexpr int TRUNK_WARPS = 16;
+
+__global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk_tf32_kernel(
+    const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ W1p, const float* __restrict__ W2p,
+    const float* __restrict__ Wt, const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out,
+    long long R, long long num_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr size_t WBYTES = (size_t)TILE_N * 128 * 4;
+    float* sW = reinterpret_cast<float*>(smem);
+    float* sA = reinterpret_cast<float*>(smem + WBYTES);
+    float* sT2 = reinterpret_cast<float*>(smem + 2 * WBYTES);           // [64][128] raw t2 rows, 16-byte pieces XOR-swizzled
+    float* s_dot = sT2 + 64 * 128;                                       // [3][4][64]: s1, d1, d2 partials per column group
+    float* s_as = s_dot + 3 * 4 * 64;
+    float* s_ad = s_as + 128;
+    float* s_w1p = s_ad + 128;                                           // [128][6]
+    float* s_w2p = s_w1p + 128 * 6;                                      // [128][8]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w2p + 128 * 8);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 128) { s_as[tid] = a_src[tid]; s_ad[tid] = a_dst[tid]; }
+    for (int i = tid; i < 128 * 6; i += blockDim.x) s_w1p[i] = W1p[i];
+    for (int i = tid; i < 128 * 8; i += blockDim.x) s_w2p[i] = W2p[i];
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    stage_block<false, TRUNK_WARPS>(sW, Wt, 0, TILE_N, 128, 128, 128, nullptr, nullptr, false, warp, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t bar = smem_u32(s_bar);
+
+    const int quad = warp & 3, cg = warp >> 2;   // TMEM lanes 32 quad .., columns 32 cg ..
+    const int trow = quad * 32 + lane;           // tile row of this thread: < 64 node 1, >= 64 node 2
+    const bool node2 = quad >= 2;
+    const int mloc = trow & 63;                  // machine within the tile
+    char* const a_dst_row = reinterpret_cast<char*>(sA) + (trow >> 3) * 4096 + (cg * 8) * 128 + (trow & 7) * 16;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long m = tile * 64 + mloc;
+        const bool mok = m < R;
+        {   // input projections on the CUDA cores, straight into the A operand
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (mok) {
+                if (node2) {
+                    const float4 u0 = __ldg(reinterpret_cast<const float4*>(f2 + m * 8)), u1 = __ldg(reinterpret_cast<const float4*>(f2 + m * 8) + 1);
+                    f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+                } else {
+                    const float2* p2 = reinterpret_cast<const float2*>(f1 + m * 6);
+                    const float2 u0 = __ldg(p2), u1 = __ldg(p2 + 1), u2 = __ldg(p2 + 2);
+                    f[0] = u0.x; f[1] = u0.y; f[2] = u1.x; f[3] = u1.y; f[4] = u2.x; f[5] = u2.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float o[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int col = cg * 32 + j * 4 + c;
+                    float acc;
+                    if (node2) {
+                        const float4 wa = *reinterpret_cast<const float4*>(s_w2p + col * 8), wb = *reinterpret_cast<const float4*>(s_w2p + col * 8 + 4);
+                        acc = fmaf(f[7], wb.w, fmaf(f[6], wb.z, fmaf(f[5], wb.y, fmaf(f[4], wb.x,
+                              fmaf(f[3], wa.w, fmaf(f[2], wa.z, fmaf(f[1], wa.y, f[0] * wa.x)))))));
+                    } else {
+                        const float2 wa = *reinterpret_cast<const float2*>(s_w1p + col * 6), wb = *reinterpret_cast<const float2*>(s_w1p + col * 6 + 2),
+                                     wc = *reinterpret_cast<const float2*>(s_w1p + col * 6 + 4);
+                        acc = fmaf(f[5], wc.y, fmaf(f[4], wc.x, fmaf(f[3], wb.y, fmaf(f[2], wb.x, fmaf(f[1], wa.y, f[0] * wa.x)))));
+                    }
+                    o[c] = to_tf32(acc);
+                }
+                *reinterpret_cast<float4*>(a_dst_row + j * 128) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+#pragma unroll 1
+        for (int layer = 0; layer < 3; layer++) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    umma_tf32(tmem_base, make_desc(aA + k * 256, 128, 4096), make_desc(aW + k * 256, 128, 4096), k > 0 ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[32];
+            TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32), r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // partial dots over this thread's 32 columns; node-2 rows also park their raw values for the node-1 threads
+            float pa = 0.f, pb = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 va = *reinterpret_cast<const float4*>(s_as + cg * 32 + 4 * j), vd = *reinterpret_cast<const float4*>(s_ad + cg * 32 + 4 * j);
+                const float x0 = __uint_as_float(r[4 * j]), x1 = __uint_as_float(r[4 * j + 1]), x2 = __uint_as_float(r[4 * j + 2]),
+                            x3 = __uint_as_float(r[4 * j + 3]);
+                pa = fmaf(x3, va.w, fmaf(x2, va.z, fmaf(x1, va.y, fmaf(x0, va.x, pa))));
+                pb = fmaf(x3, vd.w, fmaf(x2, vd.z, fmaf(x1, vd.y, fmaf(x0, vd.x, pb))));
+            }
+            if (node2) {
+                s_dot[(2 * 4 + cg) * 64 + mloc] = pb;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<uint4*>(sT2 + mloc * 128 + (((cg * 8 + j) ^ (mloc & 7)) << 2)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            } else {
+                s_dot[(0 * 4 + cg) * 64 + mloc] = pa;
+                s_dot[(1 * 4 + cg) * 64 + mloc] = pb;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            float a0 = 0.f, a1 = 1.f;  // node-2 rows: h2' = t2
+            if (!node2) {
+                const float s1 = (s_dot[0 * 64 + mloc] + s_dot[1 * 64 + mloc]) + (s_dot[2 * 64 + mloc] + s_dot[3 * 64 + mloc]);
+                const float d1 = (s_dot[4 * 64 + mloc] + s_dot[5 * 64 + mloc]) + (s_dot[6 * 64 + mloc] + s_dot[7 * 64 + mloc]);
+                const float d2 = (s_dot[8 * 64 + mloc] + s_dot[9 * 64 + mloc]) + (s_dot[10 * 64 + mloc] + s_dot[11 * 64 + mloc]);
+                float e11 = s1 + d1, e12 = s1 + d2;
+                e11 = e11 > 0.f ? e11 : 0.2f * e11;
+                e12 = e12 > 0.f ? e12 : 0.2f * e12;
+                const float mx = fmaxf(e11, e12);
+                const float p1 = expf(e11 - mx), p2 = expf(e12 - mx);
+                a0 = p1 / (p1 + p2); a1 = p2 / (p1 + p2);
+            }
+            if (layer < 2) {  // next layer's operand: elu(h') of every row, back into the A buffer (the product is done with it)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float4 x = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                           __uint_as_float(r[4 * j + 3]));
+                    if (!node2) {
+                        const float4 y = *reinterpret_cast<const float4*>(sT2 + mloc * 128 + (((cg * 8 + j) ^ (mloc & 7)) << 2));
+                        x.x = a0 * x.x + a1 * y.x; x.y = a0 * x.y + a1 * y.y; x.z = a0 * x.z + a1 * y.z; x.w = a0 * x.w + a1 * y.w;
+                    }
+                    x.x = to_tf32(elu_fast(x.x)); x.y = to_tf32(elu_fast(x.y)); x.z = to_tf32(elu_fast(x.z)); x.w = to_tf32(elu_fast(x.w));
+                    *reinterpret_cast<float4*>(a_dst_row + j * 128) = x;
+                }
+            } else if (!node2 && mok) {  // mean over the two node sets
+                float4* op = reinterpret_cast<float4*>(out + m * 128 + cg * 32);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 y = *reinterpret_cast<const float4*>(sT2 + mloc * 128 + (((cg * 8 + j) ^ (mloc & 7)) << 2));
+                    float4 x = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                           __uint_as_float(r[4 * j + 3]));
+                    x.x = 0.5f * ((a0 * x.x + a1 * y.x) + y.x); x.y = 0.5f * ((a0 * x.y + a1 * y.y) + y.y);
+                    x.z = 0.5f * ((a0 * x.z + a1 * y.z) + y.z); x.w = 0.5f * ((a0 * x.w + a1 * y.w) + y.w);
+                    op[j] = x;
+                }
+            }
+        }
+        __syncthreads();  // sT2 / s_dot / the A buffer are rewritten by the next tile
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
 }
 
 }  // namespace
@@ -776,6 +968,25 @@ int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int row
     head_tf32_kernel<<<grid, HEAD_WARPS * 32, smem, (cudaStream_t)stream>>>(X, cand, rows, rows_per_env, nodes_per_env, in_scale,
                                                                           in_shift, Wa, bias_env, bias_rows, W1, b1, w2, b2, out,
                                                                           tiles);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float* W1p, const float* W2p, const float* Wt,
+                              const float* a_src, const float* a_dst, float* out, int64_t R, void* stream) {
+    if (!fea1 || !fea2 || !W1p || !W2p || !Wt || !a_src || !a_dst || !out || R < 1) return MTFJSP_E_ARG;
+    const size_t smem = 2 * (size_t)TILE_N * 128 * 4 + (64 * 128 + 3 * 4 * 64 + 256 + 128 * 14) * 4 + 8 + 16;
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gat_trunk_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MTFJSP_E_CUDA;
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (R + 63) / 64;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gat_trunk_tf32_kernel<<<grid, TRUNK_WARPS * 32, smem, (cudaStream_t)stream>>>(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, out, R, tiles);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 

@@ -32,6 +32,7 @@ from ._lib import check
 # MTFJSP_FUSED_HEAD=0: the policy heads of the rollout path as separate launches (gather, GEMM, bias + tanh, GEMM,
 # tanh + dot) instead of the one-launch head kernel -- kept for A/B measurements
 _FUSED_HEAD = os.environ.get("MTFJSP_FUSED_HEAD", "1") != "0"
+_FUSED_TRUNK = os.environ.get("MTFJSP_FUSED_TRUNK", "1") != "0"  # likewise for the machine-node trunk
 
 
 def _ptr(t):
@@ -111,6 +112,15 @@ def head_tf32(x, cand, B, rows_per_env, nodes_per_env, in_scale, in_shift, Wa, b
     check(_lib.lib().mtfjsp_enc_head_tf32(_ptr(x), _optr(cand), B, rows_per_env, nodes_per_env, _optr(in_scale), _optr(in_shift),
                                           _ptr(Wa), _ptr(bias_env), bias_env.shape[0], _ptr(W1), _optr(b1), _ptr(w2), _optr(b2),
                                           _ptr(out), _stream()), "mtfjsp_enc_head_tf32")
+    return out
+
+
+def gat_trunk_tf32(fea1, fea2, W1p, W2p, Wt, a_src, a_dst):
+    """mtfjsp_enc_gat_trunk_tf32: input projections + three GAT layers + node-set mean in one launch -> [R,128]."""
+    R = fea1.shape[0]
+    out = torch.empty((R, 128), dtype=torch.float32, device=fea1.device)
+    check(_lib.lib().mtfjsp_enc_gat_trunk_tf32(_ptr(fea1), _ptr(fea2), _ptr(W1p), _ptr(W2p), _ptr(Wt), _ptr(a_src), _ptr(a_dst),
+                                               _ptr(out), R, _stream()), "mtfjsp_enc_gat_trunk_tf32")
     return out
 
 
@@ -713,13 +723,16 @@ class _MachineTrunk:
         R = B * self.M
         f1 = machine_fea_1.to(torch.float32).reshape(R, 6).contiguous()
         f2 = machine_fea_2.to(torch.float32).reshape(R, 8).contiguous()
-        buf = mach_proj(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"])
         Wt = self._derived("gat_Wt", lambda: self.w["gat_layer.W"].t())
         a_src = self._derived("gat_a_src", lambda: self.w["gat_layer.a"][0, :H, 0])
         a_dst = self._derived("gat_a_dst", lambda: self.w["gat_layer.a"][0, H:, 0])
-        for layer in range(3):
-            t = linear_tf32(buf, Wt, None)
-            buf = gat_attend(t, a_src, a_dst, 1, out=buf) if layer < 2 else gat_attend(t, a_src, a_dst, 2)
+        if _FUSED_TRUNK:
+            buf = gat_trunk_tf32(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"], Wt, a_src, a_dst)
+        else:
+            buf = mach_proj(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"])
+            for layer in range(3):
+                t = linear_tf32(buf, Wt, None)
+                buf = gat_attend(t, a_src, a_dst, 1, out=buf) if layer < 2 else gat_attend(t, a_src, a_dst, 2)
         nodes = _bn_train(buf, w["bn.weight"], w["bn.bias"], groups=groups).reshape(B, self.M, H)
         return nodes, nodes.mean(dim=1)
 

@@ -219,6 +219,13 @@ int mtfjsp_enc_graph_mean(const float* h, float* out, int64_t B, int N, int C, c
  * tanh_dot    out[r] = tanh(z[r]) . w + b (second tanh and the Linear(128,1) of the same MLP). */
 int mtfjsp_enc_mach_proj(const float* fea1, const float* fea2, const float* W1, const float* W2, float* out, int64_t R,
                          void* stream);
+/* The machine-node trunk up to the mean over the two node sets (actor_critic.py:381-420) in one launch, hidden = 128:
+ * input projections fea1 [R,6] W1p[128,6]^T and fea2 [R,8] W2p[128,8]^T, three GAT layers (projection by Wt = gat_layer.W^T
+ * [128 out,128 in] on tcgen05.mma kind::tf32, attention with a_src / a_dst, ELU between layers) and the node-set mean ->
+ * out [R,128].  64 machines stay on one SM through all three layers; replaces mtfjsp_enc_mach_proj +
+ * 3 x (mtfjsp_enc_linear_tf32 + mtfjsp_enc_gat_attend). */
+int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float* W1p, const float* W2p, const float* Wt,
+                              const float* a_src, const float* a_dst, float* out, int64_t R, void* stream);
 int mtfjsp_enc_gat_attend(const float* t, const float* a_src, const float* a_dst, float* out, int64_t R, int mode,
                           void* stream);
 /* Backward of mtfjsp_enc_gat_attend for the PPO update: g = gradient of its output, dt [2R,128] = gradient of t,

@@ -187,6 +187,53 @@ def test_fused_policy_head_matches_the_separate_launches(B, rpe, nodes, affine, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R", [5, 64, 1000, 64 * 148 * 2 + 17])
+def test_fused_machine_trunk_matches_the_layerwise_path(R):
+    """mtfjsp_enc_gat_trunk_tf32 (input projections + three GAT layers + node-set mean, one launch, 64 machines per SM)
+    against the same chain in FP64 with TF32-rounded GEMM operands (tight), the layer-by-layer kernels (TF32 noise) and
+    plain FP32 (TF32 tolerance over three layers)."""
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(R)
+    H = 128
+    f1 = torch.randn(R, 6, device="cuda", generator=g)
+    f2 = torch.randn(R, 8, device="cuda", generator=g)
+    W1p = torch.randn(H, 6, device="cuda", generator=g) / 6 ** 0.5
+    W2p = torch.randn(H, 8, device="cuda", generator=g) / 8 ** 0.5
+    Wt = (torch.randn(H, H, device="cuda", generator=g) / H ** 0.5).contiguous()
+    a_src = torch.randn(H, device="cuda", generator=g) / H ** 0.5
+    a_dst = torch.randn(H, device="cuda", generator=g) / H ** 0.5
+    out = enc.gat_trunk_tf32(f1, f2, W1p, W2p, Wt, a_src, a_dst)
+    torch.cuda.synchronize()
+
+    def tf32(t):
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def chain(rnd):
+        h1, h2 = F.linear(f1, W1p), F.linear(f2, W2p)
+        for layer in range(3):
+            t1 = (rnd(h1).double() @ rnd(Wt).double().T).float()
+            t2 = (rnd(h2).double() @ rnd(Wt).double().T).float()
+            e11 = F.leaky_relu(t1 @ a_src + t1 @ a_dst, 0.2)
+            e12 = F.leaky_relu(t1 @ a_src + t2 @ a_dst, 0.2)
+            att = torch.softmax(torch.stack((e11, e12), dim=-1), dim=-1)
+            h1, h2 = att[:, 0:1] * t1 + att[:, 1:2] * t2, t2
+            if layer < 2:
+                h1, h2 = F.elu(h1), F.elu(h2)
+        return 0.5 * (h1 + h2)
+
+    np.testing.assert_allclose(out.cpu().numpy(), chain(tf32).cpu().numpy(), rtol=3e-3, atol=3e-3)  # a flipped TF32 rounding = 5e-4
+    np.testing.assert_allclose(out.cpu().numpy(), chain(lambda t: t).cpu().numpy(), rtol=3e-2, atol=3e-2)
+    buf = enc.mach_proj(f1, f2, W1p, W2p)
+    for layer in range(3):
+        t = enc.linear_tf32(buf, Wt, None)
+        buf = enc.gat_attend(t, a_src, a_dst, 1 if layer < 2 else 2)
+    np.testing.assert_allclose(out.cpu().numpy(), buf.cpu().numpy(), rtol=3e-3, atol=3e-3)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("K,rows", [(128, 64), (128, 1000), (12, 333), (12, 64 * 200 + 17), (128, 64 * 148 * 3 + 5),
                                     (64, 777), (32, 4096)])
 def test_tcgen05_weight_gradient_matches_fp64_product(K, rows):
