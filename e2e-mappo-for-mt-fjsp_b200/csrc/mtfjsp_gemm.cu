@@ -14,6 +14,7 @@
 // (M=128, N=128, K=8) accumulating in TMEM, `tcgen05.commit` arrives on an mbarrier, then each warp pulls its
 // 32 TMEM lanes with `tcgen05.ld.32x32b.x32`, adds the bias, transposes through shared memory and writes 128-byte
 // coalesced rows while accumulating the column statistics.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -344,6 +345,226 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_kernel(const f
             }
         }
         if (stats) {  // fold the four row classes, then one atomic per column and warp
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double a = csum[c2][j], b = csq[c2][j];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
+                    if (sub == 0) {
+                        atomicAdd(stats + half * 64 + c2 * 32 + c4 * 4 + j, a);
+                        atomicAdd(stats + TILE_N + half * 64 + c2 * 32 + c4 * 4 + j, b);
+                    }
+                }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K = 128 layers: the same kernel with the A operand brought in by the TMA unit.  `cp.async.bulk.tensor.2d` copies
+// 128-row x 32-column boxes (128 bytes per row) of X into shared memory in the 128-byte-swizzled K-major layout that the
+// MMA descriptor names (LayoutType SWIZZLE_128B: 16-byte piece c of row r sits at r * 128 + ((c ^ (r & 7)) << 4), 8-row
+// groups 1,024 bytes apart), completion counted in bytes on the stage's mbarrier; rows past the end of X arrive as zeros.
+// One thread issues two boxes per 64-column stage instead of 256 threads issuing eight 16-byte cp.async each -- ncu
+// showed the cp.async form asking L2 for 2.9 GB of sectors for 1.2 GB of operand.  The staging warps still pass over the
+// stage once in place (TF32 rounding + the folded BatchNorm / ReLU of the producing layer), each thread on fixed
+// columns, conflict-free in the swizzled layout as well.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;             // LBO: not used by swizzled K-major layouts
+    d |= (uint64_t)(1024 >> 4) << 32;   // SBO: 8 rows x 128 bytes
+    d |= 1ull << 46;                    // descriptor version for sm_100
+    d |= 2ull << 61;                    // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+template <bool AFFINE>
+__device__ __forceinline__ void tile_transform_sw(unsigned char* stage, long long row0, long long rows, int kbase,
+                                                  const float* s_scale, const float* s_shift, bool relu, int pw, int lane) {
+    // stage = two boxes of 128 rows x 128 bytes; this thread owns logical 16-byte piece (q * 4 + c) of rows 8 * grp + r
+    const int r = lane & 7, c = lane >> 3, q = pw & 3;
+    const int piece = q * 4 + c, box = piece >> 3, pb = piece & 7;
+    const int k = kbase + piece * 4;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (AFFINE) { sc = *reinterpret_cast<const float4*>(s_scale + k); sh = *reinterpret_cast<const float4*>(s_shift + k); }
+    unsigned char* const base = stage + box * 16384 + r * 128 + ((pb ^ r) << 4);  // (8 grp + r) & 7 == r
+    float4 x[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) x[u] = *reinterpret_cast<const float4*>(base + ((pw >> 2) + 2 * u) * 1024);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int grp = (pw >> 2) + 2 * u;
+        float4 v = x[u];
+        if (AFFINE) {
+            if (row0 + grp * 8 + r < rows) {
+                v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            }
+        }
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+        *reinterpret_cast<float4*>(base + grp * 1024) = v;
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmapX, long long rows,
+                                                                             const float* __restrict__ W,
+                                                                             const float* __restrict__ bias,
+                                                                             const float* __restrict__ in_scale,
+                                                                             const float* __restrict__ in_shift, int in_relu,
+                                                                             float* __restrict__ Z, double* __restrict__ stats,
+                                                                             long long num_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int KP = 128, KS = 64, SPT = 2;
+    constexpr size_t WBYTES = (size_t)TILE_N * KP * 4, SBYTES = (size_t)TILE_M * KS * 4;
+    float* sW = reinterpret_cast<float*>(smem);
+    unsigned char* sRing = smem + WBYTES;  // 1,024-byte aligned: WBYTES = 64 KB
+    float* sStg = reinterpret_cast<float*>(sRing + NSTAGE * SBYTES);
+    float* s_bias = sStg + NEPI * 32 * STG_W;
+    float* s_scale = s_bias + TILE_N;
+    float* s_shift = s_scale + 128;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2], sfree[NSTAGE], landed[NSTAGE]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 + 2 * NSTAGE);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool affine = in_scale != nullptr;
+    if (tid < TILE_N) s_bias[tid] = bias ? bias[tid] : 0.f;
+    if (tid < 128) {
+        s_scale[tid] = affine ? in_scale[tid] : 1.f;
+        s_shift[tid] = affine ? in_shift[tid] : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar + 0), 1);
+        mbar_init(smem_u32(s_bar + 1), 1);
+        mbar_init(smem_u32(s_bar + 2), NEPI);
+        mbar_init(smem_u32(s_bar + 3), NEPI);
+        for (int st = 0; st < 2 * NSTAGE; st++) mbar_init(smem_u32(s_bar + 4 + st), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapX) : "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    stage_block<false, GEMM_WARPS>(sW, W, 0, TILE_N, KP, KP, KP, nullptr, nullptr, false, warp, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    constexpr uint32_t SBO_W = (uint32_t)(KP / 4) * 128u;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2), bar_free = smem_u32(s_bar + 4);
+    const uint32_t bar_land = smem_u32(s_bar + 4 + NSTAGE);
+
+    if (warp >= NEPI) {
+        // ================= producers =================
+        const int pw = warp - NEPI;
+        const long long my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const long long nst = my_tiles * SPT;  // stages this CTA streams, in order
+        auto issue = [&](long long g) {        // one thread: two boxes of stage g into its ring slot
+            if (g < nst) {
+                const long long tile = blockIdx.x + (g / SPT) * (long long)gridDim.x;
+                const int slot = (int)(g % NSTAGE);
+                const uint32_t dst = smem_u32(sRing + slot * SBYTES), bar = bar_land + slot * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)SBYTES) : "memory");
+                const int col = (int)(g % SPT) * KS, row = (int)(tile * TILE_M);
+                tma_load_2d(dst, &tmapX, col, row, bar);
+                tma_load_2d(dst + 16384, &tmapX, col + 32, row, bar);
+            }
+        };
+        const bool loader = tid == (NEPI + 1) * 32;  // first lane of the second staging warp
+        if (loader)
+            for (int g = 0; g < NSTAGE - 1; g++) issue(g);
+        for (long long g = 0; g < nst; g++) {
+            const long long i = g / SPT, tile = blockIdx.x + i * (long long)gridDim.x;
+            const int h = (int)(g % SPT), slot = (int)(g % NSTAGE), buf = (int)(i & 1);
+            unsigned char* sA = sRing + slot * SBYTES;
+            mbar_wait(bar_land + slot * 8, (uint32_t)((g / NSTAGE) & 1));  // stage g has landed
+            if (affine) tile_transform_sw<true>(sA, tile * TILE_M, rows, h * KS, s_scale, s_shift, in_relu != 0, pw, lane);
+            else tile_transform_sw<false>(sA, tile * TILE_M, rows, h * KS, nullptr, nullptr, false, pw, lane);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+            if (loader) {  // refill the slot stage g-1 used: its MMAs ran while this stage was being transformed
+                if (g >= 1 && g + NSTAGE - 1 < nst)
+                    mbar_wait(bar_free + (uint32_t)((g - 1) % NSTAGE) * 8, (uint32_t)(((g - 1) / NSTAGE) & 1));
+                issue(g + NSTAGE - 1);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");  // the producer warps
+            if (tid == NEPI * 32) {
+                if (h == 0 && i >= 2) mbar_wait(bar_empty + buf * 8, (uint32_t)(((i >> 1) - 1) & 1));  // TMEM[buf] drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aA = smem_u32(sA), aW = smem_u32(sW) + (uint32_t)h * (KS / 8) * 256u;
+#pragma unroll
+                for (int k = 0; k < KS / 8; k++) {  // 8 TF32 = 32 bytes of K inside the 128-byte swizzle row; 4 MMAs per box
+                    umma_tf32(tmem_base + buf * TILE_N, make_desc_sw128(aA + (k >> 2) * 16384 + (k & 3) * 32),
+                              make_desc(aW + k * 256, 128, SBO_W), (h > 0 || k > 0) ? 1u : 0u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_free + slot * 8)
+                             : "memory");
+                if (h == SPT - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_full + buf * 8)
+                                 : "memory");
+            }
+        }
+    } else {
+        // ================= epilogue (as in linear_tf32_kernel) =================
+        float* stg = sStg + warp * 32 * STG_W;
+        const int quad = warp & 3, half = warp >> 2;
+        const int sub = lane >> 3, c4 = lane & 7;
+        double csum[2][4] = {}, csq[2][4] = {};
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c4 * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + half * 64 + 32 + c4 * 4);
+        long long i = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+            const int buf = (int)(i & 1);
+            mbar_wait(bar_full + buf * 8, (uint32_t)((i >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row0 = tile * TILE_M + quad * 32;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++) {
+                const int cc = half * 2 + c2;
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TILE_N + cc * 32);
+                TMEM_LD32(taddr, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c2 == 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) mbar_arrive(bar_empty + buf * 8);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_W + ((j ^ (lane & 7)) << 2)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const float4 bb = c2 == 0 ? b0 : b1;
+                float* zp = Z + (row0 + sub) * TILE_N + cc * 32 + c4 * 4;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool full = row0 + 32 <= rows;
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int rr = it * 4 + sub;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_W + ((c4 ^ (rr & 7)) << 2));
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    if (full || row0 + rr < rows) {
+                        *reinterpret_cast<float4*>(zp + (size_t)it * 4 * TILE_N) = v;
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+                    }
+                }
+                csum[c2][0] += (double)s.x; csum[c2][1] += (double)s.y; csum[c2][2] += (double)s.z; csum[c2][3] += (double)s.w;
+                csq[c2][0] += (double)q.x; csq[c2][1] += (double)q.y; csq[c2][2] += (double)q.z; csq[c2][3] += (double)q.w;
+                __syncwarp();
+            }
+        }
+        if (stats) {
 #pragma unroll
             for (int c2 = 0; c2 < 2; c2++)
 #pragma unroll
@@ -930,6 +1151,53 @@ static int launch_linear(const float* X, int64_t rows, int K, const float* W, co
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 
+// K = 128 through the TMA kernel; returns 1 if launched, 0 if the driver entry point is not available (caller falls back)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static int launch_linear_tma(const float* X, int64_t rows, const float* W, const float* bias, const float* in_scale,
+                             const float* in_shift, int in_relu, float* Z, double* stats, cudaStream_t stream) {
+    static const int enabled = getenv("MTFJSP_GEMM_TMA") ? atoi(getenv("MTFJSP_GEMM_TMA")) : 1;
+    EncodeTiledFn enc = enabled ? encode_tiled_fn() : nullptr;
+    if (!enc || ((uintptr_t)X & 15)) return 0;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t box[2] = {32, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    const size_t smem = (size_t)TILE_N * 128 * 4 + (size_t)NSTAGE * TILE_M * 64 * 4 + (size_t)NEPI * 32 * STG_W * 4 +
+                        (TILE_N + 256) * 4 + (4 + 2 * NSTAGE) * 8 + 16;
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(linear_tf32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MTFJSP_E_CUDA;
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (rows + TILE_M - 1) / TILE_M;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    linear_tf32_tma_kernel<<<grid, GEMM_WARPS * 32, smem, stream>>>(map, rows, W, bias, in_scale, in_shift, in_relu, Z, stats, tiles);
+    return cudaGetLastError() == cudaSuccess ? 1 : MTFJSP_E_CUDA;
+}
+
 extern "C" {
 
 int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
@@ -937,6 +1205,10 @@ int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, 
     if (!X || !W || !Z || rows < 1 || K < 4 || K > 128 || (K % 4) != 0) return MTFJSP_E_ARG;
     if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (K == 128 && rows >= 4096) {  // the big layers: A operand by TMA (falls through when the driver lacks the entry point)
+        const int rc = launch_linear_tma(X, rows, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
+        if (rc != 0) return rc < 0 ? rc : MTFJSP_OK;
+    }
     if (K <= 16) return launch_linear<16>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
     if (K <= 32) return launch_linear<32>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
     if (K <= 64) return launch_linear<64>(X, rows, K, W, bias, in_scale, in_shift, in_relu, Z, stats, s);
