@@ -786,7 +786,7 @@ constexpr int HEAD_WARPS = 16;
 
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
     const float* __restrict__ X, const int32_t* __restrict__ cand, long long rows, int rpe, int nodes_per_env,
-    const float* __restrict__ in_scale, const float* __restrict__ in_shift, const float* __restrict__ Wa,
+    const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu, const float* __restrict__ Wa,
     const float* __restrict__ bias_env, long long bias_rows, const float* __restrict__ W1, const float* __restrict__ b1,
     const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out, long long num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -855,8 +855,9 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_tf32_kernel(
             const int it = warp + u * HEAD_WARPS, grp = it >> 3, q = it & 7, k = q * 16 + c4 * 4;
             float4 x = v[u];
             if (affine && s_row[slot * 128 + grp * 8 + r8] >= 0) {
-                x.x = fmaxf(x.x * s_scale[k] + s_shift[k], 0.f); x.y = fmaxf(x.y * s_scale[k + 1] + s_shift[k + 1], 0.f);
-                x.z = fmaxf(x.z * s_scale[k + 2] + s_shift[k + 2], 0.f); x.w = fmaxf(x.w * s_scale[k + 3] + s_shift[k + 3], 0.f);
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + k), sh = *reinterpret_cast<const float4*>(s_shift + k);
+                x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+                if (in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             }
             x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
             *reinterpret_cast<float4*>(reinterpret_cast<char*>(sA) + grp * 4096 + (q * 4 + c4) * 128 + r8 * 16) = x;
@@ -961,7 +962,7 @@ constexpr int TRUNK_WARPS = 16;
 __global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk_tf32_kernel(
     const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ W1p, const float* __restrict__ W2p,
     const float* __restrict__ Wt, const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out,
-    long long R, long long num_tiles) {
+    double* __restrict__ stats, long long R, long long num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr size_t WBYTES = (size_t)TILE_N * 128 * 4;
     float* sW = reinterpret_cast<float*>(smem);
@@ -1001,6 +1002,7 @@ __global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk_tf32_kernel(
     const int mloc = trow & 63;                  // machine within the tile
     char* const a_dst_row = reinterpret_cast<char*>(sA) + (trow >> 3) * 4096 + (cg * 8) * 128 + (trow & 7) * 16;
     uint32_t phase = 0;
+    double st_sum = 0.0, st_sq = 0.0;  // node-1 threads: column cg * 32 + lane of `out`, for the BatchNorm that follows
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long m = tile * 64 + mloc;
         const bool mok = m < R;
@@ -1102,8 +1104,9 @@ __global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk_tf32_kernel(
                     x.x = to_tf32(elu_fast(x.x)); x.y = to_tf32(elu_fast(x.y)); x.z = to_tf32(elu_fast(x.z)); x.w = to_tf32(elu_fast(x.w));
                     *reinterpret_cast<float4*>(a_dst_row + j * 128) = x;
                 }
-            } else if (!node2 && mok) {  // mean over the two node sets
+            } else if (!node2) {  // mean over the two node sets (warp-uniform branch: the shuffles below need every lane)
                 float4* op = reinterpret_cast<float4*>(out + m * 128 + cg * 32);
+                float o[32];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float4 y = *reinterpret_cast<const float4*>(sT2 + mloc * 128 + (((cg * 8 + j) ^ (mloc & 7)) << 2));
@@ -1111,11 +1114,35 @@ __global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk_tf32_kernel(
                                            __uint_as_float(r[4 * j + 3]));
                     x.x = 0.5f * ((a0 * x.x + a1 * y.x) + y.x); x.y = 0.5f * ((a0 * x.y + a1 * y.y) + y.y);
                     x.z = 0.5f * ((a0 * x.z + a1 * y.z) + y.z); x.w = 0.5f * ((a0 * x.w + a1 * y.w) + y.w);
-                    op[j] = x;
+                    if (mok) op[j] = x;
+                    else x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    o[4 * j] = x.x; o[4 * j + 1] = x.y; o[4 * j + 2] = x.z; o[4 * j + 3] = x.w;
+                }
+                if (stats) {  // column sums over the warp's 32 rows by recursive halving: lane l ends up with column l
+                    float q[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) q[j] = o[j] * o[j];
+#pragma unroll
+                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < n; j++) {
+                            const float so = up ? o[j] : o[j + n], ko = up ? o[j + n] : o[j];
+                            const float sq = up ? q[j] : q[j + n], kq = up ? q[j + n] : q[j];
+                            o[j] = ko + __shfl_xor_sync(0xffffffffu, so, off);
+                            q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
+                        }
+                    }
+                    st_sum += (double)o[0];
+                    st_sq += (double)q[0];
                 }
             }
         }
         __syncthreads();  // sT2 / s_dot / the A buffer are rewritten by the next tile
+    }
+    if (stats && !node2) {
+        atomicAdd(stats + cg * 32 + lane, st_sum);
+        atomicAdd(stats + 128 + cg * 32 + lane, st_sq);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1216,7 +1243,7 @@ int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, 
 }
 
 int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int rows_per_env, int nodes_per_env,
-                         const float* in_scale, const float* in_shift, const float* Wa, const float* bias_env,
+                         const float* in_scale, const float* in_shift, int in_relu, const float* Wa, const float* bias_env,
                          int64_t bias_rows, const float* W1, const float* b1, const float* w2, const float* b2, float* out,
                          void* stream) {
     if (!X || !Wa || !bias_env || !W1 || !w2 || !out || B < 1 || rows_per_env < 1) return MTFJSP_E_ARG;
@@ -1238,13 +1265,13 @@ int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int row
     const long long tiles = (rows + TILE_M - 1) / TILE_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
     head_tf32_kernel<<<grid, HEAD_WARPS * 32, smem, (cudaStream_t)stream>>>(X, cand, rows, rows_per_env, nodes_per_env, in_scale,
-                                                                          in_shift, Wa, bias_env, bias_rows, W1, b1, w2, b2, out,
-                                                                          tiles);
+                                                                          in_shift, in_relu, Wa, bias_env, bias_rows, W1, b1, w2, b2,
+                                                                          out, tiles);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 
 int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float* W1p, const float* W2p, const float* Wt,
-                              const float* a_src, const float* a_dst, float* out, int64_t R, void* stream) {
+                              const float* a_src, const float* a_dst, float* out, double* stats, int64_t R, void* stream) {
     if (!fea1 || !fea2 || !W1p || !W2p || !Wt || !a_src || !a_dst || !out || R < 1) return MTFJSP_E_ARG;
     const size_t smem = 2 * (size_t)TILE_N * 128 * 4 + (64 * 128 + 3 * 4 * 64 + 256 + 128 * 14) * 4 + 8 + 16;
     static thread_local bool configured = false;
@@ -1258,7 +1285,8 @@ int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float*
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (R + 63) / 64;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gat_trunk_tf32_kernel<<<grid, TRUNK_WARPS * 32, smem, (cudaStream_t)stream>>>(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, out, R, tiles);
+    gat_trunk_tf32_kernel<<<grid, TRUNK_WARPS * 32, smem, (cudaStream_t)stream>>>(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, out, stats, R,
+                                                                                tiles);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
 }
 

@@ -105,22 +105,23 @@ class _GraphMeanFn(torch.autograd.Function):
         return (g * inv).unsqueeze(1).expand(-1, ctx.N, -1)
 
 
-def head_tf32(x, cand, B, rows_per_env, nodes_per_env, in_scale, in_shift, Wa, bias_env, W1, b1, w2, b2):
+def head_tf32(x, cand, B, rows_per_env, nodes_per_env, in_scale, in_shift, Wa, bias_env, W1, b1, w2, b2, relu=True):
     """mtfjsp_enc_head_tf32: a whole policy head (gather, BatchNorm + ReLU of the producing layer, Linear, per-env bias,
     tanh, Linear, tanh, Linear(128, 1)) in one launch -> scores [B, rows_per_env]."""
     out = torch.empty((B, rows_per_env), dtype=torch.float32, device=x.device)
     check(_lib.lib().mtfjsp_enc_head_tf32(_ptr(x), _optr(cand), B, rows_per_env, nodes_per_env, _optr(in_scale), _optr(in_shift),
-                                          _ptr(Wa), _ptr(bias_env), bias_env.shape[0], _ptr(W1), _optr(b1), _ptr(w2), _optr(b2),
+                                          1 if relu else 0, _ptr(Wa), _ptr(bias_env), bias_env.shape[0], _ptr(W1), _optr(b1), _ptr(w2), _optr(b2),
                                           _ptr(out), _stream()), "mtfjsp_enc_head_tf32")
     return out
 
 
-def gat_trunk_tf32(fea1, fea2, W1p, W2p, Wt, a_src, a_dst):
-    """mtfjsp_enc_gat_trunk_tf32: input projections + three GAT layers + node-set mean in one launch -> [R,128]."""
+def gat_trunk_tf32(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, stats=None):
+    """mtfjsp_enc_gat_trunk_tf32: input projections + three GAT layers + node-set mean in one launch -> [R,128];
+    stats [256] f64 (optional) receives the column sums of the result and of its squares."""
     R = fea1.shape[0]
     out = torch.empty((R, 128), dtype=torch.float32, device=fea1.device)
     check(_lib.lib().mtfjsp_enc_gat_trunk_tf32(_ptr(fea1), _ptr(fea2), _ptr(W1p), _ptr(W2p), _ptr(Wt), _ptr(a_src), _ptr(a_dst),
-                                               _ptr(out), R, _stream()), "mtfjsp_enc_gat_trunk_tf32")
+                                               _ptr(out), _optr(stats), R, _stream()), "mtfjsp_enc_gat_trunk_tf32")
     return out
 
 
@@ -559,7 +560,7 @@ class _Twin:
         for t, fn in self.__dict__.get("_dcache", {}).values():
             t.copy_(fn())
 
-    def _head_tf32(self, prefix, per_row, env_terms, rows_per_env, in_scale=None, in_shift=None, cand=None):
+    def _head_tf32(self, prefix, per_row, env_terms, rows_per_env, in_scale=None, in_shift=None, cand=None, relu=True):
         """First two layers of a 3-layer tanh MLP whose input is cat(per_row [B*r,H], env_term_0 [B,H], env_term_1 [B,H]):
         the per-env blocks of the first weight matrix are applied once per env and added as a bias, the per-row block
         and the second layer run on the tcgen05 kernel -- no [B*r, 3H] concatenation, a third of the GEMM work."""
@@ -578,10 +579,10 @@ class _Twin:
             B, nodes = per_row.shape[0] // rows_per_env, 0
         if _FUSED_HEAD:
             return head_tf32(per_row, cand, B, rows_per_env, nodes, in_scale, in_shift, Wa, bias,
-                             w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"], w2, w[prefix + "linears.2.bias"])
+                             w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"], w2, w[prefix + "linears.2.bias"], relu=relu)
         if cand is not None:
             per_row = torch.gather(per_row, 1, cand.long().unsqueeze(-1).expand(-1, rows_per_env, H)).reshape(-1, H)
-        z = linear_tf32(per_row, Wa, None, in_scale, in_shift, relu=in_scale is not None)
+        z = linear_tf32(per_row, Wa, None, in_scale, in_shift, relu=relu and in_scale is not None)
         bias_tanh_(z, bias, rows_per_env)
         z = linear_tf32(z, w[prefix + "linears.1.weight"], w[prefix + "linears.1.bias"])
         return tanh_dot(z, w2, w[prefix + "linears.2.bias"]).view(B, rows_per_env)
@@ -726,6 +727,15 @@ class _MachineTrunk:
         Wt = self._derived("gat_Wt", lambda: self.w["gat_layer.W"].t())
         a_src = self._derived("gat_a_src", lambda: self.w["gat_layer.a"][0, :H, 0])
         a_dst = self._derived("gat_a_dst", lambda: self.w["gat_layer.a"][0, H:, 0])
+        self._pending_m = None
+        if _FUSED_TRUNK and groups == 1:
+            # the trunk kernel leaves the BatchNorm statistics behind; the normalisation itself is applied by the consumers
+            # (the policy head's prologue; the mean over machines commutes with the per-column affine)
+            stats = torch.zeros(256, dtype=torch.float64, device=f1.device)
+            buf = gat_trunk_tf32(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"], Wt, a_src, a_dst, stats)
+            sc, sh = bn_finalize(stats, R, w["bn.weight"], w["bn.bias"])
+            self._pending_m = (sc, sh)
+            return buf.view(B, self.M, H), buf.view(B, self.M, H).mean(dim=1) * sc + sh
         if _FUSED_TRUNK:
             buf = gat_trunk_tf32(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"], Wt, a_src, a_dst)
         else:
@@ -757,7 +767,8 @@ class MachineActor(_MachineTrunk, _Twin):
         w = self.w
         B = nodes.shape[0]
         if self.precision == "tf32":
-            s = self._head_tf32("m_policy.", nodes.reshape(-1, self.H), (pooled, h_pooled_o), self.M) * 10
+            sc, sh = self.__dict__.get("_pending_m") or (None, None)  # BatchNorm left to this consumer by _trunk_tf32
+            s = self._head_tf32("m_policy.", nodes.reshape(-1, self.H), (pooled, h_pooled_o), self.M, sc, sh, relu=False) * 10
         elif getattr(self, "train_tf32", False):
             s = _head_train(self, "m_policy.", nodes.reshape(-1, self.H), (pooled, h_pooled_o), self.M) * 10
         else:

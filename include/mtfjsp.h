@@ -222,10 +222,11 @@ int mtfjsp_enc_mach_proj(const float* fea1, const float* fea2, const float* W1, 
 /* The machine-node trunk up to the mean over the two node sets (actor_critic.py:381-420) in one launch, hidden = 128:
  * input projections fea1 [R,6] W1p[128,6]^T and fea2 [R,8] W2p[128,8]^T, three GAT layers (projection by Wt = gat_layer.W^T
  * [128 out,128 in] on tcgen05.mma kind::tf32, attention with a_src / a_dst, ELU between layers) and the node-set mean ->
- * out [R,128].  64 machines stay on one SM through all three layers; replaces mtfjsp_enc_mach_proj +
- * 3 x (mtfjsp_enc_linear_tf32 + mtfjsp_enc_gat_attend). */
+ * out [R,128]; stats (may be NULL) [256] f64 += column sums of out and of out^2 for the BatchNorm that follows
+ * (actor_critic.py:434; mtfjsp_enc_bn_finalize turns them into the affine its consumers apply).  64 machines stay on one
+ * SM through all three layers; replaces mtfjsp_enc_mach_proj + 3 x (mtfjsp_enc_linear_tf32 + mtfjsp_enc_gat_attend). */
 int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float* W1p, const float* W2p, const float* Wt,
-                              const float* a_src, const float* a_dst, float* out, int64_t R, void* stream);
+                              const float* a_src, const float* a_dst, float* out, double* stats, int64_t R, void* stream);
 int mtfjsp_enc_gat_attend(const float* t, const float* a_src, const float* a_dst, float* out, int64_t R, int mode,
                           void* stream);
 /* Backward of mtfjsp_enc_gat_attend for the PPO update: g = gradient of its output, dt [2R,128] = gradient of t,
@@ -239,12 +240,12 @@ int mtfjsp_enc_tanh_dot(const float* z, const float* w, const float* b, float* o
  * :455-470) in one launch, hidden = 128, both products on tcgen05.mma kind::tf32 with the intermediate kept on the SM:
  *   out[r] = tanh( tanh( act(X[src(r)]) Wa^T + bias_env[r / rows_per_env] ) W1^T + b1 ) . w2 + b2,   r < B * rows_per_env
  * src(r) = (r / rows_per_env) * nodes_per_env + cand[r] when cand != NULL (the candidate op of each job gathered from the
- * node embeddings), else r; act = ReLU(x * in_scale + in_shift) when in_scale != NULL (the producing layer's BatchNorm),
- * else identity; bias_env [bias_rows,128] with bias_rows = B or 1 = the first layer's bias plus its per-env column blocks
+ * node embeddings), else r; act = x * in_scale + in_shift (then ReLU if in_relu) when in_scale != NULL (the producing
+ * layer's BatchNorm), else identity; bias_env [bias_rows,128] with bias_rows = B or 1 = the first layer's bias plus its per-env column blocks
  * applied to the per-env inputs; b1 / b2 may be NULL.  Replaces torch.gather + mtfjsp_enc_linear_tf32 +
  * mtfjsp_enc_bias_tanh + mtfjsp_enc_linear_tf32 + mtfjsp_enc_tanh_dot. */
 int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int rows_per_env, int nodes_per_env,
-                         const float* in_scale, const float* in_shift, const float* Wa, const float* bias_env,
+                         const float* in_scale, const float* in_shift, int in_relu, const float* Wa, const float* bias_env,
                          int64_t bias_rows, const float* W1, const float* b1, const float* w2, const float* b2, float* out,
                          void* stream);
 /* replaces: one Linear (+ the BatchNorm statistics pass, + the previous BatchNorm/ReLU apply pass) of

@@ -139,7 +139,7 @@ def test_tcgen05_linear_matches_fp32_matmul(K, rows, affine):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,rpe,nodes,affine,per_env_bias", [(7, 6, 36, True, True), (1000, 6, 36, True, True),
                                                             (148 * 128 * 2 // 6 + 3, 6, 0, False, True), (333, 10, 100, True, False),
-                                                            (50, 20, 0, False, False)])
+                                                            (50, 20, 0, False, False), (500, 6, 0, "norelu", True)])
 def test_fused_policy_head_matches_the_separate_launches(B, rpe, nodes, affine, per_env_bias):
     """mtfjsp_enc_head_tf32 (gather + BatchNorm/ReLU prologue + Linear + per-env bias + tanh + Linear + tanh + dot, one
     launch, intermediate kept on the SM) against an FP64 evaluation with TF32-rounded GEMM operands (tight) and against
@@ -161,14 +161,16 @@ def test_fused_policy_head_matches_the_separate_launches(B, rpe, nodes, affine, 
     if affine:
         sc = torch.rand(H, device="cuda", generator=g) + 0.5
         sh = torch.randn(H, device="cuda", generator=g) * 0.3
-        per_row = torch.relu((per_row.double() * sc.double() + sh.double()).float())
+        per_row = (per_row.double() * sc.double() + sh.double()).float()
+        if affine != "norelu":
+            per_row = torch.relu(per_row)
     Wa = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
     W1 = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
     b1 = torch.randn(H, device="cuda", generator=g) * 0.2
     w2 = torch.randn(H, device="cuda", generator=g) / H ** 0.5
     b2 = torch.randn(1, device="cuda", generator=g)
     bias = torch.randn(B if per_env_bias else 1, H, device="cuda", generator=g) * 0.5
-    out = enc.head_tf32(x, cand, B, rpe, nodes, sc, sh, Wa, bias, W1, b1, w2, b2)
+    out = enc.head_tf32(x, cand, B, rpe, nodes, sc, sh, Wa, bias, W1, b1, w2, b2, relu=affine != "norelu")
     torch.cuda.synchronize()
 
     def tf32(t):
@@ -204,8 +206,11 @@ def test_fused_machine_trunk_matches_the_layerwise_path(R):
     Wt = (torch.randn(H, H, device="cuda", generator=g) / H ** 0.5).contiguous()
     a_src = torch.randn(H, device="cuda", generator=g) / H ** 0.5
     a_dst = torch.randn(H, device="cuda", generator=g) / H ** 0.5
-    out = enc.gat_trunk_tf32(f1, f2, W1p, W2p, Wt, a_src, a_dst)
+    stats = torch.zeros(256, dtype=torch.float64, device="cuda")
+    out = enc.gat_trunk_tf32(f1, f2, W1p, W2p, Wt, a_src, a_dst, stats)
     torch.cuda.synchronize()
+    np.testing.assert_allclose(stats[:128].cpu().numpy(), out.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[128:].cpu().numpy(), (out.double() ** 2).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
 
     def tf32(t):
         i = t.contiguous().view(torch.int32)
