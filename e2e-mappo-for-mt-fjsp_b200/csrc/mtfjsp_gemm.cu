@@ -416,24 +416,38 @@ __device__ __forceinline__ void tile_transform_sw(unsigned char* stage, long lon
     }
 }
 
+// AGG: the layer that follows a neighbourhood aggregation (model/gcn_mlp.py:125-149 then :238-249).  The aggregation is
+// linear, so it commutes with the product: the rows go through the MMA one by one and the <= 3-term weighted mean over
+// (self, job predecessor, machine predecessor) is formed from the PRODUCT rows in the epilogue, where the tile passes
+// through shared memory anyway -- out[r] = (y[r] + w_job y[r-1] + w_mach y[src]) / n + bias, y = act(X) W^T.  Tiles hold
+// whole envs (rpt = (128 / N) * N rows; the TMA box is rpt rows, the rest of the stage is ignored) so that every
+// neighbour is in the tile; the separate aggregation pass (one read and one write of [rows,128]) disappears.
+template <bool AGG>
 __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmapX, long long rows,
                                                                              const float* __restrict__ W,
                                                                              const float* __restrict__ bias,
                                                                              const float* __restrict__ in_scale,
                                                                              const float* __restrict__ in_shift, int in_relu,
                                                                              float* __restrict__ Z, double* __restrict__ stats,
-                                                                             long long num_tiles) {
+                                                                             long long num_tiles, int rpt, int nodes,
+                                                                             const float2* __restrict__ adj_w,
+                                                                             const int16_t* __restrict__ adj_src) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int KP = 128, KS = 64, SPT = 2;
+    constexpr int NST = AGG ? 3 : NSTAGE;  // the full-tile epilogue buffer of AGG takes one stage's room
     constexpr size_t WBYTES = (size_t)TILE_N * KP * 4, SBYTES = (size_t)TILE_M * KS * 4;
+    constexpr size_t STG_FLOATS = AGG ? (size_t)TILE_M * TILE_N : (size_t)NEPI * 32 * STG_W;
     float* sW = reinterpret_cast<float*>(smem);
     unsigned char* sRing = smem + WBYTES;  // 1,024-byte aligned: WBYTES = 64 KB
-    float* sStg = reinterpret_cast<float*>(sRing + NSTAGE * SBYTES);
-    float* s_bias = sStg + NEPI * 32 * STG_W;
+    float* sStg = reinterpret_cast<float*>(sRing + NST * SBYTES);
+    float* s_bias = sStg + STG_FLOATS;
     float* s_scale = s_bias + TILE_N;
     float* s_shift = s_scale + 128;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2], sfree[NSTAGE], landed[NSTAGE]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 + 2 * NSTAGE);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_shift + 128);  // full[2], tmem_empty[2], sfree[NST], landed[NST]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 + 2 * NST);
+    float2* s_adjw = reinterpret_cast<float2*>(s_tmem + 4);        // AGG: [128] (w_job, w_mach) of the tile's rows
+    int16_t* s_adjs = reinterpret_cast<int16_t*>(s_adjw + 128);    //      [128] tile row of the machine predecessor, -1 = none
+    const int tile_rows = AGG ? rpt : TILE_M;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool affine = in_scale != nullptr;
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
         mbar_init(smem_u32(s_bar + 1), 1);
         mbar_init(smem_u32(s_bar + 2), NEPI);
         mbar_init(smem_u32(s_bar + 3), NEPI);
-        for (int st = 0; st < 2 * NSTAGE; st++) mbar_init(smem_u32(s_bar + 4 + st), 1);
+        for (int st = 0; st < 2 * NST; st++) mbar_init(smem_u32(s_bar + 4 + st), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapX) : "memory");
     }
@@ -463,7 +477,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
     const uint32_t tmem_base = *s_tmem;
     constexpr uint32_t SBO_W = (uint32_t)(KP / 4) * 128u;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 2), bar_free = smem_u32(s_bar + 4);
-    const uint32_t bar_land = smem_u32(s_bar + 4 + NSTAGE);
+    const uint32_t bar_land = smem_u32(s_bar + 4 + NST);
 
     if (warp >= NEPI) {
         // ================= producers =================
@@ -473,29 +487,29 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
         auto issue = [&](long long g) {        // one thread: two boxes of stage g into its ring slot
             if (g < nst) {
                 const long long tile = blockIdx.x + (g / SPT) * (long long)gridDim.x;
-                const int slot = (int)(g % NSTAGE);
+                const int slot = (int)(g % NST);
                 const uint32_t dst = smem_u32(sRing + slot * SBYTES), bar = bar_land + slot * 8;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)SBYTES) : "memory");
-                const int col = (int)(g % SPT) * KS, row = (int)(tile * TILE_M);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(tile_rows * 256)) : "memory");
+                const int col = (int)(g % SPT) * KS, row = (int)(tile * tile_rows);
                 tma_load_2d(dst, &tmapX, col, row, bar);
                 tma_load_2d(dst + 16384, &tmapX, col + 32, row, bar);
             }
         };
         const bool loader = tid == (NEPI + 1) * 32;  // first lane of the second staging warp
         if (loader)
-            for (int g = 0; g < NSTAGE - 1; g++) issue(g);
+            for (int g = 0; g < NST - 1; g++) issue(g);
         for (long long g = 0; g < nst; g++) {
             const long long i = g / SPT, tile = blockIdx.x + i * (long long)gridDim.x;
-            const int h = (int)(g % SPT), slot = (int)(g % NSTAGE), buf = (int)(i & 1);
+            const int h = (int)(g % SPT), slot = (int)(g % NST), buf = (int)(i & 1);
             unsigned char* sA = sRing + slot * SBYTES;
-            mbar_wait(bar_land + slot * 8, (uint32_t)((g / NSTAGE) & 1));  // stage g has landed
-            if (affine) tile_transform_sw<true>(sA, tile * TILE_M, rows, h * KS, s_scale, s_shift, in_relu != 0, pw, lane);
-            else tile_transform_sw<false>(sA, tile * TILE_M, rows, h * KS, nullptr, nullptr, false, pw, lane);
+            mbar_wait(bar_land + slot * 8, (uint32_t)((g / NST) & 1));  // stage g has landed
+            if (affine) tile_transform_sw<true>(sA, tile * tile_rows, rows, h * KS, s_scale, s_shift, in_relu != 0, pw, lane);
+            else tile_transform_sw<false>(sA, tile * tile_rows, rows, h * KS, nullptr, nullptr, false, pw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
             if (loader) {  // refill the slot stage g-1 used: its MMAs ran while this stage was being transformed
-                if (g >= 1 && g + NSTAGE - 1 < nst)
-                    mbar_wait(bar_free + (uint32_t)((g - 1) % NSTAGE) * 8, (uint32_t)(((g - 1) / NSTAGE) & 1));
-                issue(g + NSTAGE - 1);
+                if (g >= 1 && g + NST - 1 < nst)
+                    mbar_wait(bar_free + (uint32_t)((g - 1) % NST) * 8, (uint32_t)(((g - 1) / NST) & 1));
+                issue(g + NST - 1);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");  // the producer warps
             if (tid == NEPI * 32) {
@@ -515,7 +529,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
             }
         }
     } else {
-        // ================= epilogue (as in linear_tf32_kernel) =================
+        // ================= epilogue =================
         float* stg = sStg + warp * 32 * STG_W;
         const int quad = warp & 3, half = warp >> 2;
         const int sub = lane >> 3, c4 = lane & 7;
@@ -525,6 +539,88 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
         long long i = 0;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
             const int buf = (int)(i & 1);
+            if constexpr (AGG) {
+                // the tile's adjacency rows, fetched while the products are still being formed
+                const int tr = tid;  // 256 epilogue threads, 128 tile rows
+                float2 aw = make_float2(0.f, 0.f);
+                int as = -1;
+                const long long gr = tile * rpt + tr;
+                if (tr < rpt && gr < rows) {
+                    aw = __ldg(adj_w + gr);
+                    const int sr = __ldg(adj_src + gr);
+                    as = sr >= 0 ? (tr / nodes) * nodes + sr : -1;
+                }
+                mbar_wait(bar_full + buf * 8, (uint32_t)((i >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");  // the previous tile's rows have been read
+                if (tr < TILE_M) { s_adjw[tr] = aw; s_adjs[tr] = (int16_t)as; }
+                // product rows -> the full-tile buffer (16-byte pieces XOR-swizzled by row within each 128-byte group)
+                const int yrow = quad * 32 + lane;
+#pragma unroll
+                for (int c2 = 0; c2 < 2; c2++) {
+                    uint32_t r[32];
+                    TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TILE_N + half * 64 + c2 * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<uint4*>(sStg + yrow * TILE_N + (((half * 16 + c2 * 8 + j) ^ (yrow & 7)) << 2)) =
+                            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) mbar_arrive(bar_empty + buf * 8);  // TMEM[buf] may be overwritten
+                asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");  // every product row of the tile is in place
+                const int rbase = quad * 32;
+                // this lane's eight rows: weights, predecessor rows and the scale of the mean, once for both column chunks
+                float wj[8], wm[8], half_or_one[8];
+                int prow[8];  // tile row of the machine predecessor | third << 16 | valid << 17
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int tr2 = rbase + it * 4 + sub;
+                    const bool ok = tr2 < rpt && tile * rpt + tr2 < rows;
+                    const float2 w = s_adjw[tr2];
+                    const int sr = s_adjs[tr2];
+                    const bool hj = w.x != 0.f, hm = sr >= 0;
+                    wj[it] = w.x;              // 0 without a job predecessor: the row read below is then multiplied away ...
+                    wm[it] = hm ? w.y : 0.f;   // ... and row tr2 itself stands in for a missing machine predecessor
+                    const int n = 1 + (hj ? 1 : 0) + (hm ? 1 : 0);
+                    half_or_one[it] = n == 2 ? 0.5f : 1.f;
+                    prow[it] = (hm ? sr : tr2) | (n == 3 ? 1 << 16 : 0) | (ok ? 1 << 17 : 0);
+                }
+#pragma unroll
+                for (int c2 = 0; c2 < 2; c2++) {
+                    const int piece = half * 16 + c2 * 8 + c4;  // 16-byte piece of the row this lane combines
+                    const float4 bb = c2 == 0 ? b0 : b1;
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int tr2 = rbase + it * 4 + sub;
+                        const int sr = prow[it] & 0xffff, jr = tr2 > 0 ? tr2 - 1 : 0;
+                        const float4 xs = *reinterpret_cast<const float4*>(sStg + tr2 * TILE_N + ((piece ^ (tr2 & 7)) << 2));
+                        const float4 xj = *reinterpret_cast<const float4*>(sStg + jr * TILE_N + ((piece ^ (jr & 7)) << 2));
+                        const float4 xm = *reinterpret_cast<const float4*>(sStg + sr * TILE_N + ((piece ^ (sr & 7)) << 2));
+                        float4 v;
+                        v.x = fmaf(wm[it], xm.x, fmaf(wj[it], xj.x, xs.x)); v.y = fmaf(wm[it], xm.y, fmaf(wj[it], xj.y, xs.y));
+                        v.z = fmaf(wm[it], xm.z, fmaf(wj[it], xj.z, xs.z)); v.w = fmaf(wm[it], xm.w, fmaf(wj[it], xj.w, xs.w));
+                        if (prow[it] & (1 << 16)) {  // / 3, correctly rounded: one residual step on the reciprocal product
+                            const float t = 0.333333343f;
+                            float qx = v.x * t, qy = v.y * t, qz = v.z * t, qw = v.w * t;
+                            v.x = fmaf(fmaf(-3.f, qx, v.x), t, qx); v.y = fmaf(fmaf(-3.f, qy, v.y), t, qy);
+                            v.z = fmaf(fmaf(-3.f, qz, v.z), t, qz); v.w = fmaf(fmaf(-3.f, qw, v.w), t, qw);
+                        } else {
+                            v.x *= half_or_one[it]; v.y *= half_or_one[it]; v.z *= half_or_one[it]; v.w *= half_or_one[it];
+                        }
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        if (prow[it] & (1 << 17)) {
+                            *reinterpret_cast<float4*>(Z + (tile * rpt + tr2) * TILE_N + piece * 4) = v;
+                            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                            q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+                        }
+                    }
+                    csum[c2][0] += (double)s.x; csum[c2][1] += (double)s.y; csum[c2][2] += (double)s.z; csum[c2][3] += (double)s.w;
+                    csq[c2][0] += (double)q.x; csq[c2][1] += (double)q.y; csq[c2][2] += (double)q.z; csq[c2][3] += (double)q.w;
+                }
+                continue;
+            }
             mbar_wait(bar_full + buf * 8, (uint32_t)((i >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long row0 = tile * TILE_M + quad * 32;
@@ -1209,10 +1305,10 @@ static int launch_linear_tma(const float* X, int64_t rows, const float* W, const
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 0;
     const size_t smem = (size_t)TILE_N * 128 * 4 + (size_t)NSTAGE * TILE_M * 64 * 4 + (size_t)NEPI * 32 * STG_W * 4 +
-                        (TILE_N + 256) * 4 + (4 + 2 * NSTAGE) * 8 + 16;
+                        (TILE_N + 256) * 4 + (4 + 2 * NSTAGE) * 8 + 16 + 128 * 10;
     static thread_local bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(linear_tf32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(linear_tf32_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return MTFJSP_E_CUDA;
         configured = true;
     }
@@ -1221,7 +1317,43 @@ static int launch_linear_tma(const float* X, int64_t rows, const float* W, const
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (rows + TILE_M - 1) / TILE_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    linear_tf32_tma_kernel<<<grid, GEMM_WARPS * 32, smem, stream>>>(map, rows, W, bias, in_scale, in_shift, in_relu, Z, stats, tiles);
+    linear_tf32_tma_kernel<false><<<grid, GEMM_WARPS * 32, smem, stream>>>(map, rows, W, bias, in_scale, in_shift, in_relu, Z, stats, tiles,
+                                                                         TILE_M, 0, nullptr, nullptr);
+    return cudaGetLastError() == cudaSuccess ? 1 : MTFJSP_E_CUDA;
+}
+
+// aggregation + layer in one launch (K = 128, N <= 128 nodes per env); 1 launched, 0 not available, < 0 error
+static int launch_linear_tma_agg(const float* X, int64_t B, int N, const float* adj_w, const int16_t* adj_src, const float* W,
+                                 const float* bias, const float* in_scale, const float* in_shift, int in_relu, float* Z,
+                                 double* stats, cudaStream_t stream) {
+    static const int enabled = getenv("MTFJSP_GEMM_TMA") ? atoi(getenv("MTFJSP_GEMM_TMA")) : 1;
+    EncodeTiledFn enc = enabled ? encode_tiled_fn() : nullptr;
+    if (!enc || ((uintptr_t)X & 15) || N > TILE_M) return 0;
+    const int rpt = (TILE_M / N) * N;
+    const long long rows = (long long)B * N;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t box[2] = {32, (cuuint32_t)rpt};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    const size_t smem = (size_t)TILE_N * 128 * 4 + (size_t)3 * TILE_M * 64 * 4 + (size_t)TILE_M * TILE_N * 4 + (TILE_N + 256) * 4 +
+                        (4 + 2 * 3) * 8 + 16 + 128 * 10;
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(linear_tf32_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return MTFJSP_E_CUDA;
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (rows + rpt - 1) / rpt;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    linear_tf32_tma_kernel<true><<<grid, GEMM_WARPS * 32, smem, stream>>>(map, rows, W, bias, in_scale, in_shift, in_relu, Z, stats, tiles, rpt,
+                                                                        N, reinterpret_cast<const float2*>(adj_w), adj_src);
     return cudaGetLastError() == cudaSuccess ? 1 : MTFJSP_E_CUDA;
 }
 
@@ -1288,6 +1420,16 @@ int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float*
     gat_trunk_tf32_kernel<<<grid, TRUNK_WARPS * 32, smem, (cudaStream_t)stream>>>(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, out, stats, R,
                                                                                 tiles);
     return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
+
+int mtfjsp_enc_aggregate_linear_tf32(const float* X, int64_t B, int N, const float* adj_w, const int16_t* adj_src, const float* W,
+                                     const float* bias, const float* in_scale, const float* in_shift, int in_relu, float* Z,
+                                     double* stats, void* stream) {
+    if (!X || !adj_w || !adj_src || !W || !Z || B < 1 || N < 1) return MTFJSP_E_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return MTFJSP_E_ARG;
+    const int rc = launch_linear_tma_agg(X, B, N, adj_w, adj_src, W, bias, in_scale, in_shift, in_relu, Z, stats, (cudaStream_t)stream);
+    if (rc == 0) return MTFJSP_E_STATE;  // not available for this size / driver: the caller runs the two kernels
+    return rc < 0 ? rc : MTFJSP_OK;
 }
 
 int mtfjsp_enc_bn_finalize(const double* stats, int64_t rows, const float* gamma, const float* beta, float eps,

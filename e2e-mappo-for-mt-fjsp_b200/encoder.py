@@ -33,6 +33,7 @@ from ._lib import check
 # tanh + dot) instead of the one-launch head kernel -- kept for A/B measurements
 _FUSED_HEAD = os.environ.get("MTFJSP_FUSED_HEAD", "1") != "0"
 _FUSED_TRUNK = os.environ.get("MTFJSP_FUSED_TRUNK", "1") != "0"  # likewise for the machine-node trunk
+_FUSED_AGG = os.environ.get("MTFJSP_FUSED_AGG", "1") != "0"      # likewise aggregation + first layer of a GIN MLP
 
 
 def _ptr(t):
@@ -103,6 +104,23 @@ class _GraphMeanFn(torch.autograd.Function):
     def backward(ctx, g):
         inv = torch.tensor(1.0 / ctx.N, dtype=torch.float32).item()
         return (g * inv).unsqueeze(1).expand(-1, ctx.N, -1)
+
+
+def aggregate_linear_tf32(h, adj_w, adj_src, weight, bias, in_scale=None, in_shift=None, relu=False, stats=None):
+    """mtfjsp_enc_aggregate_linear_tf32: aggregate(h) followed by the layer's product, in one launch (the weighted
+    neighbourhood mean is applied to the product rows in the epilogue).  h [B,N,128] -> [B*N,128], or None when this
+    form is not available for the size (the caller then runs aggregate + linear_tf32)."""
+    B, N = h.shape[0], h.shape[1]
+    if N > 128 or h.shape[2] != 128 or not _FUSED_AGG:
+        return None
+    z = torch.empty((B * N, 128), dtype=torch.float32, device=h.device)
+    rc = _lib.lib().mtfjsp_enc_aggregate_linear_tf32(_ptr(h), B, N, _ptr(adj_w), _ptr(adj_src), _ptr(weight), _optr(bias),
+                                                     _optr(in_scale), _optr(in_shift), 1 if relu else 0, _ptr(z), _optr(stats),
+                                                     _stream())
+    if rc == -3:  # MTFJSP_E_STATE: this form is not available here (driver without the TMA entry point)
+        return None
+    check(rc, "mtfjsp_enc_aggregate_linear_tf32")
+    return z
 
 
 def head_tf32(x, cand, B, rows_per_env, nodes_per_env, in_scale, in_shift, Wa, bias_env, W1, b1, w2, b2, relu=True):
@@ -492,13 +510,20 @@ class _GraphEncoder:
         rows = B * self.N
         sc = sh = None
         for l in (0, 1):
-            pooled = aggregate(h, adj_w, adj_src, sc, sh, relu=sc is not None).reshape(rows, -1)
             p = "encoder.feature_extract.mlps.%d." % l
-            z, isc, ish = pooled, None, None
+            z = isc = ish = None
             for i in (0, 1, 2):
                 stats = torch.zeros(256, dtype=torch.float64, device=h.device)
-                z = linear_tf32(z, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i], isc, ish,
-                                relu=isc is not None, stats=stats)
+                if i == 0:  # aggregation + first layer: one launch where the size allows it
+                    if l > 0:
+                        z = aggregate_linear_tf32(h, adj_w, adj_src, w[p + "linears.0.weight"], w[p + "linears.0.bias"], sc, sh,
+                                                  relu=True, stats=stats)
+                    if z is None:
+                        pooled = aggregate(h, adj_w, adj_src, sc, sh, relu=sc is not None).reshape(rows, -1)
+                        z = linear_tf32(pooled, w[p + "linears.0.weight"], w[p + "linears.0.bias"], None, None, stats=stats)
+                else:
+                    z = linear_tf32(z, w[p + "linears.%d.weight" % i], w[p + "linears.%d.bias" % i], isc, ish,
+                                    relu=isc is not None, stats=stats)
                 if i < 2:
                     isc, ish = bn_finalize(stats, rows, w[p + "batch_norms.%d.weight" % i], w[p + "batch_norms.%d.bias" % i])
                 else:

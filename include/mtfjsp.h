@@ -254,6 +254,14 @@ int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int row
  * stats[128:256] += column sums of Z^2 (FP64; may be NULL).  4 <= K <= 128, K % 4 == 0. */
 int mtfjsp_enc_linear_tf32(const float* X, int64_t rows, int K, const float* W, const float* bias, const float* in_scale,
                            const float* in_shift, int in_relu, float* Z, double* stats, void* stream);
+/* Neighbourhood aggregation (mtfjsp_enc_aggregate) and the layer that follows it in ONE launch, K = 128, N <= 128:
+ * Z[r] = ( y[r] + w_job[r] y[r-1] + w_mach[r] y[src(r)] ) / n(r) + bias,  y = act(X) W^T,  act as in mtfjsp_enc_linear_tf32.
+ * The aggregation is linear, so it is applied to the product rows in the epilogue (tiles hold whole envs) instead of to
+ * the operand rows in a pass of its own: one read and one write of [B*N,128] less per GIN layer.  stats as above.
+ * Returns MTFJSP_E_STATE when this form is not available (N > 128, no TMA driver entry point): run the two calls. */
+int mtfjsp_enc_aggregate_linear_tf32(const float* X, int64_t B, int N, const float* adj_w, const int16_t* adj_src, const float* W,
+                                     const float* bias, const float* in_scale, const float* in_shift, int in_relu, float* Z,
+                                     double* stats, void* stream);
 /* Weight / bias gradient of that layer for the PPO update's backward pass (ppo_algorithm.py:918-1003; torch autograd
  * runs an FP32 library GEMM there): dW[128,K] = dY^T X, db[128] = column sums of dY (may be NULL), dY [rows,128] and
  * X [rows,K] row-major f32, 4 <= K <= 128, K % 4 == 0.  tcgen05.mma kind::tf32 with the reduction over rows (both

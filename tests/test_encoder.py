@@ -189,6 +189,44 @@ def test_fused_policy_head_matches_the_separate_launches(B, rpe, nodes, affine, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,N,affine", [(5, 36, True), (1000, 36, True), (148 * 3 * 2 + 1, 36, False), (77, 100, True), (40, 128, True),
+                                        (300, 60, False)])
+def test_fused_aggregation_and_layer_match_the_two_kernels(B, N, affine):
+    """mtfjsp_enc_aggregate_linear_tf32 (the weighted neighbourhood mean applied to the product rows in the epilogue,
+    tiles of whole envs) against aggregate -> linear in FP64 (TF32-rounded GEMM operands; the sum is taken after the
+    product, so the comparison carries TF32 rounding of the single rows: 2e-3) and against the two separate kernels."""
+    torch = pytest.importorskip("torch")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + N)
+    H = 128
+    h = torch.randn(B, N, H, device="cuda", generator=g)
+    M = 6 if N == 36 else (10 if N == 100 else 4)   # ops per job: the first op of a job has no job predecessor
+    adj_w = torch.rand(B, N, 2, device="cuda", generator=g) + 0.5
+    adj_w[:, ::M, 0] = 0.0
+    adj_src = torch.randint(-1, N, (B, N), device="cuda", generator=g, dtype=torch.int16)
+    adj_w[..., 1] = torch.where(adj_src >= 0, adj_w[..., 1], torch.zeros_like(adj_w[..., 1]))
+    drop = torch.rand(B, N, device="cuda", generator=g) < 0.3   # some rows without a job predecessor at all
+    adj_w[..., 0] = torch.where(drop, torch.zeros_like(adj_w[..., 0]), adj_w[..., 0])
+    W = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
+    b = torch.randn(H, device="cuda", generator=g)
+    sc = sh = None
+    if affine:
+        sc = torch.rand(H, device="cuda", generator=g) + 0.5
+        sh = torch.randn(H, device="cuda", generator=g) * 0.3
+    stats = torch.zeros(256, dtype=torch.float64, device="cuda")
+    z = enc.aggregate_linear_tf32(h, adj_w, adj_src, W, b, sc, sh, relu=affine, stats=stats)
+    assert z is not None
+    torch.cuda.synchronize()
+    pooled = enc.aggregate(h, adj_w, adj_src, sc, sh, relu=affine).reshape(B * N, H)
+    ref = pooled.double() @ W.double().T + b.double()
+    np.testing.assert_allclose(z.double().cpu().numpy(), ref.cpu().numpy(), rtol=5e-3, atol=5e-3)
+    two = enc.linear_tf32(pooled, W, b)
+    np.testing.assert_allclose(z.cpu().numpy(), two.cpu().numpy(), rtol=5e-3, atol=5e-3)
+    np.testing.assert_allclose(stats[:128].cpu().numpy(), z.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[128:].cpu().numpy(), (z.double() ** 2).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("R", [5, 64, 1000, 64 * 148 * 2 + 17])
 def test_fused_machine_trunk_matches_the_layerwise_path(R):
     """mtfjsp_enc_gat_trunk_tf32 (input projections + three GAT layers + node-set mean, one launch, 64 machines per SM)
