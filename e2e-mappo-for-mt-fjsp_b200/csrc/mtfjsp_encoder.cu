@@ -456,9 +456,75 @@ __global__ void __launch_bounds__(256) tanh_dot_kernel(const float4* __restrict_
     if (lane == 0) out[row] = s + (b ? __ldg(b) : 0.f);
 }
 
+
+// Action selection of the rollout (algorithm/agent_func.py:22-63 select_action / sample_select_action): masked softmax over
+// the <= 32 scores of an env, one draw from it (inverse CDF on a counter-based uniform keyed by (seed, step counter, env))
+// or the arg-max, the log-probability of the drawn entry and, for the job actor, the candidate op behind the drawn job.
+// One warp per env, lane j = entry j.  Replaces masked_fill + softmax + torch.multinomial (eleven validity / draw launches)
+// + gather + log + gather: ~25 launches per actor and step.
+__device__ __forceinline__ uint64_t sel_mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ mask,
+                                                     const int32_t* __restrict__ cand, float scale, int R, long long B, int greedy,
+                                                     uint64_t seed, const int64_t* __restrict__ counter, int stream_id,
+                                                     float* __restrict__ prob, int64_t* __restrict__ action,
+                                                     float* __restrict__ log_a, int64_t* __restrict__ task) {
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const bool in = lane < R;
+    const bool open = in && mask[b * R + lane] == 0;
+    const float sc = open ? scores[b * R + lane] * scale : -INFINITY;
+    float mx = sc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = open ? expf(sc - mx) : 0.f;
+    const float tot = warp_sum(e);
+    const float p = tot > 0.f ? e / tot : 0.f;
+    if (in) prob[b * R + lane] = p;
+    int a;
+    if (greedy) {
+        const unsigned best = __ballot_sync(0xffffffffu, open && sc == mx);  // first entry that attains the maximum
+        a = best ? __ffs(best) - 1 : 0;
+    } else {
+        // inclusive prefix sum of p over the lanes; the drawn entry is the first open one whose prefix exceeds u
+        float c = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, c, o);
+            if (lane >= o) c += t;
+        }
+        const uint64_t r = sel_mix(seed ^ sel_mix((uint64_t)b * 0x100000001B3ULL + (uint64_t)(*counter) * 0x9E3779B1ULL + (uint64_t)stream_id));
+        const float total = __shfl_sync(0xffffffffu, c, 31);
+        const float u = (float)(r >> 40) * (1.0f / 16777216.0f) * total;  // [0, total)
+        const unsigned hit = __ballot_sync(0xffffffffu, open && c > u);
+        const unsigned any = __ballot_sync(0xffffffffu, open);
+        a = hit ? __ffs(hit) - 1 : (any ? 31 - __clz(any) : 0);  // rounding at the top end: the last open entry
+    }
+    const float pa = __shfl_sync(0xffffffffu, p, a);
+    if (lane == 0) {
+        action[b] = a;
+        log_a[b] = logf(pa);
+        if (task) task[b] = cand ? (int64_t)cand[b * R + a] : (int64_t)a;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int mtfjsp_enc_select(const float* scores, const uint8_t* mask, const int32_t* cand, float scale, int R, int64_t B, int greedy,
+                      uint64_t seed, const int64_t* counter, int stream_id, float* prob, int64_t* action, float* log_a,
+                      int64_t* task, void* stream) {
+    if (!scores || !mask || !prob || !action || !log_a || R < 1 || R > 32 || B < 1 || (!greedy && !counter)) return MTFJSP_E_ARG;
+    select_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(scores, mask, cand, scale, R, B, greedy, seed, counter,
+                                                                           stream_id, prob, action, log_a, task);
+    return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+}
 
 int mtfjsp_gae4(const float* r, const float* v, const float* v_next, const float* done, float* adv, double* stats, int T,
                 int64_t B, float gamma, float lam, void* stream) {

@@ -123,6 +123,25 @@ def aggregate_linear_tf32(h, adj_w, adj_src, weight, bias, in_scale=None, in_shi
     return z
 
 
+def select(scores, mask, cand, scale, greedy, rng, stream_id):
+    """mtfjsp_enc_select: masked softmax, one draw (or the arg-max), its log-probability and the candidate behind it in one
+    launch.  scores [B,R] f32, mask [B,R] u8 / bool (1 = excluded), cand [B,R] i32 or None, rng = (seed, counter) with
+    counter a device int64 tensor the caller advances once per step -> prob [B,R], action [B] i64, log_a [B], task [B] i64."""
+    B, R = scores.shape
+    dev = scores.device
+    prob = torch.empty((B, R), dtype=torch.float32, device=dev)
+    action = torch.empty(B, dtype=torch.int64, device=dev)
+    log_a = torch.empty(B, dtype=torch.float32, device=dev)
+    task = torch.empty(B, dtype=torch.int64, device=dev)
+    m8 = mask.reshape(B, R)
+    m8 = (m8 if m8.dtype == torch.uint8 else m8.to(torch.uint8)).contiguous()
+    seed, counter = rng if rng is not None else (0, None)
+    check(_lib.lib().mtfjsp_enc_select(_ptr(scores.contiguous()), _ptr(m8), _optr(cand), float(scale), R, B, 1 if greedy else 0,
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _optr(counter), stream_id, _ptr(prob), _ptr(action),
+                                       _ptr(log_a), _ptr(task), _stream()), "mtfjsp_enc_select")
+    return prob, action, log_a, task
+
+
 def head_tf32(x, cand, B, rows_per_env, nodes_per_env, in_scale, in_shift, Wa, bias_env, W1, b1, w2, b2, relu=True):
     """mtfjsp_enc_head_tf32: a whole policy head (gather, BatchNorm + ReLU of the producing layer, Linear, per-env bias,
     tanh, Linear, tanh, Linear(128, 1)) in one launch -> scores [B, rows_per_env]."""
@@ -649,9 +668,11 @@ class JobActor(_GraphEncoder, _Twin):
         self.precision = precision
         self._pending = None
 
-    def evaluate(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, groups=1, adj_dst=None):
+    def evaluate(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, groups=1, adj_dst=None,
+                 return_logits=False):
         """Action distribution and local values without sampling: prob [B,J], h_g_o_pooled [B,H], job_v [B,2].
-        h_g_m_pooled [B,H] or None (the learned `_input` vector stands in, actor_critic.py:232-240)."""
+        h_g_m_pooled [B,H] or None (the learned `_input` vector stands in, actor_critic.py:232-240).
+        return_logits: the unmasked scores instead of prob (the rollout's one-launch selection masks them itself)."""
         w = self.w
         pooled, nodes = self.encode(task_fea, adj_w, adj_src, groups, adj_dst)
         if self.precision == "tf32":
@@ -667,13 +688,21 @@ class JobActor(_GraphEncoder, _Twin):
             gm = w["_input"][None, None, :].expand_as(cf) if h_g_m_pooled is None else h_g_m_pooled.unsqueeze(-2).expand_as(cf)
             x = torch.cat((cf, pooled.unsqueeze(-2).expand_as(cf), gm), dim=-1)          # actor_critic.py:244-247
             s = _mlp3_tanh(w, "o_policy.", x).squeeze(-1)
+        job_v = (_mlp3_tanh_tf32 if self.precision == "tf32" else _mlp3_tanh)(w, "job_critic.", pooled)
+        if return_logits:
+            return s, pooled, job_v
         s = s.masked_fill(mask_operation.bool(), float("-inf"))                          # actor_critic.py:266-268
         prob = F.softmax(s, dim=-1)
-        job_v = (_mlp3_tanh_tf32 if self.precision == "tf32" else _mlp3_tanh)(w, "job_critic.", pooled)
         return prob, pooled, job_v
 
-    def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None):
-        """-> task_index [B], action_index [B] (job), log_a [B], prob [B,J], h_g_o_pooled [B,H], job_v [B,2]."""
+    def forward(self, task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, greedy=False, generator=None, rng=None):
+        """-> task_index [B], action_index [B] (job), log_a [B], prob [B,J], h_g_o_pooled [B,H], job_v [B,2].
+        rng = (seed, device step counter): sampling by the one-launch selection kernel (`select`) instead of
+        torch.multinomial on `generator`."""
+        if rng is not None and not greedy:
+            s, pooled, job_v = self.evaluate(task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation, return_logits=True)
+            prob, a, log_a, task_index = select(s, mask_operation, candidate.to(torch.int32).contiguous(), 1.0, False, rng, 0)
+            return task_index, a, log_a, prob, pooled, job_v
         prob, pooled, job_v = self.evaluate(task_fea, adj_w, adj_src, candidate, h_g_m_pooled, mask_operation)
         if greedy:                                                                       # agent_func.py greedy / sample
             a = prob.argmax(dim=-1)
@@ -788,7 +817,7 @@ class MachineActor(_MachineTrunk, _Twin):
         _check_precision(precision, hidden)
         self.precision = precision
 
-    def heads(self, nodes, pooled, h_pooled_o, machine_mask):
+    def heads(self, nodes, pooled, h_pooled_o, machine_mask, return_logits=False):
         w = self.w
         B = nodes.shape[0]
         if self.precision == "tf32":
@@ -799,14 +828,17 @@ class MachineActor(_MachineTrunk, _Twin):
         else:
             x = torch.cat((nodes, pooled.unsqueeze(1).expand_as(nodes), h_pooled_o.unsqueeze(1).expand_as(nodes)), dim=-1)
             s = _mlp3_tanh(w, "m_policy.", x).squeeze(-1) * 10
+        machine_v = (_mlp3_tanh_tf32 if self.precision == "tf32" else _mlp3_tanh)(w, "machine_critic.", pooled)
+        if return_logits:
+            return s, machine_v
         s = s.masked_fill(machine_mask.reshape(B, self.M).bool(), float("-inf"))
-        return F.softmax(s, dim=-1), (_mlp3_tanh_tf32 if self.precision == "tf32" else _mlp3_tanh)(w, "machine_critic.", pooled)
+        return F.softmax(s, dim=-1), machine_v
 
-    def forward(self, machine_fea_1, machine_fea_2, h_pooled_o, machine_mask, groups=1):
+    def forward(self, machine_fea_1, machine_fea_2, h_pooled_o, machine_mask, groups=1, return_logits=False):
         """machine_fea_1 [B,M,6], machine_fea_2 [B,M,8] f32, h_pooled_o [B,H], machine_mask [B,M] (1 = infeasible)
         -> mch_prob [B,M], h_pooled [B,H], machine_v [B,2]."""
         nodes, pooled = self.trunk(machine_fea_1, machine_fea_2, groups)
-        prob, machine_v = self.heads(nodes, pooled, h_pooled_o, machine_mask)
+        prob, machine_v = self.heads(nodes, pooled, h_pooled_o, machine_mask, return_logits)
         return prob, pooled, machine_v
 
 

@@ -1,7 +1,8 @@
 """On-device MAPPO rollout controller (reference: Run.py:290-475, algorithm/agent_func.py:22-63).
 
 One rollout step = job actor (GIN encoder + head) -> candidate-machine features -> machine actor (GAT + head) ->
-fused env step + observation.  Everything stays on the GPU: sampling is `torch.multinomial` on the device, the
+fused env step + observation.  Everything stays on the GPU: sampling is one selection kernel per actor (masked softmax,
+counter-based draw, log-probability; `torch.multinomial` with MTFJSP_FUSED_SELECT=0), the
 candidate -> op mapping, masks and rewards never visit the host, so there is no host synchronisation inside an
 episode (the reference crosses the host/device boundary four times per step).  The whole step can be captured in a
 CUDA graph and replayed (`Rollout(..., use_cuda_graph=True)`)."""
@@ -12,6 +13,7 @@ import os
 
 import torch
 
+from .encoder import select as enc_select
 from .env import BatchedMTFJSPEnv, MASK_ESA
 
 # MTFJSP_NVTX=1: NVTX ranges around the phases of a rollout step (job encoder + head, candidate-machine features, machine
@@ -43,6 +45,11 @@ class Rollout:
         self.use_graph = use_cuda_graph
         self._graph = None
         self._warm = 0
+        # sampling by the one-launch selection kernel (encoder.select): counter-based draws keyed by (seed, step counter,
+        # env); the counter lives on the device and is advanced inside the step, so CUDA-graph replays draw fresh numbers
+        self.fused_select = (not greedy) and os.environ.get("MTFJSP_FUSED_SELECT", "1") != "0"
+        self._rng_seed = seed
+        self._rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def _g(self):
         # graph replays draw from torch's default CUDA generator (capture-aware); eager mode uses the private one
@@ -59,22 +66,26 @@ class Rollout:
         env = self.env
         with torch.no_grad():
             h_in = None if first else self.h_mch
+            rng = (self._rng_seed, self._rng_step) if self.fused_select else None
             with nvtx_range("mtfjsp/job_actor"):
                 ti, ai, la, prob, h_o, jv = self.job.forward(env.task_fea, env.adj_w, env.adj_src, env.candidate, h_in,
-                                                             env.job_mask, greedy=self.greedy, generator=self._g())
+                                                             env.job_mask, greedy=self.greedy, generator=self._g(), rng=rng)
                 env.op.copy_(ti.to(torch.int32))
             with nvtx_range("mtfjsp/mfea1"):
                 m1, mmask = env.mfea1(env.op)
             with nvtx_range("mtfjsp/machine_actor"):
-                mp, h_m, mv = self.mch.forward(m1, env.mach_fea, h_o, mmask)
-            if self.greedy:
+                mp, h_m, mv = self.mch.forward(m1, env.mach_fea, h_o, mmask, return_logits=rng is not None)
+            if rng is not None:
+                mp, ma, mla, _ = enc_select(mp, mmask, None, 1.0, False, rng, 1)
+                self._rng_step.add_(1)
+            elif self.greedy:
                 ma = mp.argmax(dim=-1)
             else:
                 ma = torch.multinomial(mp, 1, generator=self._g()).squeeze(-1)
             env.mach.copy_(ma.to(torch.int32))
             self.h_mch.copy_(h_m)
             self.log_a.copy_(la)
-            self.m_log_a.copy_(torch.log(mp.gather(1, ma.unsqueeze(-1)).squeeze(-1)))
+            self.m_log_a.copy_(mla if rng is not None else torch.log(mp.gather(1, ma.unsqueeze(-1)).squeeze(-1)))
             self.job_v.copy_(jv)
             self.mch_v.copy_(mv)
             with nvtx_range("mtfjsp/env_step_obs"):

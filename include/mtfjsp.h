@@ -236,6 +236,14 @@ int mtfjsp_enc_gat_attend_bwd(const float* t, const float* a_src, const float* a
 int mtfjsp_enc_gat_attend_bwd_blocks(int64_t R);
 int mtfjsp_enc_bias_tanh(float* z, const float* bias, int64_t rows, int rows_per_env, int64_t bias_rows, void* stream);
 int mtfjsp_enc_tanh_dot(const float* z, const float* w, const float* b, float* out, int64_t rows, void* stream);
+/* Action selection of a rollout step (algorithm/agent_func.py:22-63): prob [B,R] = softmax over the entries with
+ * mask == 0 of scores * scale (R <= 32), action [B] = a draw from it (counter-based uniform keyed by seed, *counter -- a
+ * device step counter the caller advances, so that CUDA-graph replays draw fresh numbers --, env and stream_id) or the
+ * first arg-max when greedy, log_a [B] = log prob[action], task [B] (may be NULL) = cand[b][action] (cand may be NULL).
+ * Replaces masked_fill + softmax + torch.multinomial + gather + log + gather. */
+int mtfjsp_enc_select(const float* scores, const uint8_t* mask, const int32_t* cand, float scale, int R, int64_t B, int greedy,
+                      uint64_t seed, const int64_t* counter, int stream_id, float* prob, int64_t* action, float* log_a,
+                      int64_t* task, void* stream);
 /* A whole policy head (MLPActor, model/gcn_mlp.py:258-320, on the concatenated features of actor_critic.py:244-268 and
  * :455-470) in one launch, hidden = 128, both products on tcgen05.mma kind::tf32 with the intermediate kept on the SM:
  *   out[r] = tanh( tanh( act(X[src(r)]) Wa^T + bias_env[r / rows_per_env] ) W1^T + b1 ) . w2 + b2,   r < B * rows_per_env

@@ -227,6 +227,45 @@ def test_fused_aggregation_and_layer_match_the_two_kernels(B, N, affine):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R", [6, 10, 30])
+def test_selection_kernel_softmax_draws_and_log_probabilities(R):
+    """mtfjsp_enc_select against torch: prob = masked softmax, greedy = arg-max, log_a = log prob[action], task = the
+    candidate behind the action; draws never pick an excluded entry, follow the distribution (chi-square-like bound on
+    65,536 draws of one distribution) and change when the device step counter advances."""
+    torch = pytest.importorskip("torch")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    g = torch.Generator(device="cuda").manual_seed(R)
+    B = 4099
+    scores = torch.randn(B, R, device="cuda", generator=g) * 2
+    mask = torch.rand(B, R, device="cuda", generator=g) < 0.4
+    mask[:, 0] &= ~mask.all(dim=1)      # at least one open entry per row
+    cand = torch.randint(0, 600, (B, R), device="cuda", generator=g, dtype=torch.int32)
+    ref = torch.softmax((scores * 10.0).masked_fill(mask, float("-inf")), dim=-1)
+    prob, a, la, task = enc.select(scores, mask, cand, 10.0, True, None, 0)
+    np.testing.assert_allclose(prob.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    assert torch.equal(a, ref.argmax(dim=-1))
+    np.testing.assert_allclose(la.cpu().numpy(), torch.log(ref.gather(1, a[:, None])[:, 0]).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(task, cand.long().gather(1, a[:, None])[:, 0])
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    p1, a1, la1, t1 = enc.select(scores, mask, cand, 10.0, False, (7, counter), 0)
+    assert not bool(mask.gather(1, a1[:, None]).any())                     # never an excluded entry
+    np.testing.assert_allclose(la1.cpu().numpy(), torch.log(p1.gather(1, a1[:, None])[:, 0]).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    p1b, a1b, _, _ = enc.select(scores, mask, cand, 10.0, False, (7, counter), 0)
+    assert torch.equal(a1, a1b)                                            # same key, same draw
+    counter.add_(1)
+    _, a2, _, _ = enc.select(scores, mask, cand, 10.0, False, (7, counter), 0)
+    _, a3, _, _ = enc.select(scores, mask, cand, 10.0, False, (7, counter), 1)
+    soft = enc.select(scores, mask, cand, 1.0, False, (7, counter), 0)[1]
+    assert not torch.equal(soft, a2) and not torch.equal(a2, a3)           # step counter, stream id and scale all matter
+    one = torch.randn(1, R, device="cuda", generator=g).expand(65536, R).contiguous()
+    nomask = torch.zeros(65536, R, dtype=torch.bool, device="cuda")
+    pd, ad, _, _ = enc.select(one, nomask, None, 1.0, False, (11, counter), 0)
+    freq = torch.bincount(ad, minlength=R).double() / 65536
+    err = (freq - pd[0].double()).abs() / torch.sqrt(pd[0].double() * (1 - pd[0].double()) / 65536 + 1e-12)
+    assert float(err.max()) < 5.0, (freq, pd[0])                           # within five standard deviations per entry
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("R", [5, 64, 1000, 64 * 148 * 2 + 17])
 def test_fused_machine_trunk_matches_the_layerwise_path(R):
     """mtfjsp_enc_gat_trunk_tf32 (input projections + three GAT layers + node-set mean, one launch, 64 machines per SM)
