@@ -571,8 +571,8 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
                 asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");  // every product row of the tile is in place
                 const int rbase = quad * 32;
                 // this lane's eight rows: weights, predecessor rows and the scale of the mean, once for both column chunks
-                float wj[8], wm[8], half_or_one[8];
-                int prow[8];  // tile row of the machine predecessor | third << 16 | valid << 17
+                float wj[8], wm[8], half_or_one[8], dvs[8];
+                int prow[8];  // tile row of the machine predecessor | valid << 17
 #pragma unroll
                 for (int it = 0; it < 8; it++) {
                     const int tr2 = rbase + it * 4 + sub;
@@ -583,8 +583,9 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
                     wj[it] = w.x;              // 0 without a job predecessor: the row read below is then multiplied away ...
                     wm[it] = hm ? w.y : 0.f;   // ... and row tr2 itself stands in for a missing machine predecessor
                     const int n = 1 + (hj ? 1 : 0) + (hm ? 1 : 0);
-                    half_or_one[it] = n == 2 ? 0.5f : 1.f;
-                    prow[it] = (hm ? sr : tr2) | (n == 3 ? 1 << 16 : 0) | (ok ? 1 << 17 : 0);
+                    half_or_one[it] = n == 3 ? 0.333333343f : n == 2 ? 0.5f : 1.f;  // reciprocal of the member count ...
+                    dvs[it] = (float)n;                                               // ... and the count itself
+                    prow[it] = (hm ? sr : tr2) | (ok ? 1 << 17 : 0);
                 }
 #pragma unroll
                 for (int c2 = 0; c2 < 2; c2++) {
@@ -601,13 +602,12 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
                         float4 v;
                         v.x = fmaf(wm[it], xm.x, fmaf(wj[it], xj.x, xs.x)); v.y = fmaf(wm[it], xm.y, fmaf(wj[it], xj.y, xs.y));
                         v.z = fmaf(wm[it], xm.z, fmaf(wj[it], xj.z, xs.z)); v.w = fmaf(wm[it], xm.w, fmaf(wj[it], xj.w, xs.w));
-                        if (prow[it] & (1 << 16)) {  // / 3, correctly rounded: one residual step on the reciprocal product
-                            const float t = 0.333333343f;
-                            float qx = v.x * t, qy = v.y * t, qz = v.z * t, qw = v.w * t;
-                            v.x = fmaf(fmaf(-3.f, qx, v.x), t, qx); v.y = fmaf(fmaf(-3.f, qy, v.y), t, qy);
-                            v.z = fmaf(fmaf(-3.f, qz, v.z), t, qz); v.w = fmaf(fmaf(-3.f, qw, v.w), t, qw);
-                        } else {
-                            v.x *= half_or_one[it]; v.y *= half_or_one[it]; v.z *= half_or_one[it]; v.w *= half_or_one[it];
+                        {   // mean over the 1, 2 or 3 members; / 3 correctly rounded by one residual step on the reciprocal
+                            // product (the residual is exactly zero for the factors 1 and 0.5: one branch-free sequence)
+                            const float t = half_or_one[it], d = dvs[it];
+                            const float qx = v.x * t, qy = v.y * t, qz = v.z * t, qw = v.w * t;
+                            v.x = fmaf(fmaf(-d, qx, v.x), t, qx); v.y = fmaf(fmaf(-d, qy, v.y), t, qy);
+                            v.z = fmaf(fmaf(-d, qz, v.z), t, qz); v.w = fmaf(fmaf(-d, qw, v.w), t, qw);
                         }
                         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                         if (prow[it] & (1 << 17)) {

@@ -614,7 +614,8 @@ class _Twin:
         bias = w[prefix + "linears.0.bias"]
         for k, e in enumerate(env_terms):
             Wk = self._derived(prefix + "W0%d" % (k + 1), lambda k=k: W0[:, (k + 1) * H:(k + 2) * H])
-            bias = bias + linear_tf32(e.contiguous(), Wk, None)
+            term = linear_tf32(e.contiguous(), Wk, bias if k == 0 else None)  # the layer's own bias rides on the first term
+            bias = term if k == 0 else bias + term
         bias = (bias if bias.dim() == 2 else bias.unsqueeze(0)).contiguous()
         w2 = self._derived(prefix + "w2", lambda: w[prefix + "linears.2.weight"].reshape(-1))
         if cand is not None:  # per_row = the node embeddings [B, nodes, H]; the kernel gathers the candidate rows itself
@@ -789,7 +790,7 @@ class _MachineTrunk:
             buf = gat_trunk_tf32(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"], Wt, a_src, a_dst, stats)
             sc, sh = bn_finalize(stats, R, w["bn.weight"], w["bn.bias"])
             self._pending_m = (sc, sh)
-            return buf.view(B, self.M, H), buf.view(B, self.M, H).mean(dim=1) * sc + sh
+            return buf.view(B, self.M, H), _graph_mean_raw(buf.view(B, self.M, H), sc, sh, relu=False)
         if _FUSED_TRUNK:
             buf = gat_trunk_tf32(f1, f2, w["m_fea_1_fcl.weight"], w["m_fea_2_fcl.weight"], Wt, a_src, a_dst)
         else:
