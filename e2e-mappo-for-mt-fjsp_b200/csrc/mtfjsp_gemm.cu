@@ -1245,6 +1245,185 @@ __global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk_tf32_kernel(
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
 }
 
+
+// Second form of the trunk kernel: 128 machines per tile, the two node sets as TWO products per layer (t1 = h1 W into TMEM
+// columns 0..127, t2 = h2 W into 128..255), so that the thread that owns a machine's TMEM lane holds both of its rows:
+// no exchange of node-2 rows through shared memory, every thread does the same work, half the barriers per machine.
+__global__ void __launch_bounds__(TRUNK_WARPS * 32, 1) gat_trunk2_tf32_kernel(
+    const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ W1p, const float* __restrict__ W2p,
+    const float* __restrict__ Wt, const float* __restrict__ a_src, const float* __restrict__ a_dst, float* __restrict__ out,
+    double* __restrict__ stats, long long R, long long num_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr size_t WBYTES = (size_t)TILE_N * 128 * 4;
+    float* sW = reinterpret_cast<float*>(smem);
+    float* sA1 = reinterpret_cast<float*>(smem + WBYTES);
+    float* sA2 = reinterpret_cast<float*>(smem + 2 * WBYTES);
+    float* s_dot = reinterpret_cast<float*>(smem + 3 * WBYTES);          // [3][4][128]: s1, d1, d2 partials per column group
+    float* s_as = s_dot + 3 * 4 * 128;
+    float* s_ad = s_as + 128;
+    float* s_w1p = s_ad + 128;                                           // [128][6]
+    float* s_w2p = s_w1p + 128 * 6;                                      // [128][8]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w2p + 128 * 8);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 128) { s_as[tid] = a_src[tid]; s_ad[tid] = a_dst[tid]; }
+    for (int i = tid; i < 128 * 6; i += blockDim.x) s_w1p[i] = W1p[i];
+    for (int i = tid; i < 128 * 8; i += blockDim.x) s_w2p[i] = W2p[i];
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    stage_block<false, TRUNK_WARPS>(sW, Wt, 0, TILE_N, 128, 128, 128, nullptr, nullptr, false, warp, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t bar = smem_u32(s_bar);
+
+    const int quad = warp & 3, cg = warp >> 2;   // TMEM lanes 32 quad .., columns 32 cg ..
+    const int mloc = quad * 32 + lane;           // this thread's machine within the tile
+    const size_t arow = (size_t)(mloc >> 3) * 4096 + (cg * 8) * 128 + (mloc & 7) * 16;  // its 32 columns in an A buffer
+    uint32_t phase = 0;
+    double st_sum = 0.0, st_sq = 0.0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long m = tile * 128 + mloc;
+        const bool mok = m < R;
+        {   // input projections on the CUDA cores, straight into the two A operands
+            float fa[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, fb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (mok) {
+                const float2* p2 = reinterpret_cast<const float2*>(f1 + m * 6);
+                const float2 u0 = __ldg(p2), u1 = __ldg(p2 + 1), u2 = __ldg(p2 + 2);
+                fa[0] = u0.x; fa[1] = u0.y; fa[2] = u1.x; fa[3] = u1.y; fa[4] = u2.x; fa[5] = u2.y;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(f2 + m * 8)), v1 = __ldg(reinterpret_cast<const float4*>(f2 + m * 8) + 1);
+                fb[0] = v0.x; fb[1] = v0.y; fb[2] = v0.z; fb[3] = v0.w; fb[4] = v1.x; fb[5] = v1.y; fb[6] = v1.z; fb[7] = v1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float o1[4], o2[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int col = cg * 32 + j * 4 + c;
+                    const float2 wa = *reinterpret_cast<const float2*>(s_w1p + col * 6), wb = *reinterpret_cast<const float2*>(s_w1p + col * 6 + 2),
+                                 wc = *reinterpret_cast<const float2*>(s_w1p + col * 6 + 4);
+                    o1[c] = to_tf32(fmaf(fa[5], wc.y, fmaf(fa[4], wc.x, fmaf(fa[3], wb.y, fmaf(fa[2], wb.x, fmaf(fa[1], wa.y, fa[0] * wa.x))))));
+                    const float4 xa = *reinterpret_cast<const float4*>(s_w2p + col * 8), xb = *reinterpret_cast<const float4*>(s_w2p + col * 8 + 4);
+                    o2[c] = to_tf32(fmaf(fb[7], xb.w, fmaf(fb[6], xb.z, fmaf(fb[5], xb.y, fmaf(fb[4], xb.x,
+                                    fmaf(fb[3], xa.w, fmaf(fb[2], xa.z, fmaf(fb[1], xa.y, fb[0] * xa.x))))))));
+                }
+                *reinterpret_cast<float4*>(reinterpret_cast<char*>(sA1) + arow + j * 128) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<float4*>(reinterpret_cast<char*>(sA2) + arow + j * 128) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            }
+        }
+#pragma unroll 1
+        for (int layer = 0; layer < 3; layer++) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), aW = smem_u32(sW);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    umma_tf32(tmem_base, make_desc(a1 + k * 256, 128, 4096), make_desc(aW + k * 256, 128, 4096), k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    umma_tf32(tmem_base + TILE_N, make_desc(a2 + k * 256, 128, 4096), make_desc(aW + k * 256, 128, 4096), k > 0 ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r1[32], r2[32];
+            TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32), r1);
+            TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TILE_N + cg * 32), r2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float ps = 0.f, pd1 = 0.f, pd2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 va = *reinterpret_cast<const float4*>(s_as + cg * 32 + 4 * j), vd = *reinterpret_cast<const float4*>(s_ad + cg * 32 + 4 * j);
+                const float x0 = __uint_as_float(r1[4 * j]), x1 = __uint_as_float(r1[4 * j + 1]), x2 = __uint_as_float(r1[4 * j + 2]),
+                            x3 = __uint_as_float(r1[4 * j + 3]);
+                const float y0 = __uint_as_float(r2[4 * j]), y1 = __uint_as_float(r2[4 * j + 1]), y2 = __uint_as_float(r2[4 * j + 2]),
+                            y3 = __uint_as_float(r2[4 * j + 3]);
+                ps = fmaf(x3, va.w, fmaf(x2, va.z, fmaf(x1, va.y, fmaf(x0, va.x, ps))));
+                pd1 = fmaf(x3, vd.w, fmaf(x2, vd.z, fmaf(x1, vd.y, fmaf(x0, vd.x, pd1))));
+                pd2 = fmaf(y3, vd.w, fmaf(y2, vd.z, fmaf(y1, vd.y, fmaf(y0, vd.x, pd2))));
+            }
+            s_dot[(0 * 4 + cg) * 128 + mloc] = ps;
+            s_dot[(1 * 4 + cg) * 128 + mloc] = pd1;
+            s_dot[(2 * 4 + cg) * 128 + mloc] = pd2;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            const float s1 = (s_dot[0 * 128 + mloc] + s_dot[1 * 128 + mloc]) + (s_dot[2 * 128 + mloc] + s_dot[3 * 128 + mloc]);
+            const float d1 = (s_dot[4 * 128 + mloc] + s_dot[5 * 128 + mloc]) + (s_dot[6 * 128 + mloc] + s_dot[7 * 128 + mloc]);
+            const float d2 = (s_dot[8 * 128 + mloc] + s_dot[9 * 128 + mloc]) + (s_dot[10 * 128 + mloc] + s_dot[11 * 128 + mloc]);
+            float e11 = s1 + d1, e12 = s1 + d2;
+            e11 = e11 > 0.f ? e11 : 0.2f * e11;
+            e12 = e12 > 0.f ? e12 : 0.2f * e12;
+            const float mx = fmaxf(e11, e12);
+            const float p1 = expf(e11 - mx), p2 = expf(e12 - mx);
+            const float a0 = p1 / (p1 + p2), a1 = p2 / (p1 + p2);
+            if (layer < 2) {  // next layer's operands: elu(h1'), elu(h2') back into the A buffers (the products are done with them)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float4 x, y;
+                    y.x = __uint_as_float(r2[4 * j]); y.y = __uint_as_float(r2[4 * j + 1]); y.z = __uint_as_float(r2[4 * j + 2]); y.w = __uint_as_float(r2[4 * j + 3]);
+                    x.x = a0 * __uint_as_float(r1[4 * j]) + a1 * y.x; x.y = a0 * __uint_as_float(r1[4 * j + 1]) + a1 * y.y;
+                    x.z = a0 * __uint_as_float(r1[4 * j + 2]) + a1 * y.z; x.w = a0 * __uint_as_float(r1[4 * j + 3]) + a1 * y.w;
+                    x.x = to_tf32(elu_fast(x.x)); x.y = to_tf32(elu_fast(x.y)); x.z = to_tf32(elu_fast(x.z)); x.w = to_tf32(elu_fast(x.w));
+                    y.x = to_tf32(elu_fast(y.x)); y.y = to_tf32(elu_fast(y.y)); y.z = to_tf32(elu_fast(y.z)); y.w = to_tf32(elu_fast(y.w));
+                    *reinterpret_cast<float4*>(reinterpret_cast<char*>(sA1) + arow + j * 128) = x;
+                    *reinterpret_cast<float4*>(reinterpret_cast<char*>(sA2) + arow + j * 128) = y;
+                }
+            } else {  // mean over the two node sets, written out; column sums for the BatchNorm that follows
+                float4* op = reinterpret_cast<float4*>(out + m * 128 + cg * 32);
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float y = __uint_as_float(r2[j]);
+                    o[j] = mok ? 0.5f * ((a0 * __uint_as_float(r1[j]) + a1 * y) + y) : 0.f;
+                }
+                if (mok) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+                if (stats) {  // recursive halving over the warp's 32 machines: lane l ends up with column cg * 32 + l
+                    float q[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) q[j] = o[j] * o[j];
+#pragma unroll
+                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < n; j++) {
+                            const float so = up ? o[j] : o[j + n], ko = up ? o[j + n] : o[j];
+                            const float sq = up ? q[j] : q[j + n], kq = up ? q[j + n] : q[j];
+                            o[j] = ko + __shfl_xor_sync(0xffffffffu, so, off);
+                            q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
+                        }
+                    }
+                    st_sum += (double)o[0];
+                    st_sq += (double)q[0];
+                }
+            }
+        }
+        __syncthreads();  // s_dot and the A buffers are rewritten by the next tile
+    }
+    if (stats) {
+        atomicAdd(stats + cg * 32 + lane, st_sum);
+        atomicAdd(stats + 128 + cg * 32 + lane, st_sq);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+}
+
 }  // namespace
 
 template <int KP>
@@ -1405,6 +1584,24 @@ int mtfjsp_enc_head_tf32(const float* X, const int32_t* cand, int64_t B, int row
 int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float* W1p, const float* W2p, const float* Wt,
                               const float* a_src, const float* a_dst, float* out, double* stats, int64_t R, void* stream) {
     if (!fea1 || !fea2 || !W1p || !W2p || !Wt || !a_src || !a_dst || !out || R < 1) return MTFJSP_E_ARG;
+    static const int form = getenv("MTFJSP_TRUNK_FORM") ? atoi(getenv("MTFJSP_TRUNK_FORM")) : 2;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (form == 2) {  // 128 machines per tile, two products per layer
+        const size_t smem2 = 3 * (size_t)TILE_N * 128 * 4 + (3 * 4 * 128 + 256 + 128 * 14) * 4 + 8 + 16;
+        static thread_local bool configured2 = false;
+        if (!configured2) {
+            if (cudaFuncSetAttribute(gat_trunk2_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+                return MTFJSP_E_CUDA;
+            configured2 = true;
+        }
+        const long long tiles2 = (R + 127) / 128;
+        const int grid2 = (int)(tiles2 < sms ? tiles2 : sms);
+        gat_trunk2_tf32_kernel<<<grid2, TRUNK_WARPS * 32, smem2, (cudaStream_t)stream>>>(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, out, stats,
+                                                                                     R, tiles2);
+        return cudaGetLastError() == cudaSuccess ? MTFJSP_OK : MTFJSP_E_CUDA;
+    }
     const size_t smem = 2 * (size_t)TILE_N * 128 * 4 + (64 * 128 + 3 * 4 * 64 + 256 + 128 * 14) * 4 + 8 + 16;
     static thread_local bool configured = false;
     if (!configured) {
@@ -1412,9 +1609,6 @@ int mtfjsp_enc_gat_trunk_tf32(const float* fea1, const float* fea2, const float*
             return MTFJSP_E_CUDA;
         configured = true;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (R + 63) / 64;
     const int grid = (int)(tiles < sms ? tiles : sms);
     gat_trunk_tf32_kernel<<<grid, TRUNK_WARPS * 32, smem, (cudaStream_t)stream>>>(fea1, fea2, W1p, W2p, Wt, a_src, a_dst, out, stats, R,
