@@ -19,6 +19,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/mtfjsp.h"
 
 namespace {
@@ -533,7 +535,10 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
         float* stg = sStg + warp * 32 * STG_W;
         const int quad = warp & 3, half = warp >> 2;
         const int sub = lane >> 3, c4 = lane & 7;
-        double csum[2][4] = {}, csq[2][4] = {};
+        // column sums of this lane's rows over all tiles of the CTA.  AGG keeps them in FP32 (<= ~150 tiles x 8 rows per lane, then FP64
+        // across lanes and CTAs): the 16 registers this frees are what keeps its epilogue off the spill cliff
+        using Acc = typename std::conditional<AGG, float, double>::type;
+        Acc csum[2][4] = {}, csq[2][4] = {};
         const float4 b0 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c4 * 4);
         const float4 b1 = *reinterpret_cast<const float4*>(s_bias + half * 64 + 32 + c4 * 4);
         long long i = 0;
@@ -616,8 +621,8 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
                             q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
                         }
                     }
-                    csum[c2][0] += (double)s.x; csum[c2][1] += (double)s.y; csum[c2][2] += (double)s.z; csum[c2][3] += (double)s.w;
-                    csq[c2][0] += (double)q.x; csq[c2][1] += (double)q.y; csq[c2][2] += (double)q.z; csq[c2][3] += (double)q.w;
+                    csum[c2][0] += (Acc)s.x; csum[c2][1] += (Acc)s.y; csum[c2][2] += (Acc)s.z; csum[c2][3] += (Acc)s.w;
+                    csq[c2][0] += (Acc)q.x; csq[c2][1] += (Acc)q.y; csq[c2][2] += (Acc)q.z; csq[c2][3] += (Acc)q.w;
                 }
                 continue;
             }
@@ -655,8 +660,8 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
                         q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
                     }
                 }
-                csum[c2][0] += (double)s.x; csum[c2][1] += (double)s.y; csum[c2][2] += (double)s.z; csum[c2][3] += (double)s.w;
-                csq[c2][0] += (double)q.x; csq[c2][1] += (double)q.y; csq[c2][2] += (double)q.z; csq[c2][3] += (double)q.w;
+                csum[c2][0] += (Acc)s.x; csum[c2][1] += (Acc)s.y; csum[c2][2] += (Acc)s.z; csum[c2][3] += (Acc)s.w;
+                csq[c2][0] += (Acc)q.x; csq[c2][1] += (Acc)q.y; csq[c2][2] += (Acc)q.z; csq[c2][3] += (Acc)q.w;
                 __syncwarp();
             }
         }
@@ -665,7 +670,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32, 1) linear_tf32_tma_kernel(con
             for (int c2 = 0; c2 < 2; c2++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    double a = csum[c2][j], b = csq[c2][j];
+                    double a = (double)csum[c2][j], b = (double)csq[c2][j];
                     a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
                     b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
                     if (sub == 0) {
