@@ -54,5 +54,37 @@ if what in ("enc", "all"):
     z = torch.randn(R * 6, 128, device="cuda")
     enc.bias_tanh_(z, torch.randn(R, 128, device="cuda"), 6)
     enc.tanh_dot(z, torch.randn(128, device="cuda"), torch.randn(1, device="cuda"))
+    # round-2 kernels: TMA layer (rows >= 4096), aggregation in the epilogue, one-launch head / trunk (both forms), selection
+    rows = 4096 + 77
+    x = torch.randn(rows, 128, device="cuda", generator=g)
+    W = torch.randn(128, 128, device="cuda", generator=g) / 11.3
+    b = torch.randn(128, device="cuda", generator=g)
+    stats = torch.zeros(256, dtype=torch.float64, device="cuda")
+    sc, sh = torch.rand(128, device="cuda") + 0.5, torch.randn(128, device="cuda")
+    enc.linear_tf32(x, W, b)
+    enc.linear_tf32(x, W, b, sc, sh, relu=True, stats=stats)
+    for (Bq, N) in ((130, 36), (41, 100), (9, 128)):
+        h = torch.randn(Bq, N, 128, device="cuda", generator=g)
+        aw = torch.rand(Bq, N, 2, device="cuda", generator=g)
+        aw[:, 0, 0] = 0.0
+        asrc = torch.randint(-1, N, (Bq, N), device="cuda", generator=g, dtype=torch.int16)
+        assert enc.aggregate_linear_tf32(h, aw, asrc, W, b, sc, sh, relu=True, stats=stats) is not None
+    Bq = 300
+    nodes = torch.randn(Bq, 36, 128, device="cuda", generator=g)
+    cand = torch.randint(0, 36, (Bq, 6), device="cuda", generator=g, dtype=torch.int32)
+    bias = torch.randn(Bq, 128, device="cuda", generator=g)
+    enc.head_tf32(nodes, cand, Bq, 6, 36, sc, sh, W, bias, W, b, b, b[:1].contiguous())
+    enc.head_tf32(nodes.reshape(-1, 128)[: Bq * 6].contiguous(), None, Bq, 6, 0, None, None, W, bias[:1].contiguous(), W, b, b,
+                  b[:1].contiguous(), relu=False)
+    for form in ("2", "1"):
+        os.environ["MTFJSP_TRUNK_FORM"] = form  # read once per process: the second value only matters in a fresh process
+        enc.gat_trunk_tf32(torch.randn(777, 6, device="cuda"), torch.randn(777, 8, device="cuda"), torch.randn(128, 6, device="cuda"),
+                           torch.randn(128, 8, device="cuda"), W, b, b, stats)
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for R_ in (6, 20, 32):
+        sco = torch.randn(501, R_, device="cuda", generator=g)
+        msk = torch.rand(501, R_, device="cuda", generator=g) < 0.3
+        enc.select(sco, msk, None, 1.0, False, (3, counter), 0)
+        enc.select(sco, msk, torch.randint(0, 99, (501, R_), device="cuda", dtype=torch.int32), 10.0, True, None, 1)
     torch.cuda.synchronize()
     print("enc ok")

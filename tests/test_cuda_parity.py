@@ -307,6 +307,52 @@ def test_host_step_equals_device_step(pinned, B, kernel_path, monkeypatch):
     eq(pk_env.costs().cpu().numpy(), dev_env.costs().cpu().numpy())
 
 
+@pytest.mark.parametrize("B", [1, 2, 3, 5, 17])
+def test_packed_host_records_tiny_batches(B):
+    """Batches smaller than a warp's four envs (and not a multiple of it): the whole-warp record runs stop at the batch's
+    end, nothing is written behind it."""
+    J, M, E = 6, 6, 2
+    N = J * M
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    d = ins.synthetic_instances(0, B, J, M, E, 13)
+    w = ins.random_weights(0, B, 13)
+    envs = []
+    for _ in range(2):
+        env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)
+        env.load(d["t"], d["p"], d["transT"], d["edge"])
+        env.scaler_init()
+        env.reset(w)
+        envs.append(env)
+    dev_env, pk_env = envs
+    nbytes = int(pk_env.host_buffers()[1].shape[1])
+    pk_act = torch.zeros((B, 2), dtype=torch.int32).pin_memory()
+    guard = torch.full((B + 4, nbytes), 0x5A, dtype=torch.uint8).pin_memory()   # four records of canary behind the batch
+    pk_rec = guard[:B]
+    info6_only = torch.full((B + 2, 6), -9.0, dtype=torch.float64).pin_memory()
+    for s in range(N):
+        op, mach = dev_env.policy_random(seed=4)
+        dev_env.step_obs(op, mach)
+        pk_act[:, 0].copy_(op.cpu()); pk_act[:, 1].copy_(mach.cpu())
+        pk_env.step_host_packed(pk_act, pk_rec)
+        info6, cand, mask = pk_env.decode_records(pk_rec)
+        eq(info6[:, 0], dev_env.reward5[:, 0].cpu().numpy())
+        eq(info6[:, 2:], dev_env.scaled4.cpu().numpy())
+        eq(cand, dev_env.candidate.cpu().numpy())
+        eq(mask, dev_env.job_mask.cpu().numpy())
+        assert bool((guard[B:] == 0x5A).all())
+    assert bool(dev_env.done.all())
+    io_env = envm.BatchedMTFJSPEnv(B, J, M, E, left_shift=True, obs_dtype=torch.float32)
+    io_env.load(d["t"], d["p"], d["transT"], d["edge"])
+    io_env.scaler_init()
+    io_env.reset(w)
+    dev_env.reset(w); dev_env.scaler_reset(); io_env.scaler_reset()
+    op, mach = dev_env.policy_random(seed=6)
+    dev_env.step_obs(op, mach)
+    io_env.step_host(op.cpu().pin_memory(), mach.cpu().pin_memory(), info6_only[:B], None, None)
+    eq(info6_only[:B, 0].numpy(), dev_env.reward5[:, 0].cpu().numpy())
+    assert bool((info6_only[B:] == -9.0).all())
+
+
 @pytest.mark.parametrize("size", [(10, 10, 3), (20, 6, 3), (15, 10, 2), (30, 20, 5), (3, 4, 2), (9, 5, 1)])
 def test_packed_host_records_other_sizes(size):
     """Packed host-step records at sizes with odd record word counts, more than 8 jobs (several mask bytes), the COLD /
