@@ -47,7 +47,8 @@ class Rollout:
         self._warm = 0
         # sampling by the one-launch selection kernel (encoder.select): counter-based draws keyed by (seed, step counter,
         # env); the counter lives on the device and is advanced inside the step, so CUDA-graph replays draw fresh numbers
-        self.fused_select = (not greedy) and os.environ.get("MTFJSP_FUSED_SELECT", "1") != "0"
+        self.fused_select = ((not greedy) and os.environ.get("MTFJSP_FUSED_SELECT", "1") != "0"
+                             and env.J <= 32 and env.M <= 32)  # one warp lane per job / machine
         self._rng_seed = seed
         self._rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
 
