@@ -80,3 +80,45 @@ def test_sampled_rollout_finishes_with_valid_schedules():
     dur = np.take_along_axis(d["t"], st["mach"][:, :, None].astype(np.int64), axis=2)[:, :, 0]
     assert (dur > 0).all()
     np.testing.assert_array_equal(st["ft"], st["st"] + dur)
+
+
+@pytest.mark.parametrize("size", [(10, 10, 3, 96), (20, 6, 3, 64), (30, 20, 5, 8)])
+def test_tf32_actors_at_other_sizes(size):
+    """Both actors on the tcgen05 path at sizes with other tile shapes: N = 100 (aggregation in the layer's epilogue with
+    100-row tiles), N = 120 and N = 600 (separate aggregation kernel: more than 128 nodes), heads with 10 / 20 / 30 rows
+    per env, trunk with 6 / 10 / 20 machines.  First-step distributions against the FP32 actors, then a whole sampled
+    episode under CUDA-graph replay: only valid actions, every env finishes."""
+    J, M, E, B = size
+    envm = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.env")
+    ins = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.instances")
+    ro_mod = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.rollout")
+    enc = importlib.import_module("e2e-mappo-for-mt-fjsp_b200.encoder")
+    d = ins.synthetic_instances(0, B, J, M, E, 77)
+    w = ins.random_weights(0, B, 77)
+    env = envm.BatchedMTFJSPEnv(B, J, M, E, obs_dtype=torch.float32)
+    env.load(d["t"], d["p"], d["transT"], d["edge"])
+    env.scaler_init()
+    env.reset(w)
+    env.obs(1)
+    sdj, sdm = enc.seeded_state_dict(enc.job_actor_keys(128), 21), enc.seeded_state_dict(enc.machine_actor_keys(128), 22)
+    with torch.no_grad():
+        probs = {}
+        for prec in ("fp32", "tf32"):
+            job = enc.JobActor(sdj, J, M, precision=prec)
+            mch = enc.MachineActor(sdm, M, precision=prec)
+            pj, pooled, _ = job.evaluate(env.task_fea, env.adj_w, env.adj_src, env.candidate, None, env.job_mask)
+            op = env.candidate.long().gather(1, pj.argmax(dim=-1, keepdim=True)).squeeze(-1).to(torch.int32)
+            m1, mmask = env.mfea1(op if prec == "fp32" else probs["op"])
+            pm, _, _ = mch.forward(m1, env.mach_fea, pooled, mmask)
+            probs[prec] = (pj, pm)
+            probs.setdefault("op", op)
+    np.testing.assert_allclose(probs["tf32"][0].cpu().numpy(), probs["fp32"][0].cpu().numpy(), rtol=5e-2, atol=5e-3)
+    np.testing.assert_allclose(probs["tf32"][1].cpu().numpy(), probs["fp32"][1].cpu().numpy(), rtol=5e-2, atol=5e-3)
+    ro = ro_mod.Rollout(env, enc.JobActor(sdj, J, M, precision="tf32"), enc.MachineActor(sdm, M, precision="tf32"), greedy=False,
+                        use_cuda_graph=True, seed=5)
+    ro.begin_episode(w)
+    ninv = 0
+    for s in range(env.N):
+        ro.step()
+        ninv += int(env.invalid.sum().item())
+    assert ninv == 0 and int(env.done.sum().item()) == B
