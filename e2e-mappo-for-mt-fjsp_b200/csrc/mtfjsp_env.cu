@@ -734,20 +734,33 @@ struct Spec {
     static constexpr int O_MACH = 0, O_ORD = N, O_RPRED = 2 * N, O_CNT = 3 * N, O_MISC = 3 * N + M, O_NXT = O_MISC + 3;
     static constexpr int O_MIND = 0, O_TT = 2 * N;
     // idle-term scratch: two G-term chunks (at least the three machine rows the policy mode parks there), or all N terms
-    static constexpr int NPT = COLD ? (2 * G > calign(3 * M, 4) ? 2 * G : calign(3 * M, 4)) : calign(N, 4);
+    static constexpr int NPT_CHUNK = 2 * G > calign(3 * M, 4) ? 2 * G : calign(3 * M, 4), NPT_FULL = calign(N, 4);
+    static constexpr int B_SD = SM_SD * 8, B_TT = NOTT ? 0 : TT * 8, B_SI = SI * 2;
+    static constexpr int env_bytes(int npt) {
+        const int raw = calign(B_SD + B_TT + npt * 8 + B_SI, 16);
+        // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
+        return (G_ == 8) ? (raw + ((64 - raw % 128) + 128) % 128) : raw;
+    }
+    // blocks one SM holds by shared memory (228 KB, 1 KB reserved per block) and by threads: handed to ptxas through
+    // __launch_bounds__ so that registers never become the tighter limit
+    static constexpr int minb(int npt) {
+        const int by_smem = 233472 / (WARPS_ * EPW * env_bytes(npt) + 1024), by_threads = 2048 / (WARPS_ * 32);
+        const int b = by_smem < by_threads ? by_smem : by_threads;
+        return b < 32 ? b : 32;
+    }
+    // CHUNK: the idle terms pass through the two-chunk buffer.  Always with COLD; without it wherever the smaller scratch
+    // lets one more block onto an SM (J10M10: 18 -> 19 blocks, 3.07 -> 2.91 waves of 16,384 envs)
+    static constexpr bool CHUNK = COLD_ || minb(NPT_CHUNK) > minb(NPT_FULL);
+    static constexpr int NPT = CHUNK ? NPT_CHUNK : NPT_FULL;
     static_assert(NPT >= 3 * M, "the random-step mode parks three compacted machine rows in the idle-term scratch");
-    static constexpr int B_SD = SM_SD * 8, B_TT = NOTT ? 0 : TT * 8, B_PT = NPT * 8, B_SI = SI * 2;
+    static constexpr int B_PT = NPT * 8;
     static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_SI, 16);
-    // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
-    static constexpr int ENV_BYTES = (G_ == 8) ? (RAW + ((64 - RAW % 128) + 128) % 128) : RAW;
+    static constexpr int ENV_BYTES = env_bytes(NPT);
     static constexpr bool BAR_IN_PAD = ENV_BYTES - RAW >= 8;
     static constexpr int ITER = (N + G - 1) / G;
     static constexpr unsigned GMASK = (G_ == 32) ? 0xffffffffu : ((1u << G_) - 1u);
-    // blocks one SM holds by shared memory (228 KB, 1 KB reserved per block) and by threads: handed to ptxas through
-    // __launch_bounds__ so that registers never become the tighter limit
     static constexpr int SMEM_BLOCK = WARPS_ * EPW * ENV_BYTES;
-    static constexpr int MINB_S = 233472 / (SMEM_BLOCK + 1024), MINB_T = 2048 / (WARPS_ * 32);
-    static constexpr int MINB = MINB_S < MINB_T ? (MINB_S < 32 ? MINB_S : 32) : (MINB_T < 32 ? MINB_T : 32);
+    static constexpr int MINB = minb(NPT);
 };
 
 // bulk async copy global -> shared (TMA, 1-D), completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
@@ -1233,7 +1246,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         const int nsched = nsched0 + (valid ? 1 : 0);
         done = (nsched == N);
         // ---- idle time: sequential sum in (machine, route) order, DGenv_func.py:144-170 ----
-        if constexpr (S::COLD) {
+        if constexpr (S::CHUNK) {
             // terms in (machine, route) order = flat order, G at a time through a two-chunk buffer: chunk i is summed
             // (a chain of dependent additions in the reference's order, on every lane) while chunk i + 1 is being written
             const int nchunk = (__reduce_max_sync(FULL, nsched) + G - 1) / G;
@@ -1287,7 +1300,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             // -0.0), so the slots between this env's term count and the warp's trip count are zero-filled and the loop
             // needs no per-term predicates: two 16-byte loads and four additions per four terms
             const int nmax4 = (__reduce_max_sync(FULL, nsched) + 3) & ~3;
-            static_assert(S::COLD || S::B_PT >= ((N + 3) & ~3) * 8, "the padded idle sum reads whole groups of four terms");
+            static_assert(S::CHUNK || S::B_PT >= ((N + 3) & ~3) * 8, "the padded idle sum reads whole groups of four terms");
             for (int g = nsched + gl; g < nmax4; g += G) s_pt[g] = 0.0;
             __syncwarp();
             const double2* t2 = reinterpret_cast<const double2*>(s_pt);
