@@ -735,32 +735,44 @@ struct Spec {
     static constexpr int O_MIND = 0, O_TT = 2 * N;
     // idle-term scratch: two G-term chunks (at least the three machine rows the policy mode parks there), or all N terms
     static constexpr int NPT_CHUNK = 2 * G > calign(3 * M, 4) ? 2 * G : calign(3 * M, 4), NPT_FULL = calign(N, 4);
-    static constexpr int B_SD = SM_SD * 8, B_TT = NOTT ? 0 : TT * 8, B_SI = SI * 2;
-    static constexpr int env_bytes(int npt) {
-        const int raw = calign(B_SD + B_TT + npt * 8 + B_SI, 16);
+    static constexpr int B_SD = SM_SD * 8, B_SI = SI * 2;
+    static constexpr int env_bytes(int npt, int btt) {
+        const int raw = calign(B_SD + btt + npt * 8 + B_SI, 16);
         // G = 8: two envs share a half-warp; offset them by 16 banks so their 8 x 8-byte rows do not collide
         return (G_ == 8) ? (raw + ((64 - raw % 128) + 128) % 128) : raw;
     }
     // blocks one SM holds by shared memory (228 KB, 1 KB reserved per block) and by threads: handed to ptxas through
     // __launch_bounds__ so that registers never become the tighter limit
-    static constexpr int minb(int npt) {
-        const int by_smem = 233472 / (WARPS_ * EPW * env_bytes(npt) + 1024), by_threads = 2048 / (WARPS_ * 32);
+    static constexpr int minb(int npt, int btt) {
+        const int by_smem = 233472 / (WARPS_ * EPW * env_bytes(npt, btt) + 1024), by_threads = 2048 / (WARPS_ * 32);
         const int b = by_smem < by_threads ? by_smem : by_threads;
         return b < 32 ? b : 32;
     }
+    static constexpr int BTT_FULL = NOTT ? 0 : TT * 8;
+    // TTG (G = 8, compile with -DMTFJSP_SPEC_TTG=1; off): the transport table is read through L1 (prefetched when the block
+    // starts) instead of being staged, together with the two-chunk idle buffer, where that puts one more block on an SM
+    // (J6M6: 6 -> 7 blocks, 4.6 -> 3.95 waves of 65,536 envs).  Measured and rejected: the 72-register cap that seven
+    // 128-thread blocks need spills 64 bytes in the observation modes and the table reads lengthen the step's dependent
+    // chain -- one-launch random step 72.5 us against 64.5, transition alone 49.2 against 44.2 (profiles/README.md, r3w)
+#ifndef MTFJSP_SPEC_TTG
+#define MTFJSP_SPEC_TTG 0
+#endif
+    static constexpr bool TTG = MTFJSP_SPEC_TTG && !NOTT && G_ == 8 && minb(NPT_CHUNK, 0) > minb(NPT_FULL, BTT_FULL) &&
+                                minb(NPT_CHUNK, 0) > minb(NPT_CHUNK, BTT_FULL);
+    static constexpr int B_TT = TTG ? 0 : BTT_FULL;
     // CHUNK: the idle terms pass through the two-chunk buffer.  Always with COLD; without it wherever the smaller scratch
     // lets one more block onto an SM (J10M10: 18 -> 19 blocks, 3.07 -> 2.91 waves of 16,384 envs)
-    static constexpr bool CHUNK = COLD_ || minb(NPT_CHUNK) > minb(NPT_FULL);
+    static constexpr bool CHUNK = COLD_ || TTG || minb(NPT_CHUNK, B_TT) > minb(NPT_FULL, B_TT);
     static constexpr int NPT = CHUNK ? NPT_CHUNK : NPT_FULL;
     static_assert(NPT >= 3 * M, "the random-step mode parks three compacted machine rows in the idle-term scratch");
     static constexpr int B_PT = NPT * 8;
     static constexpr int RAW = calign(B_SD + B_TT + B_PT + B_SI, 16);
-    static constexpr int ENV_BYTES = env_bytes(NPT);
+    static constexpr int ENV_BYTES = env_bytes(NPT, B_TT);
     static constexpr bool BAR_IN_PAD = ENV_BYTES - RAW >= 8;
     static constexpr int ITER = (N + G - 1) / G;
     static constexpr unsigned GMASK = (G_ == 32) ? 0xffffffffu : ((1u << G_) - 1u);
     static constexpr int SMEM_BLOCK = WARPS_ * EPW * ENV_BYTES;
-    static constexpr int MINB = minb(NPT);
+    static constexpr int MINB = minb(NPT, B_TT);
 };
 
 // bulk async copy global -> shared (TMA, 1-D), completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
@@ -918,8 +930,14 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
         } else {
             bulk_g2s(s_sd, g_sd, S::SD * 8, bar);
         }
-        if constexpr (!S::NOTT) bulk_g2s(base + S::B_SD, g_xs + S::O_TT, S::TT * 8, bar);
+        if constexpr (S::B_TT > 0) bulk_g2s(base + S::B_SD, g_xs + S::O_TT, S::TT * 8, bar);
         bulk_g2s(s_si, g_si, S::SI * 2, bar);
+    }
+    if constexpr (S::TTG) {  // the transport table (M * M doubles) into L1: the step reads a few entries of it
+        if (gl < 4) {
+            const int o = gl * 16 < M * M - 1 ? gl * 16 : M * M - 1;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g_xs + S::O_TT + o));
+        }
     }
     double tr = 0.0, pr = 0.0;  // MODE_POLICY, lane k < M: t[op][k], p[op][k]
     int nsel = 1;
@@ -1010,7 +1028,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
     // duration / selected power of op v: shared memory, or (COLD) straight from the state record in HBM.  The stepped
     // op's own values are in registers (d, pa): its HBM words are written by this very launch.
     auto TT = [&](const int i, const int j) -> double {
-        if constexpr (S::NOTT) return __ldg(g_xs + S::O_TT + i * M + j);
+        if constexpr (S::NOTT || S::TTG) return __ldg(g_xs + S::O_TT + i * M + j);
         else return s_tt[i * M + j];
     };
     bool stepped = false;  // set once the action is known to be valid
@@ -1104,8 +1122,8 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
             tt_pa = __shfl_sync(FULL, ttcol, mp);
             ttmm = __shfl_sync(FULL, ttcol, mc);
         } else {
-            tt_pa = s_tt[mp * M + mc];
-            ttmm = s_tt[mc * M + mc];
+            tt_pa = TT(mp, mc);
+            ttmm = TT(mc, mc);
         }
         const double arr_a = first ? 0.0 : s_ft[aprev] + tt_pa;  // DGenv_func.py:46-66
         const int len = s_cnt[mc];
@@ -1137,7 +1155,7 @@ __global__ void __launch_bounds__(S::WARPS * 32, S::MINB) env_kernel_s(const __g
                 mvp = mvp < 0 ? 0 : mvp;
                 double ttv;
                 if constexpr (S::NOTT) ttv = __shfl_sync(FULL, ttcol, mvp);
-                else ttv = s_tt[mvp * M + mc];
+                else ttv = TT(mvp, mc);
                 if (in) {
                     double nst = vfirst ? 0.0 : s_ft[vp] + ttv;
                     bool ok;
