@@ -771,7 +771,6 @@ struct Spec {
     static constexpr bool BAR_IN_PAD = ENV_BYTES - RAW >= 8;
     static constexpr int ITER = (N + G - 1) / G;
     static constexpr unsigned GMASK = (G_ == 32) ? 0xffffffffu : ((1u << G_) - 1u);
-    static constexpr int SMEM_BLOCK = WARPS_ * EPW * ENV_BYTES;
     static constexpr int MINB = minb(NPT, B_TT);
 };
 
